@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the fastACE time-step hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config B of BASELINE.json / SURVEY.md §8d): per GPU 4096 independent economies of
+100 persons + 10 firms, 2 goods, stack 10; synthetic random-init economies
+(CustomScenario distributions) with fixed injected actions (scenario.BENCH_PRESET) and
+std::shuffle visiting orders; 40-step episodes, state restored at episode boundaries.
+A "step" = one Economy::time_step over every economy of every rank (one kernel launch per rank).
+
+Timing: every step is bracketed by CUDA events on the launching stream; between timed steps
+a 512 MiB buffer is written to flush the 126 MB L2 (untimed), so state and actions come from
+HBM.  ms_per_step = sum of event times / K, max over ranks.  `value` = agent-steps of all
+ranks / that time.  `e2e` = the same metric through fastace_env_step_host with pinned HOST
+action buffers (H2D of every action array and D2H of rewards inside the timed region).
+
+--impl reference: the reference's own CPU implementation of the path (oracle/_ref, the
+unmodified sources built by oracle/Makefile; else the C port oracle/liboracle.so) timed on
+the host cores, rank 0 only, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fastace_b200 import _abi, scenario  # noqa: E402
+
+P, F, G, S = 100, 10, 2, 10
+EPISODE = 40
+ECON_PER_GPU = 4096
+# algorithmic bytes of one economy-step (216 B per person-step,
+# 330 B per firm-step at G=2, S=10)
+BYTES_PERSON = (36 + 20 * G + 10 * S) + (24 + 8 * G)
+BYTES_FIRM = (52 + 60 * G + 8 * G * G + 5 * S) + (36 + 20 * G)
+BYTES_PER_ECON_STEP = P * BYTES_PERSON + F * BYTES_FIRM
+METRIC = "agent-steps/sec"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """dram bytes per launch of the step kernel from the committed ncu capture, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_workload(E, seed, episode=EPISODE):
+    dims = (E, P, F, G, S)
+    state, _ = scenario.custom_initial_state(dims, seed)
+    orders = scenario.OrderStream(dims, seed + 1000003)
+    acts = []
+    for t in range(episode):
+        acts.append(scenario.synthetic_actions(dims, seed=0xACE, step=t, perms=orders.next(), **scenario.BENCH_PRESET))
+    return dims, state, acts
+
+
+def cpu_baseline(sample_econ, steps, want_kind=None):
+    """Times the reference CPU path on a bounded sample with all host threads."""
+    from oracle import loader
+    cores = os.cpu_count() or 1
+    dims, state, acts = build_workload(sample_econ, seed=7, episode=min(steps, EPISODE))
+    out = _abi.alloc_host("out", dims, names=("p_reward", "f_profit"))
+    use_ref = loader.have_reference() and want_kind != "port"
+    n = 0
+    if use_ref:
+        dt = 0.0
+        ref = None
+        for t in range(steps):
+            if t % EPISODE == 0:  # fresh economies per episode, built outside the timed region
+                if ref is not None:
+                    ref.close()
+                ref = loader.Reference(dims, state, seed=99)
+            t0 = time.perf_counter()
+            ref.step(acts[t % len(acts)], out, flags=_abi.IDX_MODULO, nthreads=cores, want_perms=False)
+            dt += time.perf_counter() - t0
+            n += 1
+        ref.close()
+        kind = "reference"
+    else:
+        orc = loader.Oracle()
+        dt = 0.0
+        for t in range(steps):
+            if t % EPISODE == 0:
+                st = {k: v.copy() for k, v in state.items()}
+            t0 = time.perf_counter()
+            orc.step(dims, st, acts[t % len(acts)], out, flags=_abi.IDX_MODULO, time_before=t % EPISODE, nthreads=cores)
+            dt += time.perf_counter() - t0
+            n += 1
+        kind = "port"
+    value = sample_econ * (P + F) * n / dt
+    return {"value": value, "unit": METRIC, "cores": cores, "kind": kind,
+            "sample": f"{sample_econ} economies x {n} steps of the bench workload, one economy per thread at a time, "
+                      f"{cores} host threads ({'unmodified reference sources, single-threaded branch per economy' if kind == 'reference' else 'C port of the reference algorithm'})",
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 256
+    total_steps = args.steps + args.warmup
+    base = cpu_baseline(sample, total_steps)
+    ms = base["seconds"] / total_steps * 1e3
+    line = {
+        "metric": METRIC, "value": base["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"config B shape: {sample}-economy sample x (100 persons + 10 firms), 2 goods, stack 10, "
+                               f"fixed injected actions; CPU host cores"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from fastace_b200.env import BatchedEconomy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; fastace_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    E = args.econ
+    # economies shard by index: rank r owns global economies [r*E, (r+1)*E); distinct seeds per rank
+    dims, state, acts = build_workload(E, seed=1 + rank * E)
+    env = BatchedEconomy(dims, device=local)
+    env.set_state(state)
+    dev = torch.device("cuda", local)
+    state0 = {k: v.clone() for k, v in env.device_state_tensors().items()}  # initial state kept on device
+    live = env.device_state_tensors()
+    dacts = [env.pack_device("actions", env.alloc_actions(a)) for a in acts]
+    douts = env.alloc_outputs()
+    dout = env.pack_device("out", douts)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def reset_state(t_env):
+        for k, v in state0.items():
+            live[k].copy_(v)
+        env.set_time(0)  # the native env keeps the economy clock
+
+    def one_step(t):
+        k = t % EPISODE
+        if k == 0:
+            reset_state(t)
+        env.time_step(dacts[k], dout, flags=_abi.IDX_MODULO)
+
+    for t in range(args.warmup):
+        if not args.no_flush:
+            flush.zero_()
+        one_step(t)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = env.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        t = args.warmup + i
+        if t % EPISODE == 0:
+            reset_state(t)
+        if not args.no_flush:
+            flush.zero_()
+        starts[i].record()
+        env.time_step(dacts[t % EPISODE], dout, flags=_abi.IDX_MODULO)
+        stops[i].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    launches = env.launch_count() - launches0
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
+    total_ms = float(step_ms.sum())
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t_ms.item())
+    agent_steps = world * E * (P + F) * args.steps
+    value = agent_steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the host-pointer C ABI call (pinned host buffers) ------------
+    e2e_steps = min(args.steps, EPISODE)
+    pinned = []
+    for a in acts[:e2e_steps]:
+        pa = {}
+        for k, v in a.items():
+            tt = torch.from_numpy(v).pin_memory()
+            pa[k] = tt.numpy()
+        pinned.append((pa, _abi.struct_from_numpy("actions", pa, env.dims)))
+    hout_t = {k: torch.zeros(shp, dtype=torch.float64).pin_memory() for k, (dt, shp) in _abi.shapes("out", env.dims).items()
+              if k in _abi.OUT_MANDATORY}
+    hout = {k: v.numpy() for k, v in hout_t.items()}
+    hout_s = _abi.struct_from_numpy("out", hout, env.dims)
+    h2d = int(sum(v.nbytes for v in acts[0].values()))
+    d2h = int(sum(v.nbytes for v in hout.values()))
+    reset_state(0)
+    torch.cuda.synchronize()
+    for k in range(min(3, e2e_steps)):
+        env.time_step_host(pinned[k][1], hout_s, flags=_abi.IDX_MODULO)
+    reset_state(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0 = time.perf_counter()
+    for k in range(e2e_steps):
+        env.time_step_host(pinned[k][1], hout_s, flags=_abi.IDX_MODULO)  # synchronises internally
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * (P + F) * e2e_steps / float(t_e.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        avg_launch_s = total_ms / args.steps * 1e-3  # rank 0's own launches
+        achieved = BYTES_PER_ECON_STEP * E / avg_launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"config B: {E} economies/GPU x (100 persons + 10 firms), 2 goods, stack 10, 40-step episodes, "
+                            "fixed injected actions (scenario.BENCH_PRESET), std::shuffle visiting orders, IDX_MODULO",
+                "economies_per_gpu": E, "l2": "flushed between timed steps (512 MiB write)" if not args.no_flush else "not flushed",
+                "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
+                "wall_s_including_flushes": wall,
+            },
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(), "peak_source": peak_src,
+                         "kernel": "fastace::step_kernel<2>", "algorithmic_bytes_per_launch": BYTES_PER_ECON_STEP * E},
+        }
+        if world == 1 and not args.no_cpu:
+            base = cpu_baseline(args.cpu_sample, EPISODE)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--econ", type=int, default=ECON_PER_GPU, help="economies per GPU")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (diagnostic)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=256)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+"""ctypes mirror of include/fastace_b200.h.
+
+The reference binds its native library with plain ``ctypes`` over ``extern "C"``
+(/root/reference/py/main.py:10-126); this module does the same for the B200 library.
+It holds only struct layouts and array shape tables — no compute.
+"""
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+FASTACE_OK = 0
+IDX_ABSOLUTE = 0
+IDX_MODULO = 1
+MAX_GOODS = 8
+MAX_STACK = 16
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int32)
+_up = C.POINTER(C.c_uint32)
+_bp = C.POINTER(C.c_uint8)
+
+
+class Dims(C.Structure):
+    _fields_ = [
+        ("num_econ", C.c_int32),
+        ("num_persons", C.c_int32),
+        ("num_firms", C.c_int32),
+        ("num_goods", C.c_int32),
+        ("stack_size", C.c_int32),
+    ]
+
+    @property
+    def tuple(self):
+        return (self.num_econ, self.num_persons, self.num_firms, self.num_goods, self.stack_size)
+
+
+def make_dims(E, P, F, G, S):
+    return Dims(int(E), int(P), int(F), int(G), int(S))
+
+
+# name -> (ctypes pointer type, numpy dtype, shape function of (E,P,F,G,S))
+STATE_FIELDS = [
+    ("p_money", _dp, np.float64, lambda E, P, F, G, S: (E, P)),
+    ("p_inv", _dp, np.float64, lambda E, P, F, G, S: (E, G, P)),
+    ("p_labor", _dp, np.float64, lambda E, P, F, G, S: (E, P)),
+    ("p_util_tfp", _dp, np.float64, lambda E, P, F, G, S: (E, P)),
+    ("p_util_share", _dp, np.float64, lambda E, P, F, G, S: (E, G + 1, P)),
+    ("p_util_rho", _dp, np.float64, lambda E, P, F, G, S: (E, P)),
+    ("f_money", _dp, np.float64, lambda E, P, F, G, S: (E, F)),
+    ("f_inv", _dp, np.float64, lambda E, P, F, G, S: (E, G, F)),
+    ("f_labor", _dp, np.float64, lambda E, P, F, G, S: (E, F)),
+    ("f_last_money", _dp, np.float64, lambda E, P, F, G, S: (E, F)),
+    ("f_prod_tfp", _dp, np.float64, lambda E, P, F, G, S: (E, G, F)),
+    ("f_prod_share", _dp, np.float64, lambda E, P, F, G, S: (E, G, G + 1, F)),
+    ("f_prod_rho", _dp, np.float64, lambda E, P, F, G, S: (E, G, F)),
+    ("m_count", _ip, np.int32, lambda E, P, F, G, S: (E,)),
+    ("m_owner", _ip, np.int32, lambda E, P, F, G, S: (E, F * G)),
+    ("m_good", _ip, np.int32, lambda E, P, F, G, S: (E, F * G)),
+    ("m_left", _up, np.uint32, lambda E, P, F, G, S: (E, F * G)),
+    ("m_taken", _up, np.uint32, lambda E, P, F, G, S: (E, F * G)),
+    ("m_price", _dp, np.float64, lambda E, P, F, G, S: (E, F * G)),
+    ("j_count", _ip, np.int32, lambda E, P, F, G, S: (E,)),
+    ("j_owner", _ip, np.int32, lambda E, P, F, G, S: (E, F)),
+    ("j_left", _up, np.uint32, lambda E, P, F, G, S: (E, F)),
+    ("j_taken", _up, np.uint32, lambda E, P, F, G, S: (E, F)),
+    ("j_wage", _dp, np.float64, lambda E, P, F, G, S: (E, F)),
+]
+
+ACTION_FIELDS = [
+    ("perm_person", _ip, np.int32, lambda E, P, F, G, S: (E, P)),
+    ("perm_firm", _ip, np.int32, lambda E, P, F, G, S: (E, F)),
+    ("p_job_idx", _ip, np.int32, lambda E, P, F, G, S: (E, S, P)),
+    ("p_job_take", _bp, np.uint8, lambda E, P, F, G, S: (E, S, P)),
+    ("p_good_idx", _ip, np.int32, lambda E, P, F, G, S: (E, S, P)),
+    ("p_good_take", _bp, np.uint8, lambda E, P, F, G, S: (E, S, P)),
+    ("p_consume", _fp, np.float32, lambda E, P, F, G, S: (E, G, P)),
+    ("f_good_idx", _ip, np.int32, lambda E, P, F, G, S: (E, S, F)),
+    ("f_good_take", _bp, np.uint8, lambda E, P, F, G, S: (E, S, F)),
+    ("f_prod", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
+    ("f_offer_amt", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
+    ("f_offer_price", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
+    ("f_job_labor", _fp, np.float32, lambda E, P, F, G, S: (E, F)),
+    ("f_job_wage", _fp, np.float32, lambda E, P, F, G, S: (E, F)),
+]
+
+OUT_FIELDS = [
+    ("p_reward", _dp, np.float64, lambda E, P, F, G, S: (E, P)),
+    ("f_profit", _dp, np.float64, lambda E, P, F, G, S: (E, F)),
+    ("p_job_ok", _bp, np.uint8, lambda E, P, F, G, S: (E, S, P)),
+    ("p_good_ok", _bp, np.uint8, lambda E, P, F, G, S: (E, S, P)),
+    ("f_good_ok", _bp, np.uint8, lambda E, P, F, G, S: (E, S, F)),
+    ("old_m_left", _up, np.uint32, lambda E, P, F, G, S: (E, F * G)),
+    ("old_m_taken", _up, np.uint32, lambda E, P, F, G, S: (E, F * G)),
+    ("old_j_left", _up, np.uint32, lambda E, P, F, G, S: (E, F)),
+    ("old_j_taken", _up, np.uint32, lambda E, P, F, G, S: (E, F)),
+]
+OUT_MANDATORY = ("p_reward", "f_profit")
+
+
+class State(C.Structure):
+    _fields_ = [(n, t) for n, t, _, _ in STATE_FIELDS]
+
+
+class Actions(C.Structure):
+    _fields_ = [(n, t) for n, t, _, _ in ACTION_FIELDS]
+
+
+class StepOut(C.Structure):
+    _fields_ = [(n, t) for n, t, _, _ in OUT_FIELDS]
+
+
+class CustomScenarioParams(C.Structure):
+    """neural::CustomScenarioParams, /root/reference/src/neural/neuralScenarios.h:49-115
+    (ctypes mirror as in /root/reference/py/main.py:12-60)."""
+
+    _fields_ = [("numPeople", C.c_uint), ("numFirms", C.c_uint)] + [
+        (n, C.c_double)
+        for n in (
+            "money_mu money_sigma good1_mu good1_sigma good2_mu good2_sigma "
+            "labor_share_mu labor_share_sigma good1_share_mu good1_share_sigma good2_share_mu good2_share_sigma "
+            "discount_mu discount_sigma elasticity_mu elasticity_sigma "
+            "firm_money_mu firm_money_sigma firm_good1_mu firm_good1_sigma firm_good2_mu firm_good2_sigma "
+            "firm_tfp1_mu firm_tfp1_sigma firm_tfp2_mu firm_tfp2_sigma "
+            "firm_labor_share1_mu firm_labor_share1_sigma firm_good1_share1_mu firm_good1_share1_sigma "
+            "firm_good2_share1_mu firm_good2_share1_sigma "
+            "firm_labor_share2_mu firm_labor_share2_sigma firm_good1_share2_mu firm_good1_share2_sigma "
+            "firm_good2_share2_mu firm_good2_share2_sigma "
+            "firm_elasticity1_mu firm_elasticity1_sigma firm_elasticity2_mu firm_elasticity2_sigma"
+        ).split()
+    ]
+
+
+class TrainingParams(C.Structure):
+    """neural::TrainingParams, /root/reference/src/neural/neuralScenarios.h:148-186
+    (ctypes mirror as in /root/reference/py/main.py:63-85)."""
+
+    _fields_ = (
+        [(n, C.c_uint) for n in "numEpisodes episodeLength updateEveryNEpisodes checkpointEveryNEpisodes "
+                                "stackSize encodingSize hiddenSize nHidden nHiddenSmall".split()]
+        + [(n, C.c_double) for n in "purchaseNetLR firmPurchaseNetLR laborSearchNetLR consumptionNetLR "
+                                    "productionNetLR offerNetLR jobOfferNetLR valueNetLR firmValueNetLR".split()]
+        + [("episodeBatchSizeForLRDecay", C.c_uint), ("patienceForLRDecay", C.c_uint),
+           ("multiplierForLRDecay", C.c_double), ("reverseAnnealingPeriod", C.c_uint)]
+    )
+
+
+def field_table(kind):
+    return {"state": STATE_FIELDS, "actions": ACTION_FIELDS, "out": OUT_FIELDS}[kind]
+
+
+def shapes(kind, dims):
+    """{name: (numpy dtype, shape)} for a Dims/tuple (E,P,F,G,S)."""
+    t = dims.tuple if isinstance(dims, Dims) else tuple(dims)
+    return {n: (dt, fn(*t)) for n, _, dt, fn in field_table(kind)}
+
+
+def alloc_host(kind, dims, names=None):
+    """dict of zero-filled C-contiguous numpy arrays for the given struct."""
+    out = {}
+    for n, (dt, shp) in shapes(kind, dims).items():
+        if names is None or n in names:
+            out[n] = np.zeros(shp, dtype=dt)
+    return out
+
+
+def struct_from_numpy(kind, arrays, dims=None):
+    """Build the ctypes struct from a dict of numpy arrays (missing names -> NULL).
+    Arrays must be C-contiguous with the exact dtype; shapes are checked when dims given."""
+    cls = {"state": State, "actions": Actions, "out": StepOut}[kind]
+    s = cls()
+    shp = shapes(kind, dims) if dims is not None else None
+    for n, ptr_t, dt, _ in field_table(kind):
+        a = arrays.get(n)
+        if a is None:
+            continue
+        if not isinstance(a, np.ndarray) or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"{n}: need C-contiguous numpy array of dtype {np.dtype(dt)}")
+        if shp is not None and tuple(a.shape) != tuple(shp[n][1]):
+            raise ValueError(f"{n}: shape {a.shape} != expected {shp[n][1]}")
+        setattr(s, n, a.ctypes.data_as(ptr_t))
+    s._keepalive = arrays  # keep the buffers alive as long as the struct
+    return s
+
+
+def struct_from_pointers(kind, ptrs):
+    """Build the ctypes struct from a dict name -> integer address (device pointers)."""
+    cls = {"state": State, "actions": Actions, "out": StepOut}[kind]
+    s = cls()
+    for n, ptr_t, _, _ in field_table(kind):
+        p = ptrs.get(n)
+        if p:
+            setattr(s, n, C.cast(C.c_void_p(int(p)), ptr_t))
+    return s

@@ -1,0 +1,335 @@
+// C ABI of libfastace_b200.so: env lifetime, state I/O and the step launchers.
+// Declarations and the reference interfaces each entry point replaces: include/fastace_b200.h.
+// There is NO CPU fallback anywhere in this file: without a CUDA device every env call fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fastace_b200.h"
+#include "fastace_internal.h"
+#include "step_kernel.cuh"
+
+namespace fastace {
+
+struct FieldDesc {
+    size_t offset;   // offset of the pointer member inside its struct
+    size_t elem;     // element size in bytes
+    size_t count;    // elements for the env's dims
+};
+
+static std::vector<FieldDesc> state_fields(const fastace_dims_t& d) {
+    const size_t E = d.num_econ, P = d.num_persons, F = d.num_firms, G = d.num_goods;
+    const size_t cap = F * G;
+    return {
+        {offsetof(fastace_state_t, p_money), 8, E * P},
+        {offsetof(fastace_state_t, p_inv), 8, E * G * P},
+        {offsetof(fastace_state_t, p_labor), 8, E * P},
+        {offsetof(fastace_state_t, p_util_tfp), 8, E * P},
+        {offsetof(fastace_state_t, p_util_share), 8, E * (G + 1) * P},
+        {offsetof(fastace_state_t, p_util_rho), 8, E * P},
+        {offsetof(fastace_state_t, f_money), 8, E * F},
+        {offsetof(fastace_state_t, f_inv), 8, E * G * F},
+        {offsetof(fastace_state_t, f_labor), 8, E * F},
+        {offsetof(fastace_state_t, f_last_money), 8, E * F},
+        {offsetof(fastace_state_t, f_prod_tfp), 8, E * G * F},
+        {offsetof(fastace_state_t, f_prod_share), 8, E * G * (G + 1) * F},
+        {offsetof(fastace_state_t, f_prod_rho), 8, E * G * F},
+        {offsetof(fastace_state_t, m_count), 4, E},
+        {offsetof(fastace_state_t, m_owner), 4, E * cap},
+        {offsetof(fastace_state_t, m_good), 4, E * cap},
+        {offsetof(fastace_state_t, m_left), 4, E * cap},
+        {offsetof(fastace_state_t, m_taken), 4, E * cap},
+        {offsetof(fastace_state_t, m_price), 8, E * cap},
+        {offsetof(fastace_state_t, j_count), 4, E},
+        {offsetof(fastace_state_t, j_owner), 4, E * F},
+        {offsetof(fastace_state_t, j_left), 4, E * F},
+        {offsetof(fastace_state_t, j_taken), 4, E * F},
+        {offsetof(fastace_state_t, j_wage), 8, E * F},
+    };
+}
+
+static std::vector<FieldDesc> action_fields(const fastace_dims_t& d) {
+    const size_t E = d.num_econ, P = d.num_persons, F = d.num_firms, G = d.num_goods, S = d.stack_size;
+    return {
+        {offsetof(fastace_actions_t, perm_person), 4, E * P},
+        {offsetof(fastace_actions_t, perm_firm), 4, E * F},
+        {offsetof(fastace_actions_t, p_job_idx), 4, E * S * P},
+        {offsetof(fastace_actions_t, p_job_take), 1, E * S * P},
+        {offsetof(fastace_actions_t, p_good_idx), 4, E * S * P},
+        {offsetof(fastace_actions_t, p_good_take), 1, E * S * P},
+        {offsetof(fastace_actions_t, p_consume), 4, E * G * P},
+        {offsetof(fastace_actions_t, f_good_idx), 4, E * S * F},
+        {offsetof(fastace_actions_t, f_good_take), 1, E * S * F},
+        {offsetof(fastace_actions_t, f_prod), 4, E * G * F},
+        {offsetof(fastace_actions_t, f_offer_amt), 4, E * G * F},
+        {offsetof(fastace_actions_t, f_offer_price), 4, E * G * F},
+        {offsetof(fastace_actions_t, f_job_labor), 4, E * F},
+        {offsetof(fastace_actions_t, f_job_wage), 4, E * F},
+    };
+}
+
+static std::vector<FieldDesc> out_fields(const fastace_dims_t& d) {
+    const size_t E = d.num_econ, P = d.num_persons, F = d.num_firms, G = d.num_goods, S = d.stack_size;
+    const size_t cap = F * G;
+    return {
+        {offsetof(fastace_step_out_t, p_reward), 8, E * P},
+        {offsetof(fastace_step_out_t, f_profit), 8, E * F},
+        {offsetof(fastace_step_out_t, p_job_ok), 1, E * S * P},
+        {offsetof(fastace_step_out_t, p_good_ok), 1, E * S * P},
+        {offsetof(fastace_step_out_t, f_good_ok), 1, E * S * F},
+        {offsetof(fastace_step_out_t, old_m_left), 4, E * cap},
+        {offsetof(fastace_step_out_t, old_m_taken), 4, E * cap},
+        {offsetof(fastace_step_out_t, old_j_left), 4, E * F},
+        {offsetof(fastace_step_out_t, old_j_taken), 4, E * F},
+    };
+}
+
+template <typename T>
+static inline void*& member(T* s, size_t off) { return *reinterpret_cast<void**>(reinterpret_cast<char*>(s) + off); }
+template <typename T>
+static inline void* member(const T* s, size_t off) { return *reinterpret_cast<void* const*>(reinterpret_cast<const char*>(s) + off); }
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace fastace
+
+struct fastace_env {
+    fastace_dims_t dims;
+    int device;
+    uint32_t time;
+    uint64_t launches;
+    void* state_block;      // one allocation holding every state array
+    fastace_state_t dstate; // device pointers into state_block
+    // staging for fastace_env_step_host
+    void* act_block;
+    fastace_actions_t dact;
+    void* out_block;
+    fastace_step_out_t dout;
+    cudaStream_t stream;
+    size_t smem_bytes;
+};
+
+#define FASTACE_CUDA_CHECK(expr)                                                              \
+    do {                                                                                      \
+        cudaError_t _err = (expr);                                                            \
+        if (_err != cudaSuccess) {                                                            \
+            fastace::set_error(std::string(#expr) + ": " + cudaGetErrorString(_err));         \
+            return FASTACE_ERR_CUDA;                                                          \
+        }                                                                                     \
+    } while (0)
+
+using namespace fastace;
+
+template <typename StructT>
+static int carve(const std::vector<FieldDesc>& fields, StructT* s, void** block, bool zero) {
+    size_t total = 0;
+    for (auto& f : fields) total += align_up(f.elem * (f.count ? f.count : 1), 256);
+    FASTACE_CUDA_CHECK(cudaMalloc(block, total));
+    if (zero) FASTACE_CUDA_CHECK(cudaMemset(*block, 0, total));
+    size_t off = 0;
+    for (auto& f : fields) {
+        member(s, f.offset) = static_cast<char*>(*block) + off;
+        off += align_up(f.elem * (f.count ? f.count : 1), 256);
+    }
+    return FASTACE_OK;
+}
+
+typedef void (*kernel_fn)(const StepParams);
+static kernel_fn kernel_for_goods(int G) {
+    switch (G) {
+        case 1: return step_kernel<1>;
+        case 2: return step_kernel<2>;
+        case 3: return step_kernel<3>;
+        case 4: return step_kernel<4>;
+        case 5: return step_kernel<5>;
+        case 6: return step_kernel<6>;
+        case 7: return step_kernel<7>;
+        case 8: return step_kernel<8>;
+        default: return nullptr;
+    }
+}
+
+extern "C" {
+
+int fastace_device_count(void) {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess) {
+        set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(err));
+        return FASTACE_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** out_env) {
+    if (!dims || !out_env) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    *out_env = nullptr;
+    const fastace_dims_t d = *dims;
+    if (d.num_econ < 1 || d.num_persons < 0 || d.num_firms < 1 || d.num_goods < 1 ||
+        d.num_goods > FASTACE_MAX_GOODS || d.stack_size < 0 || d.stack_size > FASTACE_MAX_STACK) {
+        set_error("unsupported dims: need E>=1, F>=1, 1<=G<=8, 0<=S<=16");
+        return FASTACE_ERR_INVALID;
+    }
+    if (d.num_firms * d.num_goods > 254 || d.num_persons > 65535) {
+        set_error("warp-per-economy kernel needs F*G <= 254 and P <= 65535");
+        return FASTACE_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        set_error("no CUDA device visible: fastace_b200 has no CPU path");
+        return FASTACE_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { set_error("bad device index"); return FASTACE_ERR_INVALID; }
+    FASTACE_CUDA_CHECK(cudaSetDevice(device));
+
+    const SmemLayout L = make_layout(d.num_persons, d.num_firms, d.num_goods, d.stack_size);
+    int max_optin = 0;
+    FASTACE_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (L.total > max_optin) {
+        set_error("economy too large for the warp-per-economy kernel's shared-memory books");
+        return FASTACE_ERR_INVALID;
+    }
+    kernel_fn k = kernel_for_goods(d.num_goods);
+    if (L.total > 48 * 1024)
+        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+
+    fastace_env* env = new (std::nothrow) fastace_env();
+    if (!env) { set_error("out of host memory"); return FASTACE_ERR_ALLOC; }
+    std::memset(env, 0, sizeof(*env));
+    env->dims = d;
+    env->device = device;
+    env->smem_bytes = (size_t)L.total;
+    int rc = carve(state_fields(d), &env->dstate, &env->state_block, true);
+    if (rc != FASTACE_OK) { delete env; return rc; }
+    cudaError_t err = cudaStreamCreateWithFlags(&env->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) { set_error(cudaGetErrorString(err)); cudaFree(env->state_block); delete env; return FASTACE_ERR_CUDA; }
+    *out_env = env;
+    return FASTACE_OK;
+}
+
+int fastace_env_destroy(fastace_env_t* env) {
+    if (!env) return FASTACE_OK;
+    cudaSetDevice(env->device);
+    if (env->stream) cudaStreamDestroy(env->stream);
+    if (env->state_block) cudaFree(env->state_block);
+    if (env->act_block) cudaFree(env->act_block);
+    if (env->out_block) cudaFree(env->out_block);
+    delete env;
+    return FASTACE_OK;
+}
+
+int fastace_env_dims(const fastace_env_t* env, fastace_dims_t* out_dims) {
+    if (!env || !out_dims) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    *out_dims = env->dims;
+    return FASTACE_OK;
+}
+
+int fastace_env_time(const fastace_env_t* env, uint32_t* out_time) {
+    if (!env || !out_time) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    *out_time = env->time;
+    return FASTACE_OK;
+}
+
+int fastace_env_set_state(fastace_env_t* env, const fastace_state_t* host_state, uint32_t time) {
+    if (!env || !host_state) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+    for (auto& f : state_fields(env->dims)) {
+        const void* src = member(host_state, f.offset);
+        if (!src || f.count == 0) continue;
+        FASTACE_CUDA_CHECK(cudaMemcpy(member(&env->dstate, f.offset), src, f.elem * f.count, cudaMemcpyHostToDevice));
+    }
+    env->time = time;
+    return FASTACE_OK;
+}
+
+int fastace_env_get_state(const fastace_env_t* env, fastace_state_t* host_state) {
+    if (!env || !host_state) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+    FASTACE_CUDA_CHECK(cudaDeviceSynchronize());
+    for (auto& f : state_fields(env->dims)) {
+        void* dst = member(host_state, f.offset);
+        if (!dst || f.count == 0) continue;
+        FASTACE_CUDA_CHECK(cudaMemcpy(dst, member(&env->dstate, f.offset), f.elem * f.count, cudaMemcpyDeviceToHost));
+    }
+    return FASTACE_OK;
+}
+
+int fastace_env_device_state(const fastace_env_t* env, fastace_state_t* out_device_state) {
+    if (!env || !out_device_state) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    *out_device_state = env->dstate;
+    return FASTACE_OK;
+}
+
+static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const fastace_step_out_t* dout,
+                       uint32_t flags, cudaStream_t stream) {
+    for (auto& f : action_fields(env->dims)) {
+        if (f.count && !member(dact, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
+    }
+    if (!dout->p_reward || !dout->f_profit) { set_error("out: p_reward and f_profit are mandatory"); return FASTACE_ERR_INVALID; }
+    StepParams sp;
+    sp.E = env->dims.num_econ; sp.P = env->dims.num_persons; sp.F = env->dims.num_firms; sp.S = env->dims.stack_size;
+    sp.flags = flags;
+    sp.time_before = env->time;
+    sp.st = env->dstate;
+    sp.ac = *dact;
+    sp.out = *dout;
+    kernel_fn k = kernel_for_goods(env->dims.num_goods);
+    k<<<sp.E, 32, env->smem_bytes, stream>>>(sp);
+    FASTACE_CUDA_CHECK(cudaGetLastError());
+    env->time += 1;
+    env->launches += 1;
+    return FASTACE_OK;
+}
+
+int fastace_env_step_device(fastace_env_t* env, const fastace_actions_t* actions, const fastace_step_out_t* out,
+                            uint32_t flags, void* cuda_stream) {
+    if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+    return launch_step(env, actions, out, flags, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int fastace_env_step_host(fastace_env_t* env, const fastace_actions_t* actions, const fastace_step_out_t* out,
+                          uint32_t flags) {
+    if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+    if (!env->act_block) {
+        int rc = carve(action_fields(env->dims), &env->dact, &env->act_block, false);
+        if (rc != FASTACE_OK) return rc;
+        rc = carve(out_fields(env->dims), &env->dout, &env->out_block, false);
+        if (rc != FASTACE_OK) return rc;
+    }
+    for (auto& f : action_fields(env->dims)) {
+        const void* src = member(actions, f.offset);
+        if (!src && f.count) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
+        if (f.count)
+            FASTACE_CUDA_CHECK(cudaMemcpyAsync(member(&env->dact, f.offset), src, f.elem * f.count,
+                                               cudaMemcpyHostToDevice, env->stream));
+    }
+    fastace_step_out_t dout;
+    std::memset(&dout, 0, sizeof(dout));
+    for (auto& f : out_fields(env->dims))
+        if (member(out, f.offset)) member(&dout, f.offset) = member(&env->dout, f.offset);
+    int rc = launch_step(env, &env->dact, &dout, flags, env->stream);
+    if (rc != FASTACE_OK) return rc;
+    for (auto& f : out_fields(env->dims)) {
+        void* dst = member(out, f.offset);
+        if (dst && f.count)
+            FASTACE_CUDA_CHECK(cudaMemcpyAsync(dst, member(&env->dout, f.offset), f.elem * f.count,
+                                               cudaMemcpyDeviceToHost, env->stream));
+    }
+    FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->stream));
+    return FASTACE_OK;
+}
+
+int fastace_env_launch_count(const fastace_env_t* env, uint64_t* out_count) {
+    if (!env || !out_count) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    *out_count = env->launches;
+    return FASTACE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,277 @@
+/*
+ * fastace_b200.h — C ABI of the B200-native batched environment for fastACE's
+ * Economy::time_step hot path.
+ *
+ * Drop-in boundary.  The reference reaches this path in two ways:
+ *   (1) C++ callers: Economy::time_step()            /root/reference/src/base/economy.cpp:95-139
+ *       with behaviour supplied through the plugin interfaces
+ *       PersonDecisionMaker                          src/persons/utilMaxer.h:11-28
+ *       FirmDecisionMaker                            src/firms/profitMaxer.h:11-24
+ *   (2) Python callers: ctypes over `extern "C"`     src/pybindings.h:8-28, py/main.py:10-126
+ * The reference's FFI is plain `extern "C"` + ctypes, so this library is bound the same
+ * way: plain pointers and sizes, no C++ or torch types in any signature.
+ *
+ * One `fastace_env_t` holds E independent economies as structure-of-arrays device
+ * buffers.  One call to fastace_env_step_* advances every economy by exactly one
+ * Economy::time_step().  The seven plugin decisions (utilMaxer.h:17-23,
+ * profitMaxer.h:13-16) are supplied for all agents at once as action arrays
+ * (fastace_actions_t) — this replaces the per-agent synchronous plugin callbacks; the
+ * decode rules of the shipped plugins (src/neural/neuralFirmDecisionMaker.cpp:111-180,
+ * neuralPersonDecisionMaker.cpp:93-111) are applied on the device.
+ *
+ * Array layout convention: the agent (or market slot) index is always the FASTEST
+ * dimension inside an economy, the economy index the slowest:  [E][...][agent].
+ * All pointers of one struct are either all host or all device pointers, as stated
+ * by the function that takes them.
+ *
+ * Error convention: every function returns 0 (FASTACE_OK) or a negative
+ * fastace_status_t; fastace_last_error() returns a thread-local message.  (The
+ * reference has no error codes — `bool` "did not act" returns, economy.cpp:97-106 —
+ * and agents that are always in sync here, so that condition cannot arise.)
+ */
+#ifndef FASTACE_B200_H
+#define FASTACE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FASTACE_ABI_VERSION 1
+
+typedef enum fastace_status {
+    FASTACE_OK = 0,
+    FASTACE_ERR_INVALID = -1,   /* bad argument / unsupported dimension */
+    FASTACE_ERR_CUDA = -2,      /* CUDA runtime error (message in fastace_last_error) */
+    FASTACE_ERR_NO_DEVICE = -3, /* no CUDA device: there is NO CPU fallback */
+    FASTACE_ERR_ALLOC = -4
+} fastace_status_t;
+
+/* Limits of the warp-per-economy kernel (one economy = one warp, books in shared memory). */
+#define FASTACE_MAX_GOODS 8
+#define FASTACE_MAX_STACK 16
+
+typedef struct fastace_dims {
+    int32_t num_econ;    /* E  independent economies in this env (this rank's shard)      */
+    int32_t num_persons; /* P  persons per economy                                         */
+    int32_t num_firms;   /* F  firms per economy                                           */
+    int32_t num_goods;   /* G  goods (Economy::numGoods, base.h:124)                       */
+    int32_t stack_size;  /* S  offers considered per decision (DEFAULT_STACK_SIZE,
+                               src/neural/neuralConstants.h:13)                            */
+} fastace_dims_t;
+
+/*
+ * Economy state.  Mirrors the reference's objects as SoA:
+ *   Agent::money / inventory            base.h:168-171
+ *   Person::laborSupplied               base.h:214
+ *   Firm::laborHired                    base.h:257
+ *   UtilMaxer::utilFunc  (CES)          utilMaxer.h:71, vecToScalar.h:79-93
+ *   ProfitMaxer::prodFunc (one CES per output good, create_CES_VecToVec)
+ *                                       profitMaxer.h:72, vecToVec.cpp:34-53
+ *   NeuralFirmDecisionMaker::last_money src/neural/neuralEconomy.h:113
+ *   Economy::market / jobMarket         base.h:125-126  (BaseOffer/Offer/JobOffer base.h:21-66)
+ *
+ * CES parameters are stored as the CES object holds them after construction
+ * (vecToScalar.cpp:105-110): share parameters normalised to sum 1, and
+ * rho = substitutionParam = 1/(1 - elasticityOfSubstitution).
+ *
+ * The goods book is kept in MARKET ORDER (the order of Economy::market after the
+ * end-of-step flush, economy.cpp:125): entry n is what an action index n refers to.
+ * Every Offer posted by the shipped plugin is for one unit (AMOUNT_PER_OFFER = 1.0) of
+ * a single good, so `m_good` replaces Offer::quantities; every JobOffer is for
+ * LABOR_AMOUNT_PER_OFFER = 0.5 labour (neuralFirmDecisionMaker.cpp:6-7).
+ */
+typedef struct fastace_state {
+    /* persons */
+    double*   p_money;      /* [E][P]                                   */
+    double*   p_inv;        /* [E][G][P]                                */
+    double*   p_labor;      /* [E][P]       laborSupplied               */
+    double*   p_util_tfp;   /* [E][P]                                   */
+    double*   p_util_share; /* [E][G+1][P]  input 0 = leisure (1-labor) */
+    double*   p_util_rho;   /* [E][P]                                   */
+    /* firms */
+    double*   f_money;      /* [E][F]                                   */
+    double*   f_inv;        /* [E][G][F]                                */
+    double*   f_labor;      /* [E][F]       laborHired                  */
+    double*   f_last_money; /* [E][F]       money at the firm's first decision of the previous step */
+    double*   f_prod_tfp;   /* [E][G][F]        per output good         */
+    double*   f_prod_share; /* [E][G][G+1][F]   [output][input], input 0 = labour */
+    double*   f_prod_rho;   /* [E][G][F]                                */
+    /* goods market, market order, capacity F*G entries per economy */
+    int32_t*  m_count;      /* [E]                                      */
+    int32_t*  m_owner;      /* [E][F*G]     firm id of the offerer      */
+    int32_t*  m_good;       /* [E][F*G]                                 */
+    uint32_t* m_left;       /* [E][F*G]     BaseOffer::amountLeft       */
+    uint32_t* m_taken;      /* [E][F*G]     BaseOffer::amountTaken      */
+    double*   m_price;      /* [E][F*G]                                 */
+    /* job market, market order, capacity F entries per economy */
+    int32_t*  j_count;      /* [E]                                      */
+    int32_t*  j_owner;      /* [E][F]                                   */
+    uint32_t* j_left;       /* [E][F]                                   */
+    uint32_t* j_taken;      /* [E][F]                                   */
+    double*   j_wage;       /* [E][F]       wage per job lot (= wage/0.5) */
+} fastace_state_t;
+
+/*
+ * One step's injected decisions and visiting orders.
+ *   perm_*      : the order in which Economy::time_step visits agents after its two
+ *                 std::shuffle calls (economy.cpp:110-111): perm[r] = id of the agent
+ *                 visited r-th.  Must be a permutation of 0..n-1.
+ *   *_idx/_take : the stack of S offer indices an agent drew for this step
+ *                 (decisionNetHandler.cpp:327-365) and the Bernoulli "request it"
+ *                 outcomes (decisionNetHandler.cpp:368-387, 446-466).  Index n refers to
+ *                 entry n of the respective book as it stood when the step began
+ *                 (snapshot rule, decisionNetHandler.cpp:236-275, 303-308).
+ *   p_consume   : consumption proportions   (get_consumption_proportions, :496-517)
+ *   f_prod      : production-input proportions (get_production_proportions, :519-539)
+ *   f_offer_amt / f_offer_price : choose_offers  (:568-603)
+ *   f_job_labor / f_job_wage    : choose_job_offers (:606-643); the 1e8 wage clip is
+ *                 applied on the device.
+ * Continuous actions are float32 exactly as the nets emit them and are widened to
+ * double on the device (torchToEigen, decisionNetHandler.cpp:22-25).
+ */
+typedef struct fastace_actions {
+    const int32_t* perm_person;   /* [E][P]    */
+    const int32_t* perm_firm;     /* [E][F]    */
+    const int32_t* p_job_idx;     /* [E][S][P] */
+    const uint8_t* p_job_take;    /* [E][S][P] */
+    const int32_t* p_good_idx;    /* [E][S][P] */
+    const uint8_t* p_good_take;   /* [E][S][P] */
+    const float*   p_consume;     /* [E][G][P] */
+    const int32_t* f_good_idx;    /* [E][S][F] */
+    const uint8_t* f_good_take;   /* [E][S][F] */
+    const float*   f_prod;        /* [E][G][F] */
+    const float*   f_offer_amt;   /* [E][G][F] */
+    const float*   f_offer_price; /* [E][G][F] */
+    const float*   f_job_labor;   /* [E][F]    */
+    const float*   f_job_wage;    /* [E][F]    */
+} fastace_actions_t;
+
+/*
+ * Per-step outputs.  p_reward and f_profit are mandatory; every other pointer may be
+ * NULL (then it is not written).
+ *   p_reward : utility of this step's consumption (neuralPersonDecisionMaker.cpp:107-108)
+ *   f_profit : money at the firm's first decision of this step minus the same one step
+ *              earlier (neuralFirmDecisionMaker.cpp:65-74); 0 on an env's first step,
+ *              where the reference records nothing.
+ *   *_ok     : 1 where the requested unit was actually transacted.
+ *   old_*    : final counters of the PREVIOUS book's entries (the snapshot the step
+ *              traded against), taken just before their owner withdrew them
+ *              (profitMaxer.cpp:79-81, 93-95).  old_m_left is 0 for an entry that was
+ *              already dead when its owner's turn came (flushed, agent.cpp:21).
+ */
+typedef struct fastace_step_out {
+    double*   p_reward;   /* [E][P]    */
+    double*   f_profit;   /* [E][F]    */
+    uint8_t*  p_job_ok;   /* [E][S][P] optional */
+    uint8_t*  p_good_ok;  /* [E][S][P] optional */
+    uint8_t*  f_good_ok;  /* [E][S][F] optional */
+    uint32_t* old_m_left; /* [E][F*G]  optional */
+    uint32_t* old_m_taken;/* [E][F*G]  optional */
+    uint32_t* old_j_left; /* [E][F]    optional */
+    uint32_t* old_j_taken;/* [E][F]    optional */
+} fastace_step_out_t;
+
+/* step flags */
+#define FASTACE_IDX_ABSOLUTE 0u /* index n used as is; n<0 or n>=count => no request (never happens with the reference's randint) */
+#define FASTACE_IDX_MODULO   1u /* raw non-negative draw r mapped to r % count: stands in for torch::randint(0,count) (decisionNetHandler.cpp:332-334) */
+
+typedef struct fastace_env fastace_env_t;
+
+/* ---- library ---------------------------------------------------------------------- */
+int         fastace_abi_version(void);
+const char* fastace_last_error(void);
+/* number of visible CUDA devices, or a negative status */
+int         fastace_device_count(void);
+
+/* ---- env lifetime ------------------------------------------------------------------ */
+/* Allocates all state buffers for E economies on CUDA device `device` (zero-filled,
+ * empty markets, time 0).  Replaces `new Economy(goods)` + util::create<T> for every
+ * agent (economy.cpp:3-27, util.h:41-46).  Fails with FASTACE_ERR_NO_DEVICE when no
+ * GPU is present — there is no CPU path. */
+int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** out_env);
+int fastace_env_destroy(fastace_env_t* env);
+int fastace_env_dims(const fastace_env_t* env, fastace_dims_t* out_dims);
+/* Economy::get_time (base.h:91) — identical for all economies of an env */
+int fastace_env_time(const fastace_env_t* env, uint32_t* out_time);
+
+/* ---- state I/O --------------------------------------------------------------------- */
+/* Host -> device.  NULL members are left untouched.  Also sets the env time. */
+int fastace_env_set_state(fastace_env_t* env, const fastace_state_t* host_state, uint32_t time);
+/* Device -> host.  NULL members are skipped.  Mirrors the reference's read API
+ * (get_money/get_inventory/get_laborSupplied/get_laborHired/get_market/get_jobMarket,
+ * base.h:90-106,147-150,205,245). */
+int fastace_env_get_state(const fastace_env_t* env, fastace_state_t* host_state);
+/* Zero-copy: device pointers of the env's own buffers (valid until destroy). */
+int fastace_env_device_state(const fastace_env_t* env, fastace_state_t* out_device_state);
+
+/* ---- the hot path ------------------------------------------------------------------ */
+/* One Economy::time_step() for all E economies.  `actions`/`out` hold DEVICE pointers;
+ * the kernel is enqueued on `cuda_stream` (a cudaStream_t, 0 = default stream) and the
+ * call returns without synchronising. */
+int fastace_env_step_device(fastace_env_t* env, const fastace_actions_t* actions,
+                            const fastace_step_out_t* out, uint32_t flags, void* cuda_stream);
+/* Same, with HOST pointers: copies the actions to the device, steps, copies the outputs
+ * back and synchronises.  This is the end-to-end call a ctypes/C++ caller with host
+ * arrays makes. */
+int fastace_env_step_host(fastace_env_t* env, const fastace_actions_t* actions,
+                          const fastace_step_out_t* out, uint32_t flags);
+/* number of kernel launches issued by this env's step calls so far */
+int fastace_env_launch_count(const fastace_env_t* env, uint64_t* out_count);
+
+/* ---- legacy entry points of libpybindings.so (src/pybindings.h:8-28) ------------------ */
+/* Byte-identical layouts of neural::CustomScenarioParams (344 B) and
+ * neural::TrainingParams (136 B), src/neural/neuralScenarios.h:49-186, py/main.py:12-85. */
+typedef struct fastace_custom_scenario_params {
+    uint32_t numPeople, numFirms;
+    double money_mu, money_sigma, good1_mu, good1_sigma, good2_mu, good2_sigma;
+    double labor_share_mu, labor_share_sigma, good1_share_mu, good1_share_sigma,
+           good2_share_mu, good2_share_sigma;
+    double discount_mu, discount_sigma, elasticity_mu, elasticity_sigma;
+    double firm_money_mu, firm_money_sigma, firm_good1_mu, firm_good1_sigma,
+           firm_good2_mu, firm_good2_sigma;
+    double firm_tfp1_mu, firm_tfp1_sigma, firm_tfp2_mu, firm_tfp2_sigma;
+    double firm_labor_share1_mu, firm_labor_share1_sigma, firm_good1_share1_mu,
+           firm_good1_share1_sigma, firm_good2_share1_mu, firm_good2_share1_sigma;
+    double firm_labor_share2_mu, firm_labor_share2_sigma, firm_good1_share2_mu,
+           firm_good1_share2_sigma, firm_good2_share2_mu, firm_good2_share2_sigma;
+    double firm_elasticity1_mu, firm_elasticity1_sigma, firm_elasticity2_mu,
+           firm_elasticity2_sigma;
+} fastace_custom_scenario_params_t;
+
+typedef struct fastace_training_params {
+    uint32_t numEpisodes, episodeLength, updateEveryNEpisodes, checkpointEveryNEpisodes;
+    uint32_t stackSize, encodingSize, hiddenSize, nHidden, nHiddenSmall;
+    double purchaseNetLR, firmPurchaseNetLR, laborSearchNetLR, consumptionNetLR,
+           productionNetLR, offerNetLR, jobOfferNetLR, valueNetLR, firmValueNetLR;
+    uint32_t episodeBatchSizeForLRDecay, patienceForLRDecay;
+    double multiplierForLRDecay;
+    uint32_t reverseAnnealingPeriod;
+} fastace_training_params_t;
+
+/* same names and by-value struct returns as src/pybindings.cpp:8-18 */
+fastace_custom_scenario_params_t create_scenario_params(unsigned int numPeople, unsigned int numFirms);
+fastace_training_params_t        create_training_params(void);
+
+/* ---- scenario initial state (host side) ---------------------------------------------- */
+/* Fills a HOST fastace_state_t for E economies with the initial-state distributions of
+ * CustomScenario::setup (src/neural/neuralScenarios.cpp:93-161; G must be 2): economy e
+ * draws from std::minstd_rand0(seed + e) through std::normal_distribution, the same
+ * libstdc++ generators the reference uses.  Markets start empty.  `p_discount` ([E][P],
+ * may be NULL) receives the persons' discount rates, which the step itself never reads. */
+int fastace_scenario_custom_init(const fastace_dims_t* dims,
+                                 const fastace_custom_scenario_params_t* params,
+                                 uint32_t seed, fastace_state_t* host_state, double* p_discount);
+/* Fills perm_person/perm_firm ([E][P], [E][F], HOST) for `step_index` = 0,1,2,... exactly
+ * as Economy::time_step would visit agents: economy e keeps a std::minstd_rand0(seed+e)
+ * and applies std::shuffle to its person vector, then its firm vector, cumulatively
+ * (economy.cpp:110-111).  `rng_state` ([E] uint64, caller-owned, zero-initialised before
+ * step 0) and the perm arrays carry the stream and the cumulative order between calls. */
+int fastace_shuffle_orders(const fastace_dims_t* dims, uint32_t seed, uint64_t* rng_state,
+                           int32_t* perm_person, int32_t* perm_firm, int first_call);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTACE_B200_H */

@@ -1,0 +1,121 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical
+injected actions and visiting orders.  Bit-exact for matching / counters / market order,
+1e-5 relative for floating point (north_star)."""
+import numpy as np
+import pytest
+
+from fastace_b200 import _abi, scenario
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_episode(oracle, dims, steps, seed, flags=_abi.IDX_MODULO, preset=None, state=None, host_api=False,
+                 shuffled=True):
+    from fastace_b200.env import BatchedEconomy
+    E, P, F, G, S = dims
+    if state is None:
+        state = scenario.custom_initial_state(dims, seed)[0] if G == 2 else scenario.generic_initial_state(dims, seed)
+    env = BatchedEconomy(dims)
+    env.set_state(state, time=0)
+    ost = H.copy_state(state)
+    orders = scenario.OrderStream(dims, seed + 17) if shuffled else None
+    worst = 0.0
+    for t in range(steps):
+        perms = orders.next() if shuffled else None
+        act = scenario.synthetic_actions(dims, seed=seed + 1, step=t, perms=perms, **(preset or {}))
+        before = H.copy_state(ost)
+        oout = _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=flags, time_before=t)
+        if host_api:
+            gout = _abi.alloc_host("out", dims)
+            env.time_step_host(act, gout, flags=flags)
+        else:
+            dact = env.alloc_actions(act)
+            dout = env.alloc_outputs(names=None)
+            env.time_step(dact, dout, flags=flags)
+            gout = {k: v.cpu().numpy().view(_abi.shapes("out", dims)[k][0]) for k, v in dout.items()}
+        worst = max(worst, H.compare_outputs(gout, oout, dims, before))
+        worst = max(worst, H.compare_states(env.get_state(), ost, dims))
+        assert env.get_time() == t + 1
+    env.close()
+    return worst
+
+
+def test_config_b_small_batch(oracle):
+    # config B shape (100 persons + 10 firms, 2 goods, stack 10), 64 economies, 40-step episode
+    worst = _run_episode(oracle, (64, 100, 10, 2, 10), 40, seed=11, preset=scenario.BENCH_PRESET)
+    print("max rel err", worst)
+
+
+def test_config_a_default_scenario(oracle):
+    # config A: py/train.py defaults, 48 persons + 12 firms, 40 steps
+    _run_episode(oracle, (8, 48, 12, 2, 10), 40, seed=3)
+
+
+def test_host_api_matches(oracle):
+    _run_episode(oracle, (5, 37, 7, 2, 10), 12, seed=5, preset=scenario.BENCH_PRESET, host_api=True)
+
+
+@pytest.mark.parametrize("dims", [
+    (3, 1, 1, 1, 1), (4, 33, 1, 1, 3), (2, 100, 33, 2, 10), (3, 64, 40, 3, 16), (2, 31, 9, 8, 10),
+    (2, 0, 3, 2, 4), (3, 7, 5, 5, 0), (2, 257, 12, 4, 7),
+])
+def test_shapes(oracle, dims):
+    _run_episode(oracle, dims, 10, seed=dims[1] + 7 * dims[2], preset=scenario.BENCH_PRESET)
+
+
+def test_absolute_indices_with_out_of_range(oracle):
+    from fastace_b200.env import BatchedEconomy
+    dims = (6, 50, 6, 2, 10)
+    E, P, F, G, S = dims
+    state = scenario.custom_initial_state(dims, 21)[0]
+    env = BatchedEconomy(dims)
+    env.set_state(state)
+    ost = H.copy_state(state)
+    rng = np.random.default_rng(0)
+    for t in range(15):
+        act = scenario.synthetic_actions(dims, seed=9, step=t, **scenario.BENCH_PRESET)
+        # small absolute indices, some negative, some beyond any possible book size
+        for k, hi in (("p_job_idx", F + 3), ("p_good_idx", F * G + 3), ("f_good_idx", F * G + 3)):
+            act[k] = rng.integers(-2, hi, act[k].shape, dtype=np.int32)
+        before = H.copy_state(ost)
+        oout = _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=_abi.IDX_ABSOLUTE, time_before=t)
+        gout = _abi.alloc_host("out", dims)
+        env.time_step_host(act, gout, flags=_abi.IDX_ABSOLUTE)
+        H.compare_outputs(gout, oout, dims, before)
+        H.compare_states(env.get_state(), ost, dims)
+
+
+def test_extreme_actions(oracle):
+    """wage clip at 1e8, labour / amounts that overflow (int) conversion, zero proportions,
+    everyone requests everything, nobody requests anything."""
+    from fastace_b200.env import BatchedEconomy
+    dims = (4, 40, 5, 2, 10)
+    E, P, F, G, S = dims
+    state = scenario.custom_initial_state(dims, 33)[0]
+    state["f_inv"][0] *= 1e6  # huge inventories -> many lots
+    env = BatchedEconomy(dims)
+    env.set_state(state)
+    ost = H.copy_state(state)
+    for t in range(12):
+        act = scenario.synthetic_actions(dims, seed=4, step=t, **scenario.BENCH_PRESET)
+        act["f_job_wage"][1] = 3e9           # clipped to 1e8 then /0.5
+        act["f_job_labor"][2] = 3e9          # (int) overflow -> no offer
+        act["f_job_labor"][3, :2] = np.inf
+        act["f_offer_amt"][0] = 1.0
+        act["f_offer_price"][0] = 1e-3
+        act["p_consume"][1] = 0.0
+        act["p_consume"][2] = 1.0
+        if t % 3 == 0:
+            act["p_job_take"][:] = 1; act["p_good_take"][:] = 1; act["f_good_take"][:] = 1
+        if t % 3 == 1:
+            act["p_job_take"][:] = 0; act["p_good_take"][:] = 0; act["f_good_take"][:] = 0
+        before = H.copy_state(ost)
+        oout = _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=_abi.IDX_MODULO, time_before=t)
+        gout = _abi.alloc_host("out", dims)
+        env.time_step_host(act, gout, flags=_abi.IDX_MODULO)
+        H.compare_outputs(gout, oout, dims, before)
+        H.compare_states(env.get_state(), ost, dims)
