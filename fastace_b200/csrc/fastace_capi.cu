@@ -270,7 +270,10 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
     for (auto& f : action_fields(env->dims)) {
         if (f.count && !member(dact, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
     }
-    if (!dout->p_reward || !dout->f_profit) { set_error("out: p_reward and f_profit are mandatory"); return FASTACE_ERR_INVALID; }
+    if ((env->dims.num_persons > 0 && !dout->p_reward) || !dout->f_profit) {
+        set_error("out: p_reward and f_profit are mandatory");
+        return FASTACE_ERR_INVALID;
+    }
     StepParams sp;
     sp.E = env->dims.num_econ; sp.P = env->dims.num_persons; sp.F = env->dims.num_firms; sp.S = env->dims.stack_size;
     sp.flags = flags;

@@ -131,7 +131,7 @@ __device__ __forceinline__ bool request_good(int n, double& money, double* s_fmo
 }
 
 template <int G>
-__global__ void __launch_bounds__(32) step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int e = blockIdx.x;
     const int lane = threadIdx.x;
