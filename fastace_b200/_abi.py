@@ -12,6 +12,7 @@ ABI_VERSION = 1
 FASTACE_OK = 0
 IDX_ABSOLUTE = 0
 IDX_MODULO = 1
+STEP_SERIAL = 2
 MAX_GOODS = 8
 MAX_STACK = 16
 

@@ -139,16 +139,16 @@ static int carve(const std::vector<FieldDesc>& fields, StructT* s, void** block,
 }
 
 typedef void (*kernel_fn)(const StepParams);
-static kernel_fn kernel_for_goods(int G) {
+static kernel_fn kernel_for_goods(int G, bool parallel) {
     switch (G) {
-        case 1: return step_kernel<1>;
-        case 2: return step_kernel<2>;
-        case 3: return step_kernel<3>;
-        case 4: return step_kernel<4>;
-        case 5: return step_kernel<5>;
-        case 6: return step_kernel<6>;
-        case 7: return step_kernel<7>;
-        case 8: return step_kernel<8>;
+        case 1: return parallel ? step_kernel<1, true> : step_kernel<1, false>;
+        case 2: return parallel ? step_kernel<2, true> : step_kernel<2, false>;
+        case 3: return parallel ? step_kernel<3, true> : step_kernel<3, false>;
+        case 4: return parallel ? step_kernel<4, true> : step_kernel<4, false>;
+        case 5: return parallel ? step_kernel<5, true> : step_kernel<5, false>;
+        case 6: return parallel ? step_kernel<6, true> : step_kernel<6, false>;
+        case 7: return parallel ? step_kernel<7, true> : step_kernel<7, false>;
+        case 8: return parallel ? step_kernel<8, true> : step_kernel<8, false>;
         default: return nullptr;
     }
 }
@@ -194,9 +194,11 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
         set_error("economy too large for the warp-per-economy kernel's shared-memory books");
         return FASTACE_ERR_INVALID;
     }
-    kernel_fn k = kernel_for_goods(d.num_goods);
-    if (L.total > 48 * 1024)
-        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    if (L.total > 48 * 1024) {
+        for (int par = 0; par < 2; par++)
+            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)kernel_for_goods(d.num_goods, par != 0),
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    }
 
     fastace_env* env = new (std::nothrow) fastace_env();
     if (!env) { set_error("out of host memory"); return FASTACE_ERR_ALLOC; }
@@ -281,7 +283,7 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
     sp.st = env->dstate;
     sp.ac = *dact;
     sp.out = *dout;
-    kernel_fn k = kernel_for_goods(env->dims.num_goods);
+    kernel_fn k = kernel_for_goods(env->dims.num_goods, (flags & FASTACE_STEP_SERIAL) == 0);
     k<<<sp.E, 32, env->smem_bytes, stream>>>(sp);
     FASTACE_CUDA_CHECK(cudaGetLastError());
     env->time += 1;

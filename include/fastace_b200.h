@@ -177,6 +177,11 @@ typedef struct fastace_step_out {
 #define FASTACE_IDX_ABSOLUTE 0u /* index n used as is; n<0 or n>=count => no request (never happens with the reference's randint) */
 #define FASTACE_IDX_MODULO   1u /* raw non-negative draw r mapped to r % count: stands in for torch::randint(0,count) (decisionNetHandler.cpp:332-334) */
 
+/* Matching algorithm.  Default: lane-parallel fixed-point matching (kernel v2).  With
+ * FASTACE_STEP_SERIAL persons are matched by a serial walk (kernel v1), which also keeps the
+ * reference's fp64 operation order for FIRM money; outcomes are otherwise identical. */
+#define FASTACE_STEP_SERIAL  2u
+
 typedef struct fastace_env fastace_env_t;
 
 /* ---- library ---------------------------------------------------------------------- */

@@ -73,7 +73,7 @@ typedef struct {
 
 static int map_index(int32_t raw, int count, uint32_t flags, int* out) {
     if (count <= 0) return 0;
-    if (flags & FASTACE_IDX_MODULO) { *out = (int)((uint32_t)raw % (uint32_t)count); return 1; }
+    if (flags & FASTACE_IDX_MODULO) { *out = (int)((uint32_t)raw % (uint32_t)count); return 1; }  /* FASTACE_STEP_SERIAL has no meaning here */
     if (raw < 0 || raw >= count) return 0;
     *out = raw;
     return 1;

@@ -112,8 +112,11 @@ def main():
     dims = (1, 37, 7, 3, 6)       # 3 goods, ragged sizes
     record("three_goods", dims, scenario.generic_initial_state(dims, 505), steps=20, seed=15,
            flags=_abi.IDX_MODULO, preset=scenario.BENCH_PRESET)
-    dims = (1, 64, 33, 8, 4)      # config D shape in miniature: 8 goods, > 32 firms
+    dims = (1, 64, 31, 8, 4)      # config D's 8 goods in miniature (F*G = 248 book entries)
     record("eight_goods", dims, scenario.generic_initial_state(dims, 606), steps=10, seed=17,
+           flags=_abi.IDX_MODULO, preset=scenario.BENCH_PRESET)
+    dims = (1, 50, 40, 3, 6)      # more firms than lanes in a warp
+    record("many_firms", dims, scenario.generic_initial_state(dims, 707), steps=10, seed=19,
            flags=_abi.IDX_MODULO, preset=scenario.BENCH_PRESET)
 
 

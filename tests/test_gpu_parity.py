@@ -42,10 +42,19 @@ def _run_episode(oracle, dims, steps, seed, flags=_abi.IDX_MODULO, preset=None, 
     return worst
 
 
-def test_config_b_small_batch(oracle):
-    # config B shape (100 persons + 10 firms, 2 goods, stack 10), 64 economies, 40-step episode
-    worst = _run_episode(oracle, (64, 100, 10, 2, 10), 40, seed=11, preset=scenario.BENCH_PRESET)
+@pytest.mark.parametrize("mode", [0, _abi.STEP_SERIAL])
+def test_config_b_small_batch(oracle, mode):
+    # config B shape (100 persons + 10 firms, 2 goods, stack 10), 64 economies, 40-step episode;
+    # both matching kernels (lane-parallel v2 = default, serial v1)
+    worst = _run_episode(oracle, (64, 100, 10, 2, 10), 40, seed=11, preset=scenario.BENCH_PRESET,
+                         flags=_abi.IDX_MODULO | mode)
     print("max rel err", worst)
+
+
+@pytest.mark.parametrize("mode", [0, _abi.STEP_SERIAL])
+def test_bankrupt_firms(oracle, mode):
+    # untuned recipe: firms run out of money, job offers are killed by the first applicant
+    _run_episode(oracle, (32, 100, 10, 2, 10), 30, seed=5, preset=dict(labor_mu=1.0), flags=_abi.IDX_MODULO | mode)
 
 
 def test_config_a_default_scenario(oracle):
@@ -61,8 +70,9 @@ def test_host_api_matches(oracle):
     (3, 1, 1, 1, 1), (4, 33, 1, 1, 3), (2, 100, 33, 2, 10), (3, 64, 40, 3, 16), (2, 31, 9, 8, 10),
     (2, 0, 3, 2, 4), (3, 7, 5, 5, 0), (2, 257, 12, 4, 7),
 ])
-def test_shapes(oracle, dims):
-    _run_episode(oracle, dims, 10, seed=dims[1] + 7 * dims[2], preset=scenario.BENCH_PRESET)
+@pytest.mark.parametrize("mode", [0, _abi.STEP_SERIAL])
+def test_shapes(oracle, dims, mode):
+    _run_episode(oracle, dims, 10, seed=dims[1] + 7 * dims[2], preset=scenario.BENCH_PRESET, flags=_abi.IDX_MODULO | mode)
 
 
 def test_absolute_indices_with_out_of_range(oracle):
