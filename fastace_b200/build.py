@@ -14,6 +14,8 @@ LIB = os.path.join(HERE, "libfastace_b200.so")
 SOURCES = [os.path.join(CSRC, "fastace_capi.cu"), os.path.join(CSRC, "fastace_host.cpp")]
 DEPS = SOURCES + [
     os.path.join(CSRC, "step_kernel.cuh"),
+    os.path.join(CSRC, "match_update_kernels.cuh"),
+    os.path.join(CSRC, "common.cuh"),
     os.path.join(CSRC, "fastace_internal.h"),
     os.path.join(HERE, "..", "include", "fastace_b200.h"),
 ]

@@ -1,0 +1,76 @@
+// Shared device helpers of the fastACE step kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fastace_b200.h"
+
+namespace fastace {
+
+struct StepParams {
+    int E, P, F, S;
+    uint32_t flags;
+    uint32_t time_before;
+    fastace_state_t st;
+    fastace_actions_t ac;
+    fastace_step_out_t out;
+};
+
+constexpr double kEps = 1e-8;            // constants::eps (base/constants.h:9)
+constexpr double kLargeNumber = 1e8;     // constants::largeNumber (base/constants.h:10)
+constexpr double kAmountPerOffer = 1.0;  // neural/neuralFirmDecisionMaker.cpp:6
+constexpr double kLaborPerOffer = 0.5;   // neural/neuralFirmDecisionMaker.cpp:7
+constexpr int kNone = 0xFF;
+
+// (int)double as the x86-64 reference binary does it (cvttsd2si): out-of-range and NaN
+// give INT_MIN, which fails the `numOffers > 0` tests.
+__device__ __forceinline__ int x86_double_to_int(double x) {
+    if (!(x > -2147483649.0 && x < 2147483648.0)) return INT32_MIN;
+    return __double2int_rz(x);
+}
+
+// Index mapping (decisionNetHandler.cpp:327-365 draws indices in [0,count)).  count <= 254 here, so
+// the modulo of a 32-bit draw is done as two exact 32-bit "fastmod" steps (Lemire): with
+// M = floor(2^32 / c) + 1, (x mod c) = mulhi(M * x mod 2^32, c) for every x < 2^24.
+struct IndexMap {
+    uint32_t magic, count, k16;   // k16 = 65536 mod count
+    bool modulo;
+    __device__ __forceinline__ IndexMap(int cnt, uint32_t flags)
+        : magic(cnt > 0 ? 0xFFFFFFFFu / (uint32_t)cnt + 1u : 0u), count(cnt > 0 ? (uint32_t)cnt : 0u),
+          k16(cnt > 0 ? 65536u % (uint32_t)cnt : 0u), modulo((flags & FASTACE_IDX_MODULO) != 0) {}
+    __device__ __forceinline__ uint32_t mod24(uint32_t x) const { return __umulhi(magic * x, count); }
+    // precondition: count > 0 (callers skip mapping for an empty book)
+    __device__ __forceinline__ int operator()(int raw) const {
+        const uint32_t u = (uint32_t)raw;
+        if (modulo) return (int)mod24(mod24(u >> 16) * k16 + (u & 0xFFFFu));
+        return (u >= count) ? kNone : raw;
+    }
+};
+
+// pow for the reward path (1e-5 relative tolerance): exp(y*log(x)), fp64 throughout.
+// Relative error ~ |y ln x| * 2^-52, far inside the tolerance; ~3x cheaper than pow().
+__device__ __forceinline__ double pow_reward(double x, double y) { return exp(y * log(x)); }
+
+// One goods request by a buyer whose money/inventory live at (money, inv[g*istride]).
+// Agent::respond_to_offer -> review_offer_response -> accept_offer_response
+// (base/agent.cpp:99-161), fp64 updates in the reference's order.
+
+// floor(x) as a lot count: how many times `inventory >= 1.0; inventory -= 1.0` succeeds
+// (agent.cpp:140,156; the subtraction is exact for x < 2^53).  NaN never compares "short".
+__device__ __forceinline__ uint32_t unit_sales_possible(double x) {
+    if (x < 1.0) return 0u;
+    if (!(x < 4294967296.0)) return 0xFFFFFFFFu;
+    return (uint32_t)x;
+}
+
+// optional outputs: per-request success flags of one person (jobs in bits 0..15, goods in 16..31)
+__device__ __forceinline__ void write_person_ok(const StepParams& p, int e, int pid, uint32_t okm) {
+    if (p.out.p_job_ok == nullptr && p.out.p_good_ok == nullptr) return;
+    for (int i = 0; i < p.S; i++) {
+        const size_t k = ((size_t)e * p.S + i) * p.P + pid;
+        if (p.out.p_job_ok) p.out.p_job_ok[k] = (okm >> i) & 1u;
+        if (p.out.p_good_ok) p.out.p_good_ok[k] = (okm >> (16 + i)) & 1u;
+    }
+}
+
+}  // namespace fastace

@@ -12,6 +12,7 @@
 #include "../../include/fastace_b200.h"
 #include "fastace_internal.h"
 #include "step_kernel.cuh"
+#include "match_update_kernels.cuh"
 
 namespace fastace {
 
@@ -110,7 +111,10 @@ struct fastace_env {
     void* out_block;
     fastace_step_out_t dout;
     cudaStream_t stream;
-    size_t smem_bytes;
+    size_t smem_bytes;        // serial fused kernel
+    size_t match_smem_bytes;  // match_kernel
+    uint8_t* scr_pnh;         // [E][P]    match_kernel -> update_kernel
+    uint8_t* scr_pnb;         // [E][G][P]
 };
 
 #define FASTACE_CUDA_CHECK(expr)                                                              \
@@ -138,18 +142,23 @@ static int carve(const std::vector<FieldDesc>& fields, StructT* s, void** block,
     return FASTACE_OK;
 }
 
-typedef void (*kernel_fn)(const StepParams);
-static kernel_fn kernel_for_goods(int G, bool parallel) {
+typedef void (*serial_fn)(const StepParams);
+typedef void (*match_fn)(const MatchParams);
+typedef void (*update_fn)(const UpdateParams);
+struct KernelSet { serial_fn serial; match_fn match12; match_fn match16; update_fn update; };
+template <int G>
+static KernelSet kernels_of() { return {step_kernel<G>, match_kernel<G, 12>, match_kernel<G, 16>, update_kernel<G>}; }
+static KernelSet kernels_for_goods(int G) {
     switch (G) {
-        case 1: return parallel ? step_kernel<1, true> : step_kernel<1, false>;
-        case 2: return parallel ? step_kernel<2, true> : step_kernel<2, false>;
-        case 3: return parallel ? step_kernel<3, true> : step_kernel<3, false>;
-        case 4: return parallel ? step_kernel<4, true> : step_kernel<4, false>;
-        case 5: return parallel ? step_kernel<5, true> : step_kernel<5, false>;
-        case 6: return parallel ? step_kernel<6, true> : step_kernel<6, false>;
-        case 7: return parallel ? step_kernel<7, true> : step_kernel<7, false>;
-        case 8: return parallel ? step_kernel<8, true> : step_kernel<8, false>;
-        default: return nullptr;
+        case 1: return kernels_of<1>();
+        case 2: return kernels_of<2>();
+        case 3: return kernels_of<3>();
+        case 4: return kernels_of<4>();
+        case 5: return kernels_of<5>();
+        case 6: return kernels_of<6>();
+        case 7: return kernels_of<7>();
+        case 8: return kernels_of<8>();
+        default: return {nullptr, nullptr, nullptr, nullptr};
     }
 }
 
@@ -188,16 +197,19 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
     FASTACE_CUDA_CHECK(cudaSetDevice(device));
 
     const SmemLayout L = make_layout(d.num_persons, d.num_firms, d.num_goods, d.stack_size);
+    const MatchLayout ML = make_match_layout(d.num_persons, d.num_firms, d.num_goods, d.stack_size);
     int max_optin = 0;
     FASTACE_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    if (L.total > max_optin) {
+    if (L.total > max_optin || ML.total > max_optin) {
         set_error("economy too large for the warp-per-economy kernel's shared-memory books");
         return FASTACE_ERR_INVALID;
     }
-    if (L.total > 48 * 1024) {
-        for (int par = 0; par < 2; par++)
-            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)kernel_for_goods(d.num_goods, par != 0),
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    const KernelSet ks = kernels_for_goods(d.num_goods);
+    if (L.total > 48 * 1024)
+        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.serial, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    if (ML.total > 48 * 1024) {
+        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match12, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
+        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match16, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
     }
 
     fastace_env* env = new (std::nothrow) fastace_env();
@@ -206,8 +218,18 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
     env->dims = d;
     env->device = device;
     env->smem_bytes = (size_t)L.total;
+    env->match_smem_bytes = (size_t)ML.total;
     int rc = carve(state_fields(d), &env->dstate, &env->state_block, true);
     if (rc != FASTACE_OK) { delete env; return rc; }
+    {
+        const size_t np = (size_t)d.num_econ * d.num_persons;
+        cudaError_t e1 = cudaMalloc((void**)&env->scr_pnh, np ? np : 1);
+        cudaError_t e2 = cudaMalloc((void**)&env->scr_pnb, np ? np * d.num_goods : 1);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_error("cudaMalloc of matching scratch failed");
+            cudaFree(env->state_block); delete env; return FASTACE_ERR_ALLOC;
+        }
+    }
     cudaError_t err = cudaStreamCreateWithFlags(&env->stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) { set_error(cudaGetErrorString(err)); cudaFree(env->state_block); delete env; return FASTACE_ERR_CUDA; }
     *out_env = env;
@@ -221,6 +243,8 @@ int fastace_env_destroy(fastace_env_t* env) {
     if (env->state_block) cudaFree(env->state_block);
     if (env->act_block) cudaFree(env->act_block);
     if (env->out_block) cudaFree(env->out_block);
+    if (env->scr_pnh) cudaFree(env->scr_pnh);
+    if (env->scr_pnb) cudaFree(env->scr_pnb);
     delete env;
     return FASTACE_OK;
 }
@@ -283,11 +307,27 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
     sp.st = env->dstate;
     sp.ac = *dact;
     sp.out = *dout;
-    kernel_fn k = kernel_for_goods(env->dims.num_goods, (flags & FASTACE_STEP_SERIAL) == 0);
-    k<<<sp.E, 32, env->smem_bytes, stream>>>(sp);
-    FASTACE_CUDA_CHECK(cudaGetLastError());
+    const KernelSet ks = kernels_for_goods(env->dims.num_goods);
+    if (flags & FASTACE_STEP_SERIAL) {
+        ks.serial<<<sp.E, 32, env->smem_bytes, stream>>>(sp);
+        FASTACE_CUDA_CHECK(cudaGetLastError());
+        env->launches += 1;
+    } else {
+        MatchParams mp;
+        mp.sp = sp; mp.scr_pnh = env->scr_pnh; mp.scr_pnb = env->scr_pnb;
+        mp.lay = make_match_layout(sp.P, sp.F, env->dims.num_goods, sp.S);
+        (sp.S <= 12 ? ks.match12 : ks.match16)<<<sp.E, 32, env->match_smem_bytes, stream>>>(mp);
+        FASTACE_CUDA_CHECK(cudaGetLastError());
+        UpdateParams up;
+        up.sp = sp; up.scr_pnh = env->scr_pnh; up.scr_pnb = env->scr_pnb;
+        const size_t persons = (size_t)sp.E * sp.P;
+        up.person_blocks = (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
+        const int firm_blocks = (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
+        ks.update<<<up.person_blocks + firm_blocks, kUpdateThreads, 0, stream>>>(up);
+        FASTACE_CUDA_CHECK(cudaGetLastError());
+        env->launches += 2;
+    }
     env->time += 1;
-    env->launches += 1;
     return FASTACE_OK;
 }
 

@@ -27,23 +27,9 @@
 #include <stdint.h>
 
 #include "../../include/fastace_b200.h"
+#include "common.cuh"
 
 namespace fastace {
-
-struct StepParams {
-    int E, P, F, S;
-    uint32_t flags;
-    uint32_t time_before;
-    fastace_state_t st;
-    fastace_actions_t ac;
-    fastace_step_out_t out;
-};
-
-constexpr double kEps = 1e-8;            // constants::eps (base/constants.h:9)
-constexpr double kLargeNumber = 1e8;     // constants::largeNumber (base/constants.h:10)
-constexpr double kAmountPerOffer = 1.0;  // neural/neuralFirmDecisionMaker.cpp:6
-constexpr double kLaborPerOffer = 0.5;   // neural/neuralFirmDecisionMaker.cpp:7
-constexpr int kNone = 0xFF;
 
 // shared-memory carve-up for one economy (sizes in bytes, 8-aligned sections)
 struct SmemLayout {
@@ -51,15 +37,9 @@ struct SmemLayout {
     int off_mleft, off_mtaken, off_jleft, off_jtaken, off_fnh, off_fok; // u32
     int off_permp, off_permf;                                                    // u16
     int off_att, off_fatt, off_mowner, off_mgood, off_jowner, off_pnh, off_pnb, off_ffirst, off_fcnt; // u8
-    // lane-parallel matching (kernel v2)
-    int off_cnt, off_room;      // u8  [F*(G+1)][kRowStride]: per offer, per lane of the window
-    int off_dord, off_tot;      // i32 [F*(G+1)]: death ordinal / eligible total of the last evaluation
-    int off_fjob;               // u8  [F]: job-book slot of the firm's job offer, or kNone
     int att_stride;             // bytes per person in s_att: jobs at [0,S4), goods at [S4,2*S4)
     int total;
 };
-
-constexpr int kRowStride = 36;  // bytes per cell row: 9 words -> rows of consecutive offers start in distinct banks
 
 __host__ __device__ inline SmemLayout make_layout(int P, int F, int G, int S) {
     SmemLayout L;
@@ -90,53 +70,8 @@ __host__ __device__ inline SmemLayout make_layout(int P, int F, int G, int S) {
     L.off_pnb = take(G * P);
     L.off_ffirst = take(F);
     L.off_fcnt = take(F);
-    L.off_cnt = take(kRowStride * F * (G + 1));
-    L.off_room = take(kRowStride * F * (G + 1));
-    L.off_dord = take(4 * F * (G + 1));
-    L.off_tot = take(4 * F * (G + 1));
-    L.off_fjob = take(F);
     L.total = o;
     return L;
-}
-
-// (int)double as the x86-64 reference binary does it (cvttsd2si): out-of-range and NaN
-// give INT_MIN, which fails the `numOffers > 0` tests.
-__device__ __forceinline__ int x86_double_to_int(double x) {
-    if (!(x > -2147483649.0 && x < 2147483648.0)) return INT32_MIN;
-    return __double2int_rz(x);
-}
-
-// Index mapping (decisionNetHandler.cpp:327-365 draws indices in [0,count)).  The modulo uses a
-// per-economy precomputed magic (Lemire's fastmod: exact for every 32-bit numerator).
-struct IndexMap {
-    uint64_t magic;
-    uint32_t count;
-    bool modulo;
-    __device__ __forceinline__ IndexMap(int cnt, uint32_t flags)
-        : magic(cnt > 0 ? 0xFFFFFFFFFFFFFFFFull / (uint32_t)cnt + 1ull : 0ull), count(cnt > 0 ? (uint32_t)cnt : 0u),
-          modulo((flags & FASTACE_IDX_MODULO) != 0) {}
-    __device__ __forceinline__ int operator()(int raw) const {
-        if (count == 0) return kNone;
-        if (modulo) return (int)__umul64hi(magic * (uint64_t)(uint32_t)raw, (uint64_t)count);
-        return ((uint32_t)raw >= count) ? kNone : raw;
-    }
-};
-
-// pow for the reward path (1e-5 relative tolerance): exp(y*log(x)), fp64 throughout.
-// Relative error ~ |y ln x| * 2^-52, far inside the tolerance; ~3x cheaper than pow().
-__device__ __forceinline__ double pow_reward(double x, double y) { return exp(y * log(x)); }
-
-// One goods request by a buyer whose money/inventory live at (money, inv[g*istride]).
-// Agent::respond_to_offer -> review_offer_response -> accept_offer_response
-// (base/agent.cpp:99-161), fp64 updates in the reference's order.
-// optional outputs: per-request success flags of one person (jobs in bits 0..15, goods in 16..31)
-__device__ __forceinline__ void write_person_ok(const StepParams& p, int e, int pid, uint32_t okm) {
-    if (p.out.p_job_ok == nullptr && p.out.p_good_ok == nullptr) return;
-    for (int i = 0; i < p.S; i++) {
-        const size_t k = ((size_t)e * p.S + i) * p.P + pid;
-        if (p.out.p_job_ok) p.out.p_job_ok[k] = (okm >> i) & 1u;
-        if (p.out.p_good_ok) p.out.p_good_ok[k] = (okm >> (16 + i)) & 1u;
-    }
 }
 
 template <int G>
@@ -163,18 +98,10 @@ __device__ __forceinline__ bool request_good(int n, double& money, double* s_fmo
     return true;
 }
 
-// floor(x) as a lot count: how many times `inventory >= 1.0; inventory -= 1.0` succeeds
-// (agent.cpp:140,156; the subtraction is exact for x < 2^53).  NaN never compares "short".
-__device__ __forceinline__ uint32_t unit_sales_possible(double x) {
-    if (x < 1.0) return 0u;
-    if (!(x < 4294967296.0)) return 0xFFFFFFFFu;
-    return (uint32_t)x;
-}
-
-// kParallel = false: kernel v1, persons matched by a serial walk on lane 0 (strict fp64 order
-//                    for firm money as well).
-// kParallel = true : kernel v2, lanes = persons, exact fixed-point matching (see phase 1).
-template <int G, bool kParallel>
+// Fused single-kernel step with SERIAL matching (kernel v1, FASTACE_STEP_SERIAL): persons and
+// firms are matched by a walk on lane 0, every fp64 update (firm money included) in exactly the
+// reference's order.  The default path is match_kernel + update_kernel (match_update_kernels.cuh).
+template <int G>
 __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int e = blockIdx.x;
@@ -205,11 +132,6 @@ __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
     uint8_t* s_pnb = smem + L.off_pnb;
     uint8_t* s_ffirst = smem + L.off_ffirst;
     uint8_t* s_fcnt = smem + L.off_fcnt;
-    uint8_t* s_cnt = smem + L.off_cnt;
-    uint8_t* s_room = smem + L.off_room;
-    int32_t* s_dord = reinterpret_cast<int32_t*>(smem + L.off_dord);
-    int32_t* s_tot = reinterpret_cast<int32_t*>(smem + L.off_tot);
-    uint8_t* s_fjob = smem + L.off_fjob;
     const int AS = L.att_stride, S4 = AS >> 1;
 
     const size_t eP = (size_t)e * P, eF = (size_t)e * F, eCap = (size_t)e * cap;
@@ -219,6 +141,7 @@ __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
     // ------------------------------ phase 0: stage ------------------------------------
     {
         const IndexMap mapJ(NJ, p.flags), mapM(NM, p.flags);
+        const bool hasJ = NJ > 0, hasM = NM > 0;
         for (int pid = lane; pid < P; pid += 32) {
             s_pmoney[pid] = p.st.p_money[eP + pid];
             s_permp[pid] = (uint16_t)p.ac.perm_person[eP + pid];
@@ -232,9 +155,9 @@ __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
             const uint8_t* gt = p.ac.p_good_take + k0;
             uint8_t* att = s_att + pid * AS;
             for (int i = 0; i < S; i++) {
-                const int j = mapJ(ji[(size_t)i * P]), g = mapM(gi[(size_t)i * P]);
-                att[i] = (uint8_t)(jt[(size_t)i * P] ? j : kNone);
-                att[S4 + i] = (uint8_t)(gt[(size_t)i * P] ? g : kNone);
+                const int j = hasJ ? mapJ(ji[(size_t)i * P]) : kNone, g = hasM ? mapM(gi[(size_t)i * P]) : kNone;
+                att[i] = (uint8_t)((jt[(size_t)i * P] && hasJ) ? j : kNone);
+                att[S4 + i] = (uint8_t)((gt[(size_t)i * P] && hasM) ? g : kNone);
             }
             for (int i = S; i < S4; i++) { att[i] = (uint8_t)kNone; att[S4 + i] = (uint8_t)kNone; }
         }
@@ -245,12 +168,11 @@ __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
             s_fok[f] = 0;
             s_fcnt[f] = 0;
             s_ffirst[f] = 0;
-            s_fjob[f] = (uint8_t)kNone;
 #pragma unroll
             for (int g = 0; g < G; g++) s_finv[g * F + f] = p.st.f_inv[((size_t)e * G + g) * F + f];
             const size_t k0 = (size_t)e * S * F + f;
             for (int i = 0; i < S; i++) {
-                const int g = mapM(p.ac.f_good_idx[k0 + (size_t)i * F]);
+                const int g = hasM ? mapM(p.ac.f_good_idx[k0 + (size_t)i * F]) : kNone;
                 s_fatt[f * S + i] = (uint8_t)(p.ac.f_good_take[k0 + (size_t)i * F] ? g : kNone);
             }
         }
@@ -261,15 +183,7 @@ __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
         s_jtaken[n] = p.st.j_taken[eF + n];
         s_jwage[n] = p.st.j_wage[eF + n];
     }
-    if (kParallel) {
-        uint32_t* cz = reinterpret_cast<uint32_t*>(s_cnt);
-        uint32_t* rz = reinterpret_cast<uint32_t*>(s_room);
-        const int words = (kRowStride / 4) * (NJ + NM);
-        for (int k = lane; k < words; k += 32) { cz[k] = 0u; rz[k] = 0u; }
-    }
     __syncwarp();
-    if (kParallel)
-        for (int n = lane; n < NJ; n += 32) s_fjob[s_jowner[n]] = (uint8_t)n;
     for (int n = lane; n < NM; n += 32) {
         const int owner = p.st.m_owner[eCap + n];
         s_mowner[n] = (uint8_t)owner;
@@ -291,221 +205,8 @@ __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
     __syncwarp();
 
     // ------------------------------ phase 1: persons ----------------------------------
-    // kernel v2 (kParallel): lanes = persons.  A window of 32 persons with consecutive visiting
-    // ranks evaluates its whole request chains in parallel.  For every offer R the ordinal
-    // number of an ELIGIBLE request (person-side check passed: person.cpp:39 / agent.cpp:102) is
-    //     ord = (# eligible requests on R by lower lanes of the window) + (own earlier ones)
-    // and the request succeeds iff ord < D[R], the offer's death ordinal:
-    //     job offer   : lots left (firm.cpp:64), lowered to the first request its firm cannot pay
-    //                   (firm.cpp:80-84: that request kills the offer);
-    //     goods offer : min(lots left, floor(seller inventory)) (agent.cpp:124,140-143).
-    // Offers only ever lose availability, so the serial first-come-first-served outcome is the
-    // unique fixed point of (prefix counts, D).  It is reached by iterating
-    //     evaluate (lanes = persons)  ->  prefix scan (lanes = offers)  ->  evaluate ...
-    // Per (offer, lane) two bytes live in shared memory: cnt = eligible requests of that lane in
-    // the current evaluation, room = clamp(D - prefix, 0, 31) = how many of them can succeed.
-    // The iteration stops as soon as min(cnt, room) is unchanged for every cell: the next
-    // evaluation would then reproduce this one, so this one already is the fixed point.
-    // Lane k is exact after k+2 rounds at the latest; in practice 2-3 rounds per window.
-    // Person money is accumulated in the person's own request order (bit-exact); a firm's money
-    // is updated once per window as M - wage*hires + sum price*sales (same value up to fp64
-    // rounding order).
-    if (kParallel) {
-        const int NR = NJ + NM;
-        for (int base = 0; base < P; base += 32) {
-            const int r = base + lane;
-            const bool active = r < P;
-            const int pid = active ? (int)s_permp[r] : 0;
-            const double money0 = active ? s_pmoney[pid] : 0.0;
-            const uint32_t* attw = reinterpret_cast<const uint32_t*>(s_att + pid * AS);
-            for (int R = lane; R < NR; R += 32) {
-                uint32_t d;
-                if (R < NJ) {
-                    d = s_jleft[R];
-                } else {
-                    const int o = R - NJ, sel = s_mowner[o], good = s_mgood[o];
-                    d = min(s_mleft[o], unit_sales_possible(s_finv[good * F + sel]));
-#pragma unroll
-                    for (int g = 0; g < G; g++)
-                        if (g != good && s_finv[g * F + sel] < 0.0) d = 0;  // agent.cpp:140 on a zero quantity
-                }
-                const int di = (int)min(d, 0x7FFFFFFFu);
-                s_dord[R] = di;
-                // initial guess for the window: no lower lane is eligible for anything
-                uint32_t* rr = reinterpret_cast<uint32_t*>(s_room + R * kRowStride);
-                const uint32_t rm = (uint32_t)min(di, 31) * 0x01010101u;
-#pragma unroll
-                for (int k = 0; k < 8; k++) rr[k] = rm;
-            }
-            __syncwarp();
-            double money = money0;
-            int nh = 0;
-            uint32_t okm = 0;
-            for (int round = 0; round < 80; round++) {
-                // ---- evaluate the window's request chains against room[][]
-                money = money0; nh = 0; okm = 0;
-                if (active) {
-                    uint32_t w = 0;
-                    for (int i = 0; i < S; i++) {                       // utilMaxer.cpp:76-85
-                        if ((i & 3) == 0) w = attw[i >> 2];
-                        const int n = (int)(w & 0xFFu);
-                        w >>= 8;
-                        if (n != kNone && nh < 2) {                     // person.cpp:39 (0.5*nh + 0.5 <= 1)
-                            const int a = n * kRowStride + lane;
-                            const uint32_t c = s_cnt[a];
-                            s_cnt[a] = (uint8_t)(c + 1u);
-                            if (c < s_room[a]) {
-                                nh++;
-                                money += s_jwage[n];                    // person.cpp:49
-                                okm |= 1u << i;
-                            }
-                        }
-                    }
-                    const uint32_t* gw = attw + (S4 >> 2);
-                    for (int i = 0; i < S; i++) {                       // utilMaxer.cpp:64-73
-                        if ((i & 3) == 0) w = gw[i >> 2];
-                        const int n = (int)(w & 0xFFu);
-                        w >>= 8;
-                        if (n != kNone) {
-                            const double price = s_mprice[n];
-                            if (money >= price) {                       // agent.cpp:102
-                                const int a = (NJ + n) * kRowStride + lane;
-                                const uint32_t c = s_cnt[a];
-                                s_cnt[a] = (uint8_t)(c + 1u);
-                                if (c < s_room[a]) {
-                                    money -= price;                     // agent.cpp:108
-                                    okm |= 1u << (16 + i);
-                                }
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                // ---- lanes = offers: prefix of the eligible counts over the window's lanes -> room
-                bool changed = false;
-                for (int R = lane; R < NR; R += 32) {
-                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(s_cnt + R * kRowStride);
-                    uint32_t* rw = reinterpret_cast<uint32_t*>(s_room + R * kRowStride);
-                    const int d = s_dord[R];
-                    int run = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const uint32_t cv = cw[k], ro = rw[k];
-                        uint32_t rn = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            const int c = (int)((cv >> (8 * b)) & 0xFFu);
-                            const int oldroom = (int)((ro >> (8 * b)) & 0xFFu);
-                            const int room = max(0, min(31, d - run));
-                            changed |= min(c, room) != min(c, oldroom);
-                            rn |= (uint32_t)room << (8 * b);
-                            run += c;
-                        }
-                        rw[k] = rn;
-                    }
-                    s_tot[R] = run;
-                }
-                __syncwarp();
-                // ---- job offers whose firm may run out of money: first request it cannot pay
-                for (int R = lane; R < NJ; R += 32) {
-                    const uint32_t left = s_jleft[R];
-                    const int f = s_jowner[R];
-                    const double w = s_jwage[R], m0 = s_fmoney[f];
-                    const int tot = s_tot[R];
-                    int d = (int)min(left, 0x7FFFFFFFu);
-                    const int most = min(d, tot);
-                    if (!(m0 - w * (double)most >= w * (1.0 + 1e-9))) {
-                        const uint8_t* row = s_cnt + R * kRowStride;
-                        const int first = s_ffirst[f], cnt = s_fcnt[f];
-                        int pre[G];          // eligible requests on the firm's own goods offers by lower lanes
-#pragma unroll
-                        for (int g = 0; g < G; g++) pre[g] = 0;
-                        int h = 0;
-                        bool done = false;
-                        for (int l = 0; l < 32 && !done; l++) {
-                            const int c = row[l];
-                            if (c != 0) {
-                                double sales = 0.0;   // income from goods sold to lower lanes of this window
-#pragma unroll
-                                for (int g = 0; g < G; g++)
-                                    if (g < cnt) sales += s_mprice[first + g] * (double)min(pre[g], s_dord[NJ + first + g]);
-                                for (int k = 0; k < c; k++) {
-                                    if (h >= d) { done = true; break; }                                  // firm.cpp:64
-                                    if ((m0 + sales) - w * (double)h < w) { d = h; done = true; break; } // firm.cpp:80
-                                    h++;
-                                }
-                            }
-#pragma unroll
-                            for (int g = 0; g < G; g++)
-                                if (g < cnt) pre[g] += s_cnt[(NJ + first + g) * kRowStride + l];
-                        }
-                    }
-                    if (d != s_dord[R]) {
-                        // the offer dies earlier/later than assumed: redo its row with the new ordinal
-                        changed = true;
-                        s_dord[R] = d;
-                        const uint8_t* row = s_cnt + R * kRowStride;
-                        uint8_t* rrow = s_room + R * kRowStride;
-                        int run = 0;
-                        for (int l = 0; l < 32; l++) { rrow[l] = (uint8_t)max(0, min(31, d - run)); run += row[l]; }
-                    }
-                }
-                const bool again = __any_sync(0xffffffffu, changed);
-                __syncwarp();
-                {
-                    uint32_t* cz = reinterpret_cast<uint32_t*>(s_cnt);
-                    const int words = (kRowStride / 4) * NR;
-                    for (int k = lane; k < words; k += 32) cz[k] = 0u;
-                }
-                __syncwarp();
-                if (!again) break;
-            }
-            // ---- commit the window
-            if (active) {
-                s_pmoney[pid] = money;
-                s_pnh[pid] = (uint8_t)nh;
-                write_person_ok(p, e, pid, okm);
-                const uint8_t* ga = s_att + pid * AS + S4;
-                for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {
-                    const int i = __ffs(m) - 1;
-                    s_pnb[s_mgood[ga[i]] * P + pid] += 1;
-                }
-            }
-            for (int R = lane; R < NR; R += 32) {
-                const int tot = s_tot[R];
-                const int n = min(tot, s_dord[R]);
-                if (R < NJ) {
-                    const uint32_t left = s_jleft[R];
-                    s_jleft[R] = (tot > n) ? 0u : left - (uint32_t)n;   // exhausted or killed (firm.cpp:83)
-                    s_jtaken[R] += (uint32_t)n;
-                } else {
-                    const int o = R - NJ;
-                    uint32_t left = s_mleft[o] - (uint32_t)n;
-                    if (tot > n && left > 0) left = 0;                  // killed (agent.cpp:143)
-                    s_mleft[o] = left;
-                    s_mtaken[o] += (uint32_t)n;
-                    s_finv[s_mgood[o] * F + s_mowner[o]] -= (double)n;   // n exact unit subtractions
-                }
-                s_tot[R] = n;
-            }
-            __syncwarp();
-            for (int f = lane; f < F; f += 32) {
-                double m = s_fmoney[f];
-                const int j = s_fjob[f];
-                if (j != kNone) {
-                    const int h = s_tot[j];
-                    m = m - s_jwage[j] * (double)h;
-                    s_fnh[f] += (uint32_t)h;
-                }
-                const int first = s_ffirst[f], cnt = s_fcnt[f];
-                for (int o = first; o < first + cnt; o++) m = m + s_mprice[o] * (double)s_tot[NJ + o];
-                s_fmoney[f] = m;
-            }
-            __syncwarp();
-        }
-    }
     // kernel v1: serial walk
-    if (!kParallel && lane == 0) {
+    if (lane == 0) {
         for (int r = 0; r < P; r++) {
             const int pid = s_permp[r];
             double money = s_pmoney[pid];

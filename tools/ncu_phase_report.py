@@ -4,11 +4,11 @@ usage: ncu -i X.ncu-rep --page source --print-source cuda,sass --csv > src.csv ;
 import bisect, csv, sys, os
 path = sys.argv[1]
 rows = list(csv.reader(open(path)))
-src_file = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fastace_b200/csrc/step_kernel.cuh")
+fname = [a for a in sys.argv[2:] if a.endswith(".cuh")]
+fname = fname[0] if fname else "match_update_kernels.cuh"
+src_file = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fastace_b200/csrc", fname)
 src = open(src_file).read().split("\n")
-keys = ("phase 0: stage", "phase 1: persons", "---- evaluate", "---- lanes = offers", "---- job offers whose", "---- commit the window",
-        "kernel v1: serial walk", "phase 2: consume", "phase 3: firms", "phase 4: produce")
-marks = [(i + 1, l.strip()[:70]) for i, l in enumerate(src) if any(k in l for k in keys)]
+marks = [(i + 1, l.strip()[:70]) for i, l in enumerate(src) if l.strip().startswith("// ----")]
 bounds = [m[0] for m in marks]
 cur_file = None
 agg, other, lines = {}, {}, {}
@@ -24,7 +24,7 @@ for r in rows:
         ln, v, s = int(r[0]), int(r[ie]), int(r[smp])
     except ValueError:
         continue
-    if cur_file and cur_file.endswith("step_kernel.cuh"):
+    if cur_file and cur_file.endswith(fname):
         k = bisect.bisect_right(bounds, ln) - 1
         name = marks[k][1] if k >= 0 else "helpers (top of file)"
         if k < 0:
