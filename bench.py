@@ -43,6 +43,10 @@ ECON_PER_GPU = 4096
 BYTES_PERSON = (36 + 20 * G + 10 * S) + (24 + 8 * G)
 BYTES_FIRM = (52 + 60 * G + 8 * G * G + 5 * S) + (36 + 20 * G)
 BYTES_PER_ECON_STEP = P * BYTES_PERSON + F * BYTES_FIRM
+# share of those bytes that the dominant kernel (match_kernel) moves: per person
+# money 8 + orders 10S + rank 4 read, money 8 written; per firm money 8 + inventory 8G + laborHired 8 +
+# orders 5S + rank 4 + own offers 16G + job offer 24 read, money 8 + reward 8 written
+BYTES_MATCH_PER_ECON_STEP = P * (8 + 10 * S + 4 + 8) + F * (8 + 8 * G + 8 + 5 * S + 4 + 16 * G + 24 + 16)
 METRIC = "agent-steps/sec"
 
 
@@ -242,43 +246,87 @@ def run_ours(args):
     agent_steps = world * E * (P + F) * args.steps
     value = agent_steps / (total_ms_max * 1e-3)
 
-    # ---- end to end through the host-pointer C ABI call (pinned host buffers) ------------
+    # ---- per-kernel device time (CUDA events inside the library, FASTACE_STEP_PROFILE) ------
+    env.kernel_times()
+    for i in range(min(args.steps, EPISODE)):
+        if i % EPISODE == 0:
+            reset_state(i)
+        if not args.no_flush:
+            flush.zero_()
+        env.time_step(dacts[i % EPISODE], dout, flags=_abi.IDX_MODULO | _abi.STEP_PROFILE)
+    match_ms, update_ms, prof_steps = env.kernel_times()
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers) -------------------
+    # The call a user with host arrays makes: fastace_env_step_host_compact with FASTACE_STEP_ASYNC
+    # (compact action encoding, copies of neighbouring steps overlap the kernels), fastace_env_sync at
+    # the end.  Every step's H2D of all action arrays and D2H of rewards + profits is inside the timed
+    # region.  The plain int32 encoding, synchronous, is timed as well ("e2e_int32_sync").
     e2e_steps = min(args.steps, EPISODE)
-    pinned = []
-    for a in acts[:e2e_steps]:
-        pa = {}
-        for k, v in a.items():
-            tt = torch.from_numpy(v).pin_memory()
-            pa[k] = tt.numpy()
-        pinned.append((pa, _abi.struct_from_numpy("actions", pa, env.dims)))
-    hout_t = {k: torch.zeros(shp, dtype=torch.float64).pin_memory() for k, (dt, shp) in _abi.shapes("out", env.dims).items()
-              if k in _abi.OUT_MANDATORY}
-    hout = {k: v.numpy() for k, v in hout_t.items()}
-    hout_s = _abi.struct_from_numpy("out", hout, env.dims)
-    h2d = int(sum(v.nbytes for v in acts[0].values()))
-    d2h = int(sum(v.nbytes for v in hout.values()))
+    st_host = {k: v.copy() for k, v in state.items()}
+    # compact encoding needs the book sizes of each step: replay them once with the device path
     reset_state(0)
-    torch.cuda.synchronize()
-    for k in range(min(3, e2e_steps)):
-        env.time_step_host(pinned[k][1], hout_s, flags=_abi.IDX_MODULO)
-    reset_state(0)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0 = time.perf_counter()
+    counts = []
     for k in range(e2e_steps):
-        env.time_step_host(pinned[k][1], hout_s, flags=_abi.IDX_MODULO)  # synchronises internally
+        cnt = env.get_state(names=("j_count", "m_count"))
+        counts.append((cnt["j_count"].copy(), cnt["m_count"].copy()))
+        env.time_step(dacts[k], dout, flags=_abi.IDX_MODULO)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - e0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * E * (P + F) * e2e_steps / float(t_e.item())
+
+    def pin(d):
+        out = {}
+        for k, v in d.items():
+            a = np.ascontiguousarray(v)
+            view16 = a.dtype == np.uint16
+            t = torch.from_numpy(a.view(np.int16) if view16 else a).pin_memory()
+            out[k] = t.numpy().view(np.uint16) if view16 else t.numpy()
+        return out
+
+    pinned_c, pinned_i = [], []
+    for k in range(e2e_steps):
+        cz = pin(_abi.compact_actions_for_counts(acts[k], counts[k][0], counts[k][1], True))
+        pinned_c.append((cz, _abi.struct_from_numpy("compact", cz, env.dims)))
+    for k in range(min(e2e_steps, 10)):
+        pa = pin(acts[k])
+        pinned_i.append((pa, _abi.struct_from_numpy("actions", pa, env.dims)))
+    houts = []
+    for k in range(e2e_steps):
+        ho = pin({n: np.zeros(shp, dtype=np.float64) for n, (dt, shp) in _abi.shapes("out", env.dims).items()
+                  if n in _abi.OUT_MANDATORY})
+        houts.append((ho, _abi.struct_from_numpy("out", ho, env.dims)))
+    h2d = int(sum(v.nbytes for v in pinned_c[0][0].values()))
+    h2d_int32 = int(sum(v.nbytes for v in acts[0].values()))
+    d2h = int(sum(v.nbytes for v in houts[0][0].values()))
+
+    def run_e2e(structs, flags, n):
+        reset_state(0)
+        torch.cuda.synchronize()
+        for k in range(min(3, n)):  # warm-up (allocates the staging buffers)
+            env.time_step_host(structs[k][1], houts[k][1], flags=flags)
+        env.sync()
+        reset_state(0)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(n):
+            env.time_step_host(structs[k][1], houts[k][1], flags=flags)
+        env.sync()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        return world * E * (P + F) * n / float(t_e.item())
+
+    e2e_value = run_e2e(pinned_c, _abi.IDX_MODULO | _abi.STEP_ASYNC, e2e_steps)
+    e2e_int32 = run_e2e(pinned_i, _abi.IDX_MODULO, len(pinned_i))
 
     if rank == 0:
         peak, peak_src = peaks()
-        avg_launch_s = total_ms / args.steps * 1e-3  # rank 0's own launches
-        achieved = BYTES_PER_ECON_STEP * E / avg_launch_s / 1e9
+        avg_step_s = total_ms / args.steps * 1e-3  # rank 0's own steps
+        step_achieved = BYTES_PER_ECON_STEP * E / avg_step_s / 1e9
+        match_s = match_ms / max(prof_steps, 1) * 1e-3
+        update_s = update_ms / max(prof_steps, 1) * 1e-3
+        achieved = BYTES_MATCH_PER_ECON_STEP * E / match_s / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -291,11 +339,19 @@ def run_ours(args):
                 "wall_s_including_flushes": wall,
             },
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "fastace_env_step_host_compact + FASTACE_STEP_ASYNC, fastace_env_sync at the end (pinned host buffers)"},
+            "e2e_int32_sync": {"value": e2e_int32, "unit": METRIC, "h2d_bytes_per_step": h2d_int32, "d2h_bytes_per_step": d2h,
+                               "api": "fastace_env_step_host (int32 indices, u8 flags), synchronous"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "peak_source": peak_src,
-                         "kernel": "fastace::step_kernel<2>", "algorithmic_bytes_per_launch": BYTES_PER_ECON_STEP * E},
+                         "kernel": "fastace::match_kernel<2,12> (dominant: %.0f%% of the step's device time)" % (100 * match_s / max(match_s + update_s, 1e-12)),
+                         "algorithmic_bytes_per_launch": BYTES_MATCH_PER_ECON_STEP * E,
+                         "launch_ms": match_s * 1e3,
+                         "step": {"kernels": {"match_kernel_ms": match_s * 1e3, "update_kernel_ms": update_s * 1e3},
+                                  "algorithmic_bytes_per_step": BYTES_PER_ECON_STEP * E, "achieved": step_achieved,
+                                  "frac": step_achieved / peak}},
         }
         if world == 1 and not args.no_cpu:
             base = cpu_baseline(args.cpu_sample, EPISODE)

@@ -13,6 +13,8 @@ FASTACE_OK = 0
 IDX_ABSOLUTE = 0
 IDX_MODULO = 1
 STEP_SERIAL = 2
+STEP_PROFILE = 4
+STEP_ASYNC = 8
 MAX_GOODS = 8
 MAX_STACK = 16
 
@@ -21,6 +23,7 @@ _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)
 _up = C.POINTER(C.c_uint32)
 _bp = C.POINTER(C.c_uint8)
+_hp = C.POINTER(C.c_uint16)
 
 
 class Dims(C.Structure):
@@ -86,6 +89,24 @@ ACTION_FIELDS = [
     ("f_job_wage", _fp, np.float32, lambda E, P, F, G, S: (E, F)),
 ]
 
+# fastace_actions_compact_t: one-byte indices, bit-mask takes, 16-bit orders
+COMPACT_FIELDS = [
+    ("perm_person", _hp, np.uint16, lambda E, P, F, G, S: (E, P)),
+    ("perm_firm", _hp, np.uint16, lambda E, P, F, G, S: (E, F)),
+    ("p_job_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, S, P)),
+    ("p_job_take", _hp, np.uint16, lambda E, P, F, G, S: (E, P)),
+    ("p_good_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, S, P)),
+    ("p_good_take", _hp, np.uint16, lambda E, P, F, G, S: (E, P)),
+    ("p_consume", _fp, np.float32, lambda E, P, F, G, S: (E, G, P)),
+    ("f_good_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, S, F)),
+    ("f_good_take", _hp, np.uint16, lambda E, P, F, G, S: (E, F)),
+    ("f_prod", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
+    ("f_offer_amt", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
+    ("f_offer_price", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
+    ("f_job_labor", _fp, np.float32, lambda E, P, F, G, S: (E, F)),
+    ("f_job_wage", _fp, np.float32, lambda E, P, F, G, S: (E, F)),
+]
+
 OUT_FIELDS = [
     ("p_reward", _dp, np.float64, lambda E, P, F, G, S: (E, P)),
     ("f_profit", _dp, np.float64, lambda E, P, F, G, S: (E, F)),
@@ -106,6 +127,10 @@ class State(C.Structure):
 
 class Actions(C.Structure):
     _fields_ = [(n, t) for n, t, _, _ in ACTION_FIELDS]
+
+
+class ActionsCompact(C.Structure):
+    _fields_ = [(n, t) for n, t, _, _ in COMPACT_FIELDS]
 
 
 class StepOut(C.Structure):
@@ -148,7 +173,7 @@ class TrainingParams(C.Structure):
 
 
 def field_table(kind):
-    return {"state": STATE_FIELDS, "actions": ACTION_FIELDS, "out": OUT_FIELDS}[kind]
+    return {"state": STATE_FIELDS, "actions": ACTION_FIELDS, "compact": COMPACT_FIELDS, "out": OUT_FIELDS}[kind]
 
 
 def shapes(kind, dims):
@@ -169,7 +194,7 @@ def alloc_host(kind, dims, names=None):
 def struct_from_numpy(kind, arrays, dims=None):
     """Build the ctypes struct from a dict of numpy arrays (missing names -> NULL).
     Arrays must be C-contiguous with the exact dtype; shapes are checked when dims given."""
-    cls = {"state": State, "actions": Actions, "out": StepOut}[kind]
+    cls = {"state": State, "actions": Actions, "compact": ActionsCompact, "out": StepOut}[kind]
     s = cls()
     shp = shapes(kind, dims) if dims is not None else None
     for n, ptr_t, dt, _ in field_table(kind):
@@ -187,10 +212,43 @@ def struct_from_numpy(kind, arrays, dims=None):
 
 def struct_from_pointers(kind, ptrs):
     """Build the ctypes struct from a dict name -> integer address (device pointers)."""
-    cls = {"state": State, "actions": Actions, "out": StepOut}[kind]
+    cls = {"state": State, "actions": Actions, "compact": ActionsCompact, "out": StepOut}[kind]
     s = cls()
     for n, ptr_t, _, _ in field_table(kind):
         p = ptrs.get(n)
         if p:
             setattr(s, n, C.cast(C.c_void_p(int(p)), ptr_t))
     return s
+
+
+def compact_actions_for_counts(actions, j_count, m_count, modulo):
+    """Same decisions in the compact encoding, given the current book sizes ([E] arrays).
+    modulo: the byte stored is (raw % count) so that byte % count == raw % count.
+    absolute: out-of-range / negative indices become 255 (no request)."""
+    a = actions
+    E = a["perm_person"].shape[0]
+    jc = np.asarray(j_count, dtype=np.int64).reshape(E, 1, 1)
+    mc = np.asarray(m_count, dtype=np.int64).reshape(E, 1, 1)
+
+    def idx8(raw, cnt):
+        raw = raw.astype(np.int64)
+        if modulo:
+            u = raw & 0xFFFFFFFF
+            return np.where(cnt > 0, u % np.maximum(cnt, 1), 0).astype(np.uint8)
+        ok = (raw >= 0) & (raw < cnt)
+        return np.where(ok, raw, 255).astype(np.uint8)
+
+    def mask16(take):  # [E][S][N] u8 -> [E][N] u16
+        S = take.shape[1]
+        w = (1 << np.arange(S, dtype=np.uint32)).reshape(1, S, 1)
+        return ((take != 0).astype(np.uint32) * w).sum(axis=1).astype(np.uint16)
+
+    out = {
+        "perm_person": a["perm_person"].astype(np.uint16), "perm_firm": a["perm_firm"].astype(np.uint16),
+        "p_job_idx": idx8(a["p_job_idx"], jc), "p_job_take": mask16(a["p_job_take"]),
+        "p_good_idx": idx8(a["p_good_idx"], mc), "p_good_take": mask16(a["p_good_take"]),
+        "f_good_idx": idx8(a["f_good_idx"], mc), "f_good_take": mask16(a["f_good_take"]),
+    }
+    for k in ("p_consume", "f_prod", "f_offer_amt", "f_offer_price", "f_job_labor", "f_job_wage"):
+        out[k] = a[k]
+    return {k: np.ascontiguousarray(v) for k, v in out.items()}

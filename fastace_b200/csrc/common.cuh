@@ -11,10 +11,16 @@ struct StepParams {
     int E, P, F, S;
     uint32_t flags;
     uint32_t time_before;
+    int compact;                    // 1: decisions come from `cz` (index/take/order arrays) + the float arrays of `ac`
     fastace_state_t st;
-    fastace_actions_t ac;
+    fastace_actions_t ac;           // continuous actions are always read from here
+    fastace_actions_compact_t cz;
     fastace_step_out_t out;
 };
+
+__device__ __forceinline__ int perm_firm_at(const StepParams& p, size_t k) {
+    return p.compact ? (int)p.cz.perm_firm[k] : p.ac.perm_firm[k];
+}
 
 constexpr double kEps = 1e-8;            // constants::eps (base/constants.h:9)
 constexpr double kLargeNumber = 1e8;     // constants::largeNumber (base/constants.h:10)

@@ -73,6 +73,26 @@ static std::vector<FieldDesc> action_fields(const fastace_dims_t& d) {
     };
 }
 
+static std::vector<FieldDesc> compact_fields(const fastace_dims_t& d) {
+    const size_t E = d.num_econ, P = d.num_persons, F = d.num_firms, G = d.num_goods, S = d.stack_size;
+    return {
+        {offsetof(fastace_actions_compact_t, perm_person), 2, E * P},
+        {offsetof(fastace_actions_compact_t, perm_firm), 2, E * F},
+        {offsetof(fastace_actions_compact_t, p_job_idx), 1, E * S * P},
+        {offsetof(fastace_actions_compact_t, p_job_take), 2, E * P},
+        {offsetof(fastace_actions_compact_t, p_good_idx), 1, E * S * P},
+        {offsetof(fastace_actions_compact_t, p_good_take), 2, E * P},
+        {offsetof(fastace_actions_compact_t, p_consume), 4, E * G * P},
+        {offsetof(fastace_actions_compact_t, f_good_idx), 1, E * S * F},
+        {offsetof(fastace_actions_compact_t, f_good_take), 2, E * F},
+        {offsetof(fastace_actions_compact_t, f_prod), 4, E * G * F},
+        {offsetof(fastace_actions_compact_t, f_offer_amt), 4, E * G * F},
+        {offsetof(fastace_actions_compact_t, f_offer_price), 4, E * G * F},
+        {offsetof(fastace_actions_compact_t, f_job_labor), 4, E * F},
+        {offsetof(fastace_actions_compact_t, f_job_wage), 4, E * F},
+    };
+}
+
 static std::vector<FieldDesc> out_fields(const fastace_dims_t& d) {
     const size_t E = d.num_econ, P = d.num_persons, F = d.num_firms, G = d.num_goods, S = d.stack_size;
     const size_t cap = F * G;
@@ -105,16 +125,27 @@ struct fastace_env {
     uint64_t launches;
     void* state_block;      // one allocation holding every state array
     fastace_state_t dstate; // device pointers into state_block
-    // staging for fastace_env_step_host
-    void* act_block;
-    fastace_actions_t dact;
-    void* out_block;
-    fastace_step_out_t dout;
-    cudaStream_t stream;
+    // double-buffered device staging for the host-pointer calls
+    void* act_block[2];
+    fastace_actions_t dact[2];
+    void* cact_block[2];
+    fastace_actions_compact_t dcact[2];
+    void* out_block[2];
+    fastace_step_out_t dout[2];
+    cudaStream_t stream;        // kernels of the host-pointer calls
+    cudaStream_t copy_in, copy_out;
+    cudaEvent_t h2d_done[2], kern_done[2], d2h_done[2];
+    bool buf_used[2];
+    bool have_host_streams;
+    uint64_t host_steps;
     size_t smem_bytes;        // serial fused kernel
     size_t match_smem_bytes;  // match_kernel
     uint8_t* scr_pnh;         // [E][P]    match_kernel -> update_kernel
     uint8_t* scr_pnb;         // [E][G][P]
+    cudaEvent_t ev[3];        // FASTACE_STEP_PROFILE
+    bool have_ev;
+    double prof_match_ms, prof_update_ms;
+    uint64_t prof_steps;
 };
 
 #define FASTACE_CUDA_CHECK(expr)                                                              \
@@ -241,8 +272,16 @@ int fastace_env_destroy(fastace_env_t* env) {
     cudaSetDevice(env->device);
     if (env->stream) cudaStreamDestroy(env->stream);
     if (env->state_block) cudaFree(env->state_block);
-    if (env->act_block) cudaFree(env->act_block);
-    if (env->out_block) cudaFree(env->out_block);
+    for (int b = 0; b < 2; b++) {
+        if (env->act_block[b]) cudaFree(env->act_block[b]);
+        if (env->cact_block[b]) cudaFree(env->cact_block[b]);
+        if (env->out_block[b]) cudaFree(env->out_block[b]);
+    }
+    if (env->have_host_streams) {
+        cudaStreamDestroy(env->copy_in); cudaStreamDestroy(env->copy_out);
+        for (int b = 0; b < 2; b++) { cudaEventDestroy(env->h2d_done[b]); cudaEventDestroy(env->kern_done[b]); cudaEventDestroy(env->d2h_done[b]); }
+    }
+    if (env->have_ev) for (int i = 0; i < 3; i++) cudaEventDestroy(env->ev[i]);
     if (env->scr_pnh) cudaFree(env->scr_pnh);
     if (env->scr_pnb) cudaFree(env->scr_pnb);
     delete env;
@@ -291,21 +330,34 @@ int fastace_env_device_state(const fastace_env_t* env, fastace_state_t* out_devi
     return FASTACE_OK;
 }
 
-static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const fastace_step_out_t* dout,
-                       uint32_t flags, cudaStream_t stream) {
-    for (auto& f : action_fields(env->dims)) {
-        if (f.count && !member(dact, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
+static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const fastace_actions_compact_t* dcz,
+                       const fastace_step_out_t* dout, uint32_t flags, cudaStream_t stream) {
+    if (dcz) {
+        for (auto& f : compact_fields(env->dims))
+            if (f.count && !member(dcz, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
+        if (flags & FASTACE_STEP_SERIAL) { set_error("the serial kernel takes the int32 action encoding"); return FASTACE_ERR_INVALID; }
+    } else {
+        for (auto& f : action_fields(env->dims))
+            if (f.count && !member(dact, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
     }
     if ((env->dims.num_persons > 0 && !dout->p_reward) || !dout->f_profit) {
         set_error("out: p_reward and f_profit are mandatory");
         return FASTACE_ERR_INVALID;
     }
     StepParams sp;
+    std::memset(&sp, 0, sizeof(sp));
     sp.E = env->dims.num_econ; sp.P = env->dims.num_persons; sp.F = env->dims.num_firms; sp.S = env->dims.stack_size;
     sp.flags = flags;
     sp.time_before = env->time;
     sp.st = env->dstate;
-    sp.ac = *dact;
+    if (dcz) {
+        sp.compact = 1;
+        sp.cz = *dcz;
+        sp.ac.p_consume = dcz->p_consume; sp.ac.f_prod = dcz->f_prod; sp.ac.f_offer_amt = dcz->f_offer_amt;
+        sp.ac.f_offer_price = dcz->f_offer_price; sp.ac.f_job_labor = dcz->f_job_labor; sp.ac.f_job_wage = dcz->f_job_wage;
+    } else {
+        sp.ac = *dact;
+    }
     sp.out = *dout;
     const KernelSet ks = kernels_for_goods(env->dims.num_goods);
     if (flags & FASTACE_STEP_SERIAL) {
@@ -313,11 +365,18 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         FASTACE_CUDA_CHECK(cudaGetLastError());
         env->launches += 1;
     } else {
+        const bool prof = (flags & FASTACE_STEP_PROFILE) != 0;
+        if (prof && !env->have_ev) {
+            for (int i = 0; i < 3; i++) FASTACE_CUDA_CHECK(cudaEventCreate(&env->ev[i]));
+            env->have_ev = true;
+        }
         MatchParams mp;
         mp.sp = sp; mp.scr_pnh = env->scr_pnh; mp.scr_pnb = env->scr_pnb;
         mp.lay = make_match_layout(sp.P, sp.F, env->dims.num_goods, sp.S);
+        if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[0], stream));
         (sp.S <= 12 ? ks.match12 : ks.match16)<<<sp.E, 32, env->match_smem_bytes, stream>>>(mp);
         FASTACE_CUDA_CHECK(cudaGetLastError());
+        if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[1], stream));
         UpdateParams up;
         up.sp = sp; up.scr_pnh = env->scr_pnh; up.scr_pnb = env->scr_pnb;
         const size_t persons = (size_t)sp.E * sp.P;
@@ -326,6 +385,14 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         ks.update<<<up.person_blocks + firm_blocks, kUpdateThreads, 0, stream>>>(up);
         FASTACE_CUDA_CHECK(cudaGetLastError());
         env->launches += 2;
+        if (prof) {
+            FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[2], stream));
+            FASTACE_CUDA_CHECK(cudaEventSynchronize(env->ev[2]));
+            float a = 0.f, b = 0.f;
+            FASTACE_CUDA_CHECK(cudaEventElapsedTime(&a, env->ev[0], env->ev[1]));
+            FASTACE_CUDA_CHECK(cudaEventElapsedTime(&b, env->ev[1], env->ev[2]));
+            env->prof_match_ms += a; env->prof_update_ms += b; env->prof_steps += 1;
+        }
     }
     env->time += 1;
     return FASTACE_OK;
@@ -335,39 +402,107 @@ int fastace_env_step_device(fastace_env_t* env, const fastace_actions_t* actions
                             uint32_t flags, void* cuda_stream) {
     if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
     FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
-    return launch_step(env, actions, out, flags, static_cast<cudaStream_t>(cuda_stream));
+    return launch_step(env, actions, nullptr, out, flags, static_cast<cudaStream_t>(cuda_stream));
 }
+
+int fastace_env_step_device_compact(fastace_env_t* env, const fastace_actions_compact_t* actions,
+                                    const fastace_step_out_t* out, uint32_t flags, void* cuda_stream) {
+    if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+    return launch_step(env, nullptr, actions, out, flags, static_cast<cudaStream_t>(cuda_stream));
+}
+
+}  // extern "C"
+
+// Host-pointer step.  Pipeline per call (buffer b = call parity):
+//   copy_in : [wait kernels that last read buffer b] H2D of every action array -> h2d_done[b]
+//   stream  : [wait h2d_done[b], d2h_done[b]] match + update kernels            -> kern_done[b]
+//   copy_out: [wait kern_done[b]] D2H of the requested outputs                   -> d2h_done[b]
+// so with FASTACE_STEP_ASYNC the copies of neighbouring steps overlap the kernels.
+template <typename ActT>
+static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::vector<FieldDesc>& fields,
+                          ActT* dacts, void** blocks, bool compact, const fastace_step_out_t* out, uint32_t flags) {
+    FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+    if (!env->have_host_streams) {
+        FASTACE_CUDA_CHECK(cudaStreamCreateWithFlags(&env->copy_in, cudaStreamNonBlocking));
+        FASTACE_CUDA_CHECK(cudaStreamCreateWithFlags(&env->copy_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            FASTACE_CUDA_CHECK(cudaEventCreateWithFlags(&env->h2d_done[b], cudaEventDisableTiming));
+            FASTACE_CUDA_CHECK(cudaEventCreateWithFlags(&env->kern_done[b], cudaEventDisableTiming));
+            FASTACE_CUDA_CHECK(cudaEventCreateWithFlags(&env->d2h_done[b], cudaEventDisableTiming));
+        }
+        env->have_host_streams = true;
+    }
+    const int b = (int)(env->host_steps & 1);
+    if (!blocks[b]) {
+        int rc = carve(fields, &dacts[b], &blocks[b], false);
+        if (rc != FASTACE_OK) return rc;
+    }
+    if (!env->out_block[b]) {
+        int rc = carve(out_fields(env->dims), &env->dout[b], &env->out_block[b], false);
+        if (rc != FASTACE_OK) return rc;
+    }
+    for (auto& f : fields)
+        if (f.count && !member(actions, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
+    if (env->buf_used[b]) FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->copy_in, env->kern_done[b], 0));
+    for (auto& f : fields)
+        if (f.count)
+            FASTACE_CUDA_CHECK(cudaMemcpyAsync(member(&dacts[b], f.offset), member(actions, f.offset), f.elem * f.count,
+                                               cudaMemcpyHostToDevice, env->copy_in));
+    FASTACE_CUDA_CHECK(cudaEventRecord(env->h2d_done[b], env->copy_in));
+    FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->stream, env->h2d_done[b], 0));
+    if (env->buf_used[b]) FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->stream, env->d2h_done[b], 0));
+    fastace_step_out_t dout;
+    std::memset(&dout, 0, sizeof(dout));
+    for (auto& f : out_fields(env->dims))
+        if (member(out, f.offset)) member(&dout, f.offset) = member(&env->dout[b], f.offset);
+    int rc = compact ? launch_step(env, nullptr, reinterpret_cast<const fastace_actions_compact_t*>(&dacts[b]), &dout, flags, env->stream)
+                     : launch_step(env, reinterpret_cast<const fastace_actions_t*>(&dacts[b]), nullptr, &dout, flags, env->stream);
+    if (rc != FASTACE_OK) return rc;
+    FASTACE_CUDA_CHECK(cudaEventRecord(env->kern_done[b], env->stream));
+    FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->copy_out, env->kern_done[b], 0));
+    for (auto& f : out_fields(env->dims)) {
+        void* dst = member(out, f.offset);
+        if (dst && f.count)
+            FASTACE_CUDA_CHECK(cudaMemcpyAsync(dst, member(&env->dout[b], f.offset), f.elem * f.count,
+                                               cudaMemcpyDeviceToHost, env->copy_out));
+    }
+    FASTACE_CUDA_CHECK(cudaEventRecord(env->d2h_done[b], env->copy_out));
+    env->buf_used[b] = true;
+    env->host_steps += 1;
+    if (!(flags & FASTACE_STEP_ASYNC)) FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->copy_out));
+    return FASTACE_OK;
+}
+
+extern "C" {
 
 int fastace_env_step_host(fastace_env_t* env, const fastace_actions_t* actions, const fastace_step_out_t* out,
                           uint32_t flags) {
     if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    return step_host_impl(env, actions, action_fields(env->dims), env->dact, env->act_block, false, out, flags);
+}
+
+int fastace_env_step_host_compact(fastace_env_t* env, const fastace_actions_compact_t* actions,
+                                  const fastace_step_out_t* out, uint32_t flags) {
+    if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    return step_host_impl(env, actions, compact_fields(env->dims), env->dcact, env->cact_block, true, out, flags);
+}
+
+int fastace_env_sync(fastace_env_t* env) {
+    if (!env) { set_error("null argument"); return FASTACE_ERR_INVALID; }
     FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
-    if (!env->act_block) {
-        int rc = carve(action_fields(env->dims), &env->dact, &env->act_block, false);
-        if (rc != FASTACE_OK) return rc;
-        rc = carve(out_fields(env->dims), &env->dout, &env->out_block, false);
-        if (rc != FASTACE_OK) return rc;
+    if (env->have_host_streams) {
+        FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->copy_in));
+        FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->stream));
+        FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->copy_out));
     }
-    for (auto& f : action_fields(env->dims)) {
-        const void* src = member(actions, f.offset);
-        if (!src && f.count) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
-        if (f.count)
-            FASTACE_CUDA_CHECK(cudaMemcpyAsync(member(&env->dact, f.offset), src, f.elem * f.count,
-                                               cudaMemcpyHostToDevice, env->stream));
-    }
-    fastace_step_out_t dout;
-    std::memset(&dout, 0, sizeof(dout));
-    for (auto& f : out_fields(env->dims))
-        if (member(out, f.offset)) member(&dout, f.offset) = member(&env->dout, f.offset);
-    int rc = launch_step(env, &env->dact, &dout, flags, env->stream);
-    if (rc != FASTACE_OK) return rc;
-    for (auto& f : out_fields(env->dims)) {
-        void* dst = member(out, f.offset);
-        if (dst && f.count)
-            FASTACE_CUDA_CHECK(cudaMemcpyAsync(dst, member(&env->dout, f.offset), f.elem * f.count,
-                                               cudaMemcpyDeviceToHost, env->stream));
-    }
-    FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->stream));
+    return FASTACE_OK;
+}
+
+int fastace_env_kernel_times(fastace_env_t* env, double* match_ms, double* update_ms, uint64_t* steps) {
+    if (!env || !match_ms || !update_ms || !steps) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    *match_ms = env->prof_match_ms; *update_ms = env->prof_update_ms; *steps = env->prof_steps;
+    env->prof_match_ms = env->prof_update_ms = 0.0; env->prof_steps = 0;
     return FASTACE_OK;
 }
 

@@ -43,7 +43,7 @@ constexpr int kRowStride = 36;   // bytes per cell row: 9 words -> consecutive o
 constexpr int kMaxStack = FASTACE_MAX_STACK;
 
 struct MatchLayout {
-    int off_pmoney, off_fmoney, off_finv, off_mprice, off_jwage;                 // double
+    int off_pmoney, off_fmoney, off_finv, off_mprice, off_jwage, off_flast;      // double
     int off_mleft, off_mtaken, off_jleft, off_jtaken, off_fnh, off_fok;          // u32
     int off_dord, off_tot;                                                       // i32 [F*(G+1)]
     int off_permp, off_permf;                                                    // u16
@@ -67,6 +67,7 @@ __host__ __device__ inline MatchLayout make_match_layout(int P, int F, int G, in
     L.off_finv = take(8 * G * F);
     L.off_mprice = take(8 * cap);
     L.off_jwage = take(8 * F);
+    L.off_flast = take(8 * F);
     L.off_mleft = take(4 * cap);
     L.off_mtaken = take(4 * cap);
     L.off_jleft = take(4 * F);
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     double* s_finv = reinterpret_cast<double*>(smem + L.off_finv);
     double* s_mprice = reinterpret_cast<double*>(smem + L.off_mprice);
     double* s_jwage = reinterpret_cast<double*>(smem + L.off_jwage);
+    double* s_flast = reinterpret_cast<double*>(smem + L.off_flast);   // last_money in, profit out
     uint32_t* s_mleft = reinterpret_cast<uint32_t*>(smem + L.off_mleft);
     uint32_t* s_mtaken = reinterpret_cast<uint32_t*>(smem + L.off_mtaken);
     uint32_t* s_jleft = reinterpret_cast<uint32_t*>(smem + L.off_jleft);
@@ -157,12 +159,23 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
         const bool hasJ = NJ > 0, hasM = NM > 0;   // empty book: no requests at all (decisionNetHandler.cpp:398-403, 476-480)
         for (int pid = lane; pid < P; pid += 32) {
             s_pmoney[pid] = p.st.p_money[eP + pid];
-            s_permp[pid] = (uint16_t)p.ac.perm_person[eP + pid];
+            s_permp[pid] = p.compact ? p.cz.perm_person[eP + pid] : (uint16_t)p.ac.perm_person[eP + pid];
         }
         // request lists -> person-major rows; 4 consecutive persons per lane when rows are 16B-aligned
         const size_t row0 = (size_t)e * S * P;
-        if ((P & 3) == 0) {
+        if (p.compact) {
+            for (int pid = lane; pid < P; pid += 32) {
+                const uint32_t tj = hasJ ? p.cz.p_job_take[eP + pid] : 0u, tg = hasM ? p.cz.p_good_take[eP + pid] : 0u;
+                uint8_t* row = s_att + pid * AS;
+                for (int i = 0; i < S; i++) {
+                    const size_t k = row0 + (size_t)i * P + pid;
+                    row[i] = (uint8_t)(((tj >> i) & 1u) ? mapJ((int)p.cz.p_job_idx[k]) : kNone);
+                    row[S4 + i] = (uint8_t)(((tg >> i) & 1u) ? mapM((int)p.cz.p_good_idx[k]) : kNone);
+                }
+            }
+        } else if ((P & 3) == 0) {
             const int Q = P >> 2;
+#pragma unroll 2
             for (int i = 0; i < S; i++) {
                 const int4* ji = reinterpret_cast<const int4*>(p.ac.p_job_idx + row0 + (size_t)i * P);
                 const int4* gi = reinterpret_cast<const int4*>(p.ac.p_good_idx + row0 + (size_t)i * P);
@@ -202,7 +215,8 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
         }
         for (int f = lane; f < F; f += 32) {
             s_fmoney[f] = p.st.f_money[eF + f];
-            s_permf[f] = (uint16_t)p.ac.perm_firm[eF + f];
+            s_flast[f] = p.st.f_last_money[eF + f];
+            s_permf[f] = (uint16_t)perm_firm_at(p, eF + f);
             s_fnh[f] = 0;
             s_fok[f] = 0;
             s_fcnt[f] = 0;
@@ -211,8 +225,14 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
 #pragma unroll
             for (int g = 0; g < G; g++) s_finv[g * F + f] = p.st.f_inv[((size_t)e * G + g) * F + f];
             const size_t k0 = (size_t)e * S * F + f;
-            for (int i = 0; i < S; i++)
-                s_fatt[f * S + i] = (uint8_t)((p.ac.f_good_take[k0 + (size_t)i * F] && hasM) ? mapM(p.ac.f_good_idx[k0 + (size_t)i * F]) : kNone);
+            if (p.compact) {
+                const uint32_t tg = hasM ? p.cz.f_good_take[eF + f] : 0u;
+                for (int i = 0; i < S; i++)
+                    s_fatt[f * S + i] = (uint8_t)(((tg >> i) & 1u) ? mapM((int)p.cz.f_good_idx[k0 + (size_t)i * F]) : kNone);
+            } else {
+                for (int i = 0; i < S; i++)
+                    s_fatt[f * S + i] = (uint8_t)((p.ac.f_good_take[k0 + (size_t)i * F] && hasM) ? mapM(p.ac.f_good_idx[k0 + (size_t)i * F]) : kNone);
+            }
         }
     }
     for (int n = lane; n < NJ; n += 32) {
@@ -332,9 +352,12 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
                 uint32_t* rw = reinterpret_cast<uint32_t*>(s_room + R * kRowStride);
                 const int d = s_dord[R];
                 int run = 0;
+                uint32_t cvs[8], ros[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) { cvs[k] = cw[k]; ros[k] = rw[k]; }   // all loads in flight at once
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const uint32_t cv = cw[k], ro = rw[k];
+                    const uint32_t cv = cvs[k], ro = ros[k];
                     uint32_t rn = 0;
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
@@ -409,12 +432,13 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
             s_pmoney[pid] = money;
             s_pnh[pid] = (uint8_t)nh;
             write_person_ok(p, e, pid, okm);
+            for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {      // one purchase per set bit
+                const int i = __ffs(m) - 1;
+                uint32_t w = ag[0];
 #pragma unroll
-            for (int i = 0; i < SMAX; i++) {
-                if (i < S && ((okm >> (16 + i)) & 1u)) {
-                    const int n = (int)((ag[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-                    s_pnb[s_mgood[n] * Pp + pid] += 1;
-                }
+                for (int k = 1; k < SMAX / 4; k++) if ((i >> 2) == k) w = ag[k];
+                const int n = (int)((w >> (8 * (i & 3))) & 0xFFu);
+                s_pnb[s_mgood[n] * Pp + pid] += 1;
             }
         }
         for (int R = lane; R < NR; R += 32) {
@@ -494,8 +518,8 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
             // first decision: profit of the previous step (neuralFirmDecisionMaker.cpp:65-74)
             {
                 const double m = s_fmoney[f];
-                const double last = p.st.f_last_money[eF + f];
-                p.out.f_profit[eF + f] = (p.time_before > 0) ? (m - last) : 0.0;
+                const double last = s_flast[f];
+                s_flast[f] = (p.time_before > 0) ? (m - last) : 0.0;   // profit, written out below
                 p.st.f_last_money[eF + f] = m;
             }
             // ProfitMaxer::buy_goods (firms/profitMaxer.cpp:102-111)
@@ -528,16 +552,18 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
             // ProfitMaxer::sell_goods withdraws last step's offers (firms/profitMaxer.cpp:79-81);
             // nothing between buy_goods and that point touches another agent.
             for (int n = first; n < first + cnt; n++) {
-                if (p.out.old_m_left) p.out.old_m_left[eCap + n] = s_mleft[n];
-                if (p.out.old_m_taken) p.out.old_m_taken[eCap + n] = s_mtaken[n];
+                s_dord[n] = (int)s_mleft[n];   // final counters of the withdrawn entry (s_dord is free now)
                 s_mleft[n] = 0;
             }
         }
     }
     __syncwarp();
     // ------------------------------ firms: results to HBM -----------------------------------
+    if (p.out.old_m_left) for (int n = lane; n < NM; n += 32) p.out.old_m_left[eCap + n] = (uint32_t)s_dord[n];
+    if (p.out.old_m_taken) for (int n = lane; n < NM; n += 32) p.out.old_m_taken[eCap + n] = s_mtaken[n];
     for (int f = lane; f < F; f += 32) {
         p.st.f_money[eF + f] = s_fmoney[f];
+        p.out.f_profit[eF + f] = s_flast[f];
 #pragma unroll
         for (int g = 0; g < G; g++) p.st.f_inv[((size_t)e * G + g) * F + f] = s_finv[g * F + f];
         double labor = p.st.f_labor[eF + f];
@@ -615,7 +641,7 @@ __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateP
         int lots = 0, jlots = 0, f = 0;
         double price = 0.0, jwage = 0.0, newinv = 0.0;
         if (active) {
-            f = p.ac.perm_firm[eF + r];
+            f = perm_firm_at(p, eF + r);
             double in[G + 1];
             in[0] = p.st.f_labor[eF + f];
             double xg = 0.0, invg = 0.0;

@@ -68,6 +68,12 @@ class BatchedEconomy:
         lib.check(self._lib.fastace_env_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def kernel_times(self):
+        """(match_ms, update_ms, steps) accumulated by steps run with STEP_PROFILE; resets."""
+        a, b, n = C.c_double(), C.c_double(), C.c_uint64()
+        lib.check(self._lib.fastace_env_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     def set_state(self, state, time=0):
         """Load a host state dict (numpy arrays in the layout of include/fastace_b200.h)."""
         st = _abi.struct_from_numpy("state", state, self.dims)
@@ -114,6 +120,18 @@ class BatchedEconomy:
                 out[n] = torch.zeros(shp, dtype=_TORCH_DTYPES[dt], device=dev)
         return out
 
+    def alloc_compact_actions(self, host_compact):
+        """Device tensors (uint16 viewed as int16) for a compact action dict."""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        out = {}
+        for n, (dt, shp) in _abi.shapes("compact", self.dims).items():
+            a = np.ascontiguousarray(host_compact[n])
+            if a.dtype == np.uint16:
+                a = a.view(np.int16)
+            out[n] = torch.from_numpy(a).to(dev)
+        return out
+
     def alloc_outputs(self, names=_abi.OUT_MANDATORY):
         torch = _torch()
         dev = torch.device("cuda", self.device)
@@ -143,18 +161,28 @@ class BatchedEconomy:
         """Economy::time_step for all economies.  `actions` / `out` are dicts of torch CUDA
         tensors or pre-packed structs (pack_device).  Asynchronous on `stream`
         (default: torch's current stream)."""
-        ac = actions if isinstance(actions, _abi.Actions) else self.pack_device("actions", actions)
         ou = out if isinstance(out, _abi.StepOut) else self.pack_device("out", out)
         if stream is None:
             stream = _torch().cuda.current_stream(self.device).cuda_stream
+        if isinstance(actions, _abi.ActionsCompact):
+            lib.check(self._lib.fastace_env_step_device_compact(self._h, C.byref(actions), C.byref(ou), int(flags), C.c_void_p(stream)))
+            return
+        ac = actions if isinstance(actions, _abi.Actions) else self.pack_device("actions", actions)
         lib.check(self._lib.fastace_env_step_device(self._h, C.byref(ac), C.byref(ou), int(flags), C.c_void_p(stream)))
 
     def time_step_host(self, actions, out, flags=_abi.IDX_ABSOLUTE):
         """Same with host numpy arrays (or pre-built structs of host pointers): copies in,
         steps, copies out, synchronises."""
-        ac = actions if isinstance(actions, _abi.Actions) else _abi.struct_from_numpy("actions", actions, self.dims)
         ou = out if isinstance(out, _abi.StepOut) else _abi.struct_from_numpy("out", out, self.dims)
+        if isinstance(actions, _abi.ActionsCompact):
+            lib.check(self._lib.fastace_env_step_host_compact(self._h, C.byref(actions), C.byref(ou), int(flags)))
+            return
+        ac = actions if isinstance(actions, _abi.Actions) else _abi.struct_from_numpy("actions", actions, self.dims)
         lib.check(self._lib.fastace_env_step_host(self._h, C.byref(ac), C.byref(ou), int(flags)))
+
+    def sync(self):
+        """Wait for every step enqueued by time_step_host(..., flags | STEP_ASYNC)."""
+        lib.check(self._lib.fastace_env_sync(self._h))
 
 
 class _CudaView:

@@ -17,7 +17,8 @@ EXPORTED_SYMBOLS = [
     "fastace_abi_version", "fastace_last_error", "fastace_device_count",
     "fastace_env_create", "fastace_env_destroy", "fastace_env_dims", "fastace_env_time",
     "fastace_env_set_state", "fastace_env_get_state", "fastace_env_device_state",
-    "fastace_env_step_device", "fastace_env_step_host", "fastace_env_launch_count",
+    "fastace_env_step_device", "fastace_env_step_host", "fastace_env_step_device_compact",
+    "fastace_env_step_host_compact", "fastace_env_sync", "fastace_env_launch_count", "fastace_env_kernel_times",
     "create_scenario_params", "create_training_params",
     "fastace_scenario_custom_init", "fastace_shuffle_orders",
 ]
@@ -62,8 +63,16 @@ def load():
     L.fastace_env_step_device.argtypes = [vp, C.POINTER(_abi.Actions), C.POINTER(_abi.StepOut), C.c_uint32, vp]
     L.fastace_env_step_host.restype = C.c_int
     L.fastace_env_step_host.argtypes = [vp, C.POINTER(_abi.Actions), C.POINTER(_abi.StepOut), C.c_uint32]
+    L.fastace_env_step_device_compact.restype = C.c_int
+    L.fastace_env_step_device_compact.argtypes = [vp, C.POINTER(_abi.ActionsCompact), C.POINTER(_abi.StepOut), C.c_uint32, vp]
+    L.fastace_env_step_host_compact.restype = C.c_int
+    L.fastace_env_step_host_compact.argtypes = [vp, C.POINTER(_abi.ActionsCompact), C.POINTER(_abi.StepOut), C.c_uint32]
+    L.fastace_env_sync.restype = C.c_int
+    L.fastace_env_sync.argtypes = [vp]
     L.fastace_env_launch_count.restype = C.c_int
     L.fastace_env_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.fastace_env_kernel_times.restype = C.c_int
+    L.fastace_env_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.create_scenario_params.restype = _abi.CustomScenarioParams
     L.create_scenario_params.argtypes = [C.c_uint, C.c_uint]
     L.create_training_params.restype = _abi.TrainingParams

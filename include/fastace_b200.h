@@ -149,6 +149,31 @@ typedef struct fastace_actions {
 } fastace_actions_t;
 
 /*
+ * Compact encoding of exactly the same decisions (for callers that want less PCIe / HBM
+ * traffic: 34 B instead of 116 B per person-step at S = 10, G = 2).  Offer indices are one byte
+ * (the books of this kernel never exceed 254 entries), the Bernoulli outcomes of an agent's S
+ * slots are one bit mask (bit i = slot i), visiting orders are 16-bit.  With FASTACE_IDX_MODULO
+ * the byte is a raw draw mapped to draw % count; otherwise it is the index itself (>= count: no
+ * request).
+ */
+typedef struct fastace_actions_compact {
+    const uint16_t* perm_person;   /* [E][P]    */
+    const uint16_t* perm_firm;     /* [E][F]    */
+    const uint8_t*  p_job_idx;     /* [E][S][P] */
+    const uint16_t* p_job_take;    /* [E][P]    */
+    const uint8_t*  p_good_idx;    /* [E][S][P] */
+    const uint16_t* p_good_take;   /* [E][P]    */
+    const float*    p_consume;     /* [E][G][P] */
+    const uint8_t*  f_good_idx;    /* [E][S][F] */
+    const uint16_t* f_good_take;   /* [E][F]    */
+    const float*    f_prod;        /* [E][G][F] */
+    const float*    f_offer_amt;   /* [E][G][F] */
+    const float*    f_offer_price; /* [E][G][F] */
+    const float*    f_job_labor;   /* [E][F]    */
+    const float*    f_job_wage;    /* [E][F]    */
+} fastace_actions_compact_t;
+
+/*
  * Per-step outputs.  p_reward and f_profit are mandatory; every other pointer may be
  * NULL (then it is not written).
  *   p_reward : utility of this step's consumption (neuralPersonDecisionMaker.cpp:107-108)
@@ -181,6 +206,13 @@ typedef struct fastace_step_out {
  * FASTACE_STEP_SERIAL persons are matched by a serial walk (kernel v1), which also keeps the
  * reference's fp64 operation order for FIRM money; outcomes are otherwise identical. */
 #define FASTACE_STEP_SERIAL  2u
+/* Diagnostic: bracket each kernel of the step with CUDA events on the launching stream and
+ * synchronise after the step; totals are read with fastace_env_kernel_times. */
+#define FASTACE_STEP_PROFILE 4u
+/* Host-pointer calls only: return without waiting for the step.  Actions are double-buffered on
+ * the device, so the copy-in of step t+1 overlaps the kernels of step t.  Host arrays passed to
+ * an asynchronous call must stay valid, and outputs are complete, only after fastace_env_sync. */
+#define FASTACE_STEP_ASYNC   8u
 
 typedef struct fastace_env fastace_env_t;
 
@@ -222,8 +254,18 @@ int fastace_env_step_device(fastace_env_t* env, const fastace_actions_t* actions
  * arrays makes. */
 int fastace_env_step_host(fastace_env_t* env, const fastace_actions_t* actions,
                           const fastace_step_out_t* out, uint32_t flags);
+/* The same two calls for the compact action encoding. */
+int fastace_env_step_device_compact(fastace_env_t* env, const fastace_actions_compact_t* actions,
+                                    const fastace_step_out_t* out, uint32_t flags, void* cuda_stream);
+int fastace_env_step_host_compact(fastace_env_t* env, const fastace_actions_compact_t* actions,
+                                  const fastace_step_out_t* out, uint32_t flags);
+/* Waits for every step enqueued by the host-pointer calls of this env. */
+int fastace_env_sync(fastace_env_t* env);
 /* number of kernel launches issued by this env's step calls so far */
 int fastace_env_launch_count(const fastace_env_t* env, uint64_t* out_count);
+/* Accumulated device time (milliseconds, CUDA events) of the steps run with FASTACE_STEP_PROFILE:
+ * match_kernel, update_kernel, and the number of such steps.  Resets the accumulators. */
+int fastace_env_kernel_times(fastace_env_t* env, double* match_ms, double* update_ms, uint64_t* steps);
 
 /* ---- legacy entry points of libpybindings.so (src/pybindings.h:8-28) ------------------ */
 /* Byte-identical layouts of neural::CustomScenarioParams (344 B) and

@@ -129,3 +129,68 @@ def test_extreme_actions(oracle):
         env.time_step_host(act, gout, flags=_abi.IDX_MODULO)
         H.compare_outputs(gout, oout, dims, before)
         H.compare_states(env.get_state(), ost, dims)
+
+
+@pytest.mark.parametrize("modulo", [True, False])
+@pytest.mark.parametrize("device_path", [True, False])
+def test_compact_encoding_matches(oracle, modulo, device_path):
+    """fastace_actions_compact_t carries the same decisions: same results as the oracle on the
+    standard encoding (host-pointer path with ASYNC pipelining, and device-pointer path)."""
+    from fastace_b200.env import BatchedEconomy
+    dims = (9, 100, 10, 2, 10)
+    E, P, F, G, S = dims
+    state = scenario.custom_initial_state(dims, 77)[0]
+    env = BatchedEconomy(dims)
+    env.set_state(state)
+    ost = H.copy_state(state)
+    orders = scenario.OrderStream(dims, 78)
+    flags = _abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE
+    rng = np.random.default_rng(5)
+    keep = []
+    for t in range(14):
+        act = scenario.synthetic_actions(dims, seed=79, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
+        if not modulo:
+            for k, hi in (("p_job_idx", F + 2), ("p_good_idx", F * G + 2), ("f_good_idx", F * G + 2)):
+                act[k] = rng.integers(-1, hi, act[k].shape, dtype=np.int32)
+        cz = _abi.compact_actions_for_counts(act, ost["j_count"], ost["m_count"], modulo)
+        before = H.copy_state(ost)
+        oout = _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=flags, time_before=t)
+        gout = _abi.alloc_host("out", dims)
+        if device_path:
+            dcz = env.alloc_compact_actions(cz)
+            dout = env.alloc_outputs(names=None)
+            env.time_step(env.pack_device("compact", dcz), dout, flags=flags)
+            gout = {k: v.cpu().numpy().view(_abi.shapes("out", dims)[k][0]) for k, v in dout.items()}
+        else:
+            czs = _abi.struct_from_numpy("compact", cz, env.dims)
+            keep.append((cz, czs))
+            env.time_step_host(czs, gout, flags=flags | _abi.STEP_ASYNC)
+            env.sync()
+        H.compare_outputs(gout, oout, dims, before)
+        H.compare_states(env.get_state(), ost, dims)
+    env.close()
+
+
+def test_async_host_pipeline_equals_sync(oracle):
+    """several asynchronous host-pointer steps in flight (double-buffered staging) give the same
+    trajectory as synchronous stepping; per-step outputs land in per-step host buffers"""
+    from fastace_b200.env import BatchedEconomy
+    dims = (16, 100, 10, 2, 10)
+    state = scenario.custom_initial_state(dims, 5)[0]
+    acts = [scenario.synthetic_actions(dims, seed=6, step=t, **scenario.BENCH_PRESET) for t in range(12)]
+    envs, outs = [], []
+    for mode in (0, _abi.STEP_ASYNC):
+        env = BatchedEconomy(dims)
+        env.set_state(state)
+        o = [_abi.alloc_host("out", dims, names=("p_reward", "f_profit")) for _ in acts]
+        for t, a in enumerate(acts):
+            env.time_step_host(a, o[t], flags=_abi.IDX_MODULO | mode)
+        env.sync()
+        envs.append(env.get_state())
+        outs.append(o)
+        env.close()
+    for k in envs[0]:
+        assert np.array_equal(envs[0][k], envs[1][k]), k
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a["p_reward"], b["p_reward"]) and np.array_equal(a["f_profit"], b["f_profit"])
