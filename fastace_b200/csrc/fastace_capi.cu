@@ -380,9 +380,9 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         UpdateParams up;
         up.sp = sp; up.scr_pnh = env->scr_pnh; up.scr_pnb = env->scr_pnb;
         const size_t persons = (size_t)sp.E * sp.P;
-        up.person_blocks = (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
-        const int firm_blocks = (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
-        ks.update<<<up.person_blocks + firm_blocks, kUpdateThreads, 0, stream>>>(up);
+        const int person_blocks = (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
+        up.firm_blocks = (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
+        ks.update<<<person_blocks + up.firm_blocks, kUpdateThreads, 0, stream>>>(up);
         FASTACE_CUDA_CHECK(cudaGetLastError());
         env->launches += 2;
         if (prof) {

@@ -43,15 +43,17 @@ constexpr int kRowStride = 36;   // bytes per cell row: 9 words -> consecutive o
 constexpr int kMaxStack = FASTACE_MAX_STACK;
 
 struct MatchLayout {
-    int off_pmoney, off_fmoney, off_finv, off_mprice, off_jwage, off_flast;      // double
+    int off_mrec;                                                                // uint4 [F*G]: price (f64), owner | good<<8
+    int off_pmoney, off_fmoney, off_finv, off_jwage;                             // double
     int off_mleft, off_mtaken, off_jleft, off_jtaken, off_fnh, off_fok;          // u32
     int off_dord, off_tot;                                                       // i32 [F*(G+1)]
     int off_permp, off_permf;                                                    // u16
-    int off_att;                                                                 // u8 [P][2*S4]: jobs at [0,S4), goods at [S4,2*S4)
-    int off_fatt, off_mowner, off_mgood, off_jowner, off_pnh, off_pnb, off_ffirst, off_fcnt, off_fjob;
+    int off_att;                                                                 // u8 [P][AS]: jobs at [0,S), goods at [S,2S), AS = 2S rounded up to 4
+    int off_fatt;                                                                // u8 [F][16]
+    int off_jowner, off_pnh, off_pnb, off_ffirst, off_fcnt, off_fjob;
     int off_cnt, off_room;                                                       // u8 [F*(G+1)][kRowStride]
     int Pp;                                                                      // P rounded up to 4
-    int S4;                                                                      // S rounded up to 4
+    int AS;                                                                      // bytes per person in the request table
     int total;
 };
 
@@ -61,13 +63,13 @@ __host__ __device__ inline MatchLayout make_match_layout(int P, int F, int G, in
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 7) & ~7; return r; };
     L.Pp = (P + 3) & ~3;
-    L.S4 = (S + 3) & ~3;
+    L.AS = (2 * S + 3) & ~3;
+    L.off_mrec = take(16 * cap);          // first: 16-byte aligned
+    L.off_fatt = take(16 * F);
     L.off_pmoney = take(8 * P);
     L.off_fmoney = take(8 * F);
     L.off_finv = take(8 * G * F);
-    L.off_mprice = take(8 * cap);
     L.off_jwage = take(8 * F);
-    L.off_flast = take(8 * F);
     L.off_mleft = take(4 * cap);
     L.off_mtaken = take(4 * cap);
     L.off_jleft = take(4 * F);
@@ -78,10 +80,7 @@ __host__ __device__ inline MatchLayout make_match_layout(int P, int F, int G, in
     L.off_tot = take(4 * nr);
     L.off_permp = take(2 * P);
     L.off_permf = take(2 * F);
-    L.off_att = take(P * 2 * L.S4);
-    L.off_fatt = take(F * S);
-    L.off_mowner = take(cap);
-    L.off_mgood = take(cap);
+    L.off_att = take(P * L.AS + 8);   // +8: the gather may read one word past the last row
     L.off_jowner = take(F);
     L.off_pnh = take(L.Pp);
     L.off_pnb = take(G * L.Pp);
@@ -117,14 +116,13 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     const int P = p.P, F = p.F, S = p.S;
     const int cap = F * G;
     const MatchLayout& L = mp.lay;
-    const int Pp = L.Pp, S4 = L.S4, AS = 2 * L.S4;
+    const int Pp = L.Pp, AS = L.AS;
 
     double* s_pmoney = reinterpret_cast<double*>(smem + L.off_pmoney);
     double* s_fmoney = reinterpret_cast<double*>(smem + L.off_fmoney);
     double* s_finv = reinterpret_cast<double*>(smem + L.off_finv);
-    double* s_mprice = reinterpret_cast<double*>(smem + L.off_mprice);
+    uint4* s_mrec = reinterpret_cast<uint4*>(smem + L.off_mrec);
     double* s_jwage = reinterpret_cast<double*>(smem + L.off_jwage);
-    double* s_flast = reinterpret_cast<double*>(smem + L.off_flast);   // last_money in, profit out
     uint32_t* s_mleft = reinterpret_cast<uint32_t*>(smem + L.off_mleft);
     uint32_t* s_mtaken = reinterpret_cast<uint32_t*>(smem + L.off_mtaken);
     uint32_t* s_jleft = reinterpret_cast<uint32_t*>(smem + L.off_jleft);
@@ -137,8 +135,6 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     uint16_t* s_permf = reinterpret_cast<uint16_t*>(smem + L.off_permf);
     uint8_t* s_att = smem + L.off_att;
     uint8_t* s_fatt = smem + L.off_fatt;
-    uint8_t* s_mowner = smem + L.off_mowner;
-    uint8_t* s_mgood = smem + L.off_mgood;
     uint8_t* s_jowner = smem + L.off_jowner;
     uint8_t* s_pnh = smem + L.off_pnh;
     uint8_t* s_pnb = smem + L.off_pnb;
@@ -147,6 +143,10 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     uint8_t* s_fjob = smem + L.off_fjob;
     uint8_t* s_cnt = smem + L.off_cnt;
     uint8_t* s_room = smem + L.off_room;
+    double* s_flast = reinterpret_cast<double*>(s_room);   // firm phase only (cells are free then): last_money in, profit out
+    auto rec_price = [&](int n) { return *reinterpret_cast<const double*>(&s_mrec[n]); };
+    auto rec_owner = [&](int n) { return (int)(s_mrec[n].z & 0xFFu); };
+    auto rec_good = [&](int n) { return (int)((s_mrec[n].z >> 8) & 0xFFu); };
 
     const size_t eP = (size_t)e * P, eF = (size_t)e * F, eCap = (size_t)e * cap;
     const int NM = p.st.m_count[e];
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
                 for (int i = 0; i < S; i++) {
                     const size_t k = row0 + (size_t)i * P + pid;
                     row[i] = (uint8_t)(((tj >> i) & 1u) ? mapJ((int)p.cz.p_job_idx[k]) : kNone);
-                    row[S4 + i] = (uint8_t)(((tg >> i) & 1u) ? mapM((int)p.cz.p_good_idx[k]) : kNone);
+                    row[S + i] = (uint8_t)(((tg >> i) & 1u) ? mapM((int)p.cz.p_good_idx[k]) : kNone);
                 }
             }
         } else if ((P & 3) == 0) {
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
                     row[AS] = (uint8_t)((ta.y && hasJ) ? mapJ(a.y) : kNone);
                     row[2 * AS] = (uint8_t)((ta.z && hasJ) ? mapJ(a.z) : kNone);
                     row[3 * AS] = (uint8_t)((ta.w && hasJ) ? mapJ(a.w) : kNone);
-                    row += S4;
+                    row += S;
                     row[0] = (uint8_t)((tb.x && hasM) ? mapM(b.x) : kNone);
                     row[AS] = (uint8_t)((tb.y && hasM) ? mapM(b.y) : kNone);
                     row[2 * AS] = (uint8_t)((tb.z && hasM) ? mapM(b.z) : kNone);
@@ -201,12 +201,10 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
                 const size_t rb = row0 + (size_t)i * P;
                 for (int pid = lane; pid < P; pid += 32) {
                     s_att[pid * AS + i] = (uint8_t)((p.ac.p_job_take[rb + pid] && hasJ) ? mapJ(p.ac.p_job_idx[rb + pid]) : kNone);
-                    s_att[pid * AS + S4 + i] = (uint8_t)((p.ac.p_good_take[rb + pid] && hasM) ? mapM(p.ac.p_good_idx[rb + pid]) : kNone);
+                    s_att[pid * AS + S + i] = (uint8_t)((p.ac.p_good_take[rb + pid] && hasM) ? mapM(p.ac.p_good_idx[rb + pid]) : kNone);
                 }
             }
         }
-        for (int pid = lane; pid < P; pid += 32)   // pad slots S..S4-1
-            for (int i = S; i < S4; i++) { s_att[pid * AS + i] = (uint8_t)kNone; s_att[pid * AS + S4 + i] = (uint8_t)kNone; }
         {
             uint32_t* z = reinterpret_cast<uint32_t*>(s_pnh);
             for (int k = lane; k < (Pp >> 2); k += 32) z[k] = 0u;
@@ -215,7 +213,6 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
         }
         for (int f = lane; f < F; f += 32) {
             s_fmoney[f] = p.st.f_money[eF + f];
-            s_flast[f] = p.st.f_last_money[eF + f];
             s_permf[f] = (uint16_t)perm_firm_at(p, eF + f);
             s_fnh[f] = 0;
             s_fok[f] = 0;
@@ -225,13 +222,14 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
 #pragma unroll
             for (int g = 0; g < G; g++) s_finv[g * F + f] = p.st.f_inv[((size_t)e * G + g) * F + f];
             const size_t k0 = (size_t)e * S * F + f;
+            for (int i = S; i < 16; i++) s_fatt[f * 16 + i] = (uint8_t)kNone;
             if (p.compact) {
                 const uint32_t tg = hasM ? p.cz.f_good_take[eF + f] : 0u;
                 for (int i = 0; i < S; i++)
-                    s_fatt[f * S + i] = (uint8_t)(((tg >> i) & 1u) ? mapM((int)p.cz.f_good_idx[k0 + (size_t)i * F]) : kNone);
+                    s_fatt[f * 16 + i] = (uint8_t)(((tg >> i) & 1u) ? mapM((int)p.cz.f_good_idx[k0 + (size_t)i * F]) : kNone);
             } else {
                 for (int i = 0; i < S; i++)
-                    s_fatt[f * S + i] = (uint8_t)((p.ac.f_good_take[k0 + (size_t)i * F] && hasM) ? mapM(p.ac.f_good_idx[k0 + (size_t)i * F]) : kNone);
+                    s_fatt[f * 16 + i] = (uint8_t)((p.ac.f_good_take[k0 + (size_t)i * F] && hasM) ? mapM(p.ac.f_good_idx[k0 + (size_t)i * F]) : kNone);
             }
         }
     }
@@ -250,19 +248,19 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     for (int n = lane; n < NJ; n += 32) s_fjob[s_jowner[n]] = (uint8_t)n;
     for (int n = lane; n < NM; n += 32) {
         const int owner = p.st.m_owner[eCap + n];
-        s_mowner[n] = (uint8_t)owner;
-        s_mgood[n] = (uint8_t)p.st.m_good[eCap + n];
+        const double price = p.st.m_price[eCap + n];
+        s_mrec[n] = make_uint4((uint32_t)__double2loint(price), (uint32_t)__double2hiint(price),
+                               (uint32_t)(owner & 0xFF) | ((uint32_t)(p.st.m_good[eCap + n] & 0xFF) << 8), 0u);
         s_mleft[n] = p.st.m_left[eCap + n];
         s_mtaken[n] = p.st.m_taken[eCap + n];
-        s_mprice[n] = p.st.m_price[eCap + n];
         // a firm's entries are contiguous in market order (it posts all goods in one turn)
         const int prev = (n > 0) ? p.st.m_owner[eCap + n - 1] : -1;
         if (owner != prev) s_ffirst[owner] = (uint8_t)n;
     }
     __syncwarp();
     for (int n = lane; n < NM; n += 32) {
-        const int owner = s_mowner[n];
-        const int next = (n + 1 < NM) ? s_mowner[n + 1] : -1;
+        const int owner = rec_owner(n);
+        const int next = (n + 1 < NM) ? rec_owner(n + 1) : -1;
         if (owner != next) s_fcnt[owner] = (uint8_t)(n + 1 - s_ffirst[owner]);
     }
     __syncwarp();
@@ -273,15 +271,22 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
         const bool active = r < P;
         const int pid = active ? (int)s_permp[r] : 0;
         const double money0 = active ? s_pmoney[pid] : 0.0;
-        // the lane's request lists, 4 slots per register (kNone beyond S)
+        // the lane's request lists, 4 slots per register (kNone beyond S); goods start at byte S
         uint32_t aj[SMAX / 4], ag[SMAX / 4];
         {
             const uint32_t* aw = reinterpret_cast<const uint32_t*>(s_att + pid * AS);
-            const int W = S4 >> 2;
+            const int gw = S >> 2, gs = 8 * (S & 3);
 #pragma unroll
             for (int k = 0; k < SMAX / 4; k++) {
-                aj[k] = (active && k < W) ? aw[k] : 0xFFFFFFFFu;
-                ag[k] = (active && k < W) ? aw[W + k] : 0xFFFFFFFFu;
+                const int valid = min(max(S - 4 * k, 0), 4);                       // slots of this word that exist
+                const uint32_t none = valid >= 4 ? 0u : (0xFFFFFFFFu << (8 * valid));
+                uint32_t j = 0xFFFFFFFFu, g = 0xFFFFFFFFu;
+                if (active && valid > 0) {
+                    j = aw[k] | none;
+                    g = __funnelshift_r(aw[gw + k], aw[gw + k + 1], gs) | none;
+                }
+                aj[k] = j;
+                ag[k] = g;
             }
         }
         for (int R = lane; R < NR; R += 32) {
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
             if (R < NJ) {
                 d = s_jleft[R];
             } else {
-                const int o = R - NJ, sel = s_mowner[o], good = s_mgood[o];
+                const int o = R - NJ, sel = rec_owner(o), good = rec_good(o);
                 d = min(s_mleft[o], unit_sales_possible(s_finv[good * F + sel]));
 #pragma unroll
                 for (int g = 0; g < G; g++)
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
                 if (i < S) {
                     const int n = (int)((ag[i >> 2] >> (8 * (i & 3))) & 0xFFu);
                     if (n != kNone) {
-                        const double price = s_mprice[n];
+                        const double price = rec_price(n);
                         if (money >= price) {                           // agent.cpp:102
                             const int a = (NJ + n) * kRowStride + lane;
                             const uint32_t c = s_cnt[a];
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
                             double sales = 0.0;   // income from goods sold to lower lanes of this window
 #pragma unroll
                             for (int g = 0; g < G; g++)
-                                if (g < cnt) sales += s_mprice[first + g] * (double)min(pre[g], s_dord[NJ + first + g]);
+                                if (g < cnt) sales += rec_price(first + g) * (double)min(pre[g], s_dord[NJ + first + g]);
                             for (int k = 0; k < c; k++) {
                                 if (h >= d) { done = true; break; }                                  // firm.cpp:64
                                 if ((m0 + sales) - w * (double)h < w) { d = h; done = true; break; } // firm.cpp:80
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
 #pragma unroll
                 for (int k = 1; k < SMAX / 4; k++) if ((i >> 2) == k) w = ag[k];
                 const int n = (int)((w >> (8 * (i & 3))) & 0xFFu);
-                s_pnb[s_mgood[n] * Pp + pid] += 1;
+                s_pnb[rec_good(n) * Pp + pid] += 1;
             }
         }
         for (int R = lane; R < NR; R += 32) {
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
                 if (tot > n && left > 0) left = 0;                  // killed (agent.cpp:143)
                 s_mleft[o] = left;
                 s_mtaken[o] += (uint32_t)n;
-                s_finv[s_mgood[o] * F + s_mowner[o]] -= (double)n;   // n exact unit subtractions
+                s_finv[rec_good(o) * F + rec_owner(o)] -= (double)n;   // n exact unit subtractions
             }
             s_tot[R] = n;
         }
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
                 s_fnh[f] += (uint32_t)h;
             }
             const int first = s_ffirst[f], cnt = s_fcnt[f];
-            for (int o = first; o < first + cnt; o++) m = m + s_mprice[o] * (double)s_tot[NJ + o];
+            for (int o = first; o < first + cnt; o++) m = m + rec_price(o) * (double)s_tot[NJ + o];
             s_fmoney[f] = m;
         }
         __syncwarp();
@@ -486,17 +491,21 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     if (p.out.old_j_taken) for (int n = lane; n < NJ; n += 32) p.out.old_j_taken[eF + n] = s_jtaken[n];
 
     // ------------------------------ firms: serial walk in visiting order ---------------------
+    for (int f = lane; f < F; f += 32) s_flast[f] = p.st.f_last_money[eF + f];
+    __syncwarp();
     if (lane == 0) {
         for (int r = 0; r < F; r++) {
             const int f = s_permf[r];
             const int first = s_ffirst[f], cnt = s_fcnt[f];
+            const uint4 slots = *reinterpret_cast<const uint4*>(s_fatt + f * 16);   // the firm's request bytes
+            double money = s_fmoney[f];
             // Agent::check_my_offers (base/agent.cpp:54-97): running inventoryLeft over own entries
             {
                 double invLeft[G];
 #pragma unroll
                 for (int g = 0; g < G; g++) invLeft[g] = s_finv[g * F + f];
                 for (int n = first; n < first + cnt; n++) {
-                    const int good = s_mgood[n];
+                    const int good = rec_good(n);
                     uint32_t left = s_mleft[n];
                     double delta = kAmountPerOffer * (double)left;     // agent.cpp:73 (other goods: 0*left = 0)
                     for (;;) {
@@ -517,37 +526,46 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
             }
             // first decision: profit of the previous step (neuralFirmDecisionMaker.cpp:65-74)
             {
-                const double m = s_fmoney[f];
                 const double last = s_flast[f];
-                s_flast[f] = (p.time_before > 0) ? (m - last) : 0.0;   // profit, written out below
-                p.st.f_last_money[eF + f] = m;
+                s_flast[f] = (p.time_before > 0) ? (money - last) : 0.0;   // profit, written out below
+                p.st.f_last_money[eF + f] = money;
             }
-            // ProfitMaxer::buy_goods (firms/profitMaxer.cpp:102-111)
+            // ProfitMaxer::buy_goods (firms/profitMaxer.cpp:102-111); the buyer's money stays in a register
             uint32_t ok = 0;
+#pragma unroll 1
             for (int i = 0; i < S; i++) {
-                const int n = s_fatt[f * S + i];
-                if (n == kNone) continue;
-                const double money = s_fmoney[f];
-                const double price = s_mprice[n];
-                if (!(money >= price)) continue;
-                const uint32_t left = s_mleft[n];
-                if (!(left > 0)) continue;
-                const int s = s_mowner[n], good = s_mgood[n];
-                bool short_ = false;
+                const uint32_t word = (i < 4) ? slots.x : (i < 8) ? slots.y : (i < 12) ? slots.z : slots.w;
+                const int n = (int)((word >> (8 * (i & 3))) & 0xFFu);
+                if (n != kNone) {
+                    const uint4 rec = s_mrec[n];
+                    const double price = __hiloint2double((int)rec.y, (int)rec.x);
+                    if (money >= price) {                                  // agent.cpp:102
+                        const uint32_t left = s_mleft[n];
+                        if (left > 0) {                                    // agent.cpp:124
+                            const int s = (int)(rec.z & 0xFFu), good = (int)((rec.z >> 8) & 0xFFu);
+                            bool short_ = false;                           // agent.cpp:140
 #pragma unroll
-                for (int g = 0; g < G; g++) {
-                    const double q = (g == good) ? kAmountPerOffer : 0.0;
-                    if (s_finv[g * F + s] < q) short_ = true;
+                            for (int g = 0; g < G; g++) {
+                                const double q = (g == good) ? kAmountPerOffer : 0.0;
+                                if (s_finv[g * F + s] < q) short_ = true;
+                            }
+                            if (short_) {
+                                s_mleft[n] = 0;                            // agent.cpp:143
+                            } else {
+                                // seller first (agent.cpp:155-160), then buyer (agent.cpp:108-109)
+                                if (s == f) money += price; else s_fmoney[s] += price;
+                                s_finv[good * F + s] -= kAmountPerOffer;
+                                s_mleft[n] = left - 1;
+                                s_mtaken[n] += 1;
+                                money -= price;
+                                s_finv[good * F + f] += kAmountPerOffer;
+                                ok |= 1u << i;
+                            }
+                        }
+                    }
                 }
-                if (short_) { s_mleft[n] = 0; continue; }
-                s_fmoney[s] += price;                                  // seller first (may be f itself)
-                s_finv[good * F + s] -= kAmountPerOffer;
-                s_mleft[n] = left - 1;
-                s_mtaken[n] += 1;
-                s_fmoney[f] -= price;                                  // then buyer
-                s_finv[good * F + f] += kAmountPerOffer;
-                ok |= 1u << i;
             }
+            s_fmoney[f] = money;
             s_fok[f] = ok;
             // ProfitMaxer::sell_goods withdraws last step's offers (firms/profitMaxer.cpp:79-81);
             // nothing between buy_goods and that point touches another agent.
@@ -578,13 +596,14 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// update_kernel: blocks [0, person_blocks) handle persons (one thread each), the remaining blocks
-// handle firms (one warp per economy, lanes = (visiting rank, output good) pairs).
+// update_kernel: blocks [0, firm_blocks) handle firms (one warp per economy, lanes = (visiting rank,
+// output good) pairs; scheduled first because their fp64 pow chains are the longest), the remaining
+// blocks handle persons (one thread each).
 struct UpdateParams {
     StepParams sp;
     const uint8_t* scr_pnh;
     const uint8_t* scr_pnb;
-    int person_blocks;
+    int firm_blocks;
 };
 
 constexpr int kUpdateThreads = 128;
@@ -593,10 +612,10 @@ template <int G>
 __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateParams up) {
     const StepParams& p = up.sp;
     const int P = p.P, F = p.F;
-    if ((int)blockIdx.x < up.person_blocks) {
+    if ((int)blockIdx.x >= up.firm_blocks) {
         // ---- UtilMaxer::consume_goods (utilMaxer.cpp:88-92) + choose_goods_to_consume
         //      (neuralPersonDecisionMaker.cpp:93-111) + UtilMaxer::u (utilMaxer.cpp:54-62)
-        const size_t t = (size_t)blockIdx.x * kUpdateThreads + threadIdx.x;
+        const size_t t = (size_t)((int)blockIdx.x - up.firm_blocks) * kUpdateThreads + threadIdx.x;
         if (t >= (size_t)p.E * P) return;
         const int e = (int)(t / P), pid = (int)(t % P);
         const double labor = kLaborPerOffer * (double)up.scr_pnh[t];       // exact: 0, 0.5 or 1.0
@@ -626,7 +645,7 @@ __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateP
     // ---- firms: produce (profitMaxer.cpp:68-72), sell_goods / search_for_laborers decode
     //      (neuralFirmDecisionMaker.cpp:111-180), new books in market order (economy.cpp:52-59, 125-126)
     const int warps_per_block = kUpdateThreads / 32;
-    const int e = ((int)blockIdx.x - up.person_blocks) * warps_per_block + (threadIdx.x >> 5);
+    const int e = (int)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (e >= p.E) return;
     const int lane = threadIdx.x & 31;
     const int cap = F * G;
