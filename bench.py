@@ -320,6 +320,37 @@ def run_ours(args):
     e2e_value = run_e2e(pinned_c, _abi.IDX_MODULO | _abi.STEP_ASYNC, e2e_steps)
     e2e_int32 = run_e2e(pinned_i, _abi.IDX_MODULO, len(pinned_i))
 
+    # ---- full rollout (config C flavour): batched policy forward on tensor cores + env step ----------
+    rollout = None
+    if args.rollout:
+        from fastace_b200 import policy
+        torch.backends.cuda.matmul.allow_tf32 = True
+        nets = policy.DecisionNets(numGoods=G, stackSize=S).to(dev).eval()
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + rank)
+        results = {}
+        for label, dt in (("tf32", None), ("bf16", torch.bfloat16)):
+            pol = policy.BatchedPolicy(env, nets, generator=gen, autocast_dtype=dt)
+            reset_state(0)
+            rsteps = 8
+            perm_dev = [(torch.from_numpy(a["perm_person"]).to(dev), torch.from_numpy(a["perm_firm"]).to(dev)) for a in acts[:rsteps + 2]]
+            for k in range(2):
+                pol.step(perm_dev[k], dout, flags=_abi.IDX_ABSOLUTE)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for k in range(rsteps):
+                pol.step(perm_dev[2 + k], dout, flags=_abi.IDX_ABSOLUTE)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / rsteps
+            t_r = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_r, op=dist.ReduceOp.MAX)
+            results[label] = {"ms_per_step": float(t_r.item()), "value": world * E * (P + F) / (float(t_r.item()) * 1e-3)}
+        rollout = {"unit": METRIC, "policy": "11 decision nets (hidden 100 x 12 layers), random init, batched over all agents via torch",
+                   "semantics": "decisions taken from the state at the start of the step (DESIGN.md §7)", **results}
+
     if rank == 0:
         peak, peak_src = peaks()
         avg_step_s = total_ms / args.steps * 1e-3  # rank 0's own steps
@@ -353,6 +384,8 @@ def run_ours(args):
                                   "algorithmic_bytes_per_step": BYTES_PER_ECON_STEP * E, "achieved": step_achieved,
                                   "frac": step_achieved / peak}},
         }
+        if rollout is not None:
+            line["full_rollout"] = rollout
         if world == 1 and not args.no_cpu:
             base = cpu_baseline(args.cpu_sample, EPISODE)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -372,6 +405,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (diagnostic)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--rollout", action="store_true", help="also time the full rollout with the batched policy forward")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -1,0 +1,391 @@
+"""Batched policy forward — the caller on the other side of the plugin boundary.
+
+The reference evaluates its 11 decision networks one agent at a time (batch-1 forwards,
+/root/reference/src/neural/decisionNetHandler.cpp:49-69, 390-643).  Here the same networks
+(/root/reference/src/neural/decisionNets.cpp) carry a leading batch dimension and run for every
+agent of every economy at once on torch CUDA tensors; inputs are read zero-copy from the env's
+device buffers (BatchedEconomy.device_state_tensors) and outputs are written in the action layout
+of include/fastace_b200.h.  Tensor cores are used through torch (TF32 / bf16 autocast) — this file
+contains no hand-written kernel; the env step stays the hand-written path.
+
+Parameter names are the reference's (`dimReduce`, `hidden{i}`, `last`, `flatten`, `first`,
+`hidden_firstStage{i}`, `hidden_secondStage_{a,b}{i}`, `last_{a,b}`, `offerFlatten`, `jobOfferFlatten`,
+sub-modules `offerEncoder` / `jobOfferEncoder`), so a state_dict maps 1:1 onto the reference's
+`named_parameters()` (checked against the compiled reference modules in tests/test_policy.py).
+"""
+import math
+
+import torch
+from torch import nn
+
+SQRT2PI = 2 / (math.sqrt(4 / math.pi) * math.sqrt(0.5))  # neuralConstants.h:10: 2 / (M_2_SQRTPI * M_SQRT1_2)
+
+
+def _xavier(module):
+    """xavier_init (decisionNets.cpp:6-12): xavier-normal weights, bias 0.01."""
+    if isinstance(module, nn.Linear):
+        nn.init.xavier_normal_(module.weight)
+        nn.init.constant_(module.bias, 0.01)
+
+
+class _Hidden(nn.Module):
+    """registers `hidden0..hiddenN-1` (or another prefix) as direct children, like the reference"""
+
+    def _add_layers(self, prefix, sizes):
+        layers = []
+        for i, (a, b) in enumerate(sizes):
+            lin = nn.Linear(a, b)
+            self.add_module(f"{prefix}{i}", lin)
+            layers.append(lin)
+        return layers
+
+
+class OfferEncoder(_Hidden):
+    """decisionNets.cpp:42-80.  x: [..., numFeatures] -> [..., encodingSize]"""
+
+    def __init__(self, stackSize, numFeatures, hiddenSize, numHidden, encodingSize):
+        super().__init__()
+        self.stackSize, self.numHidden, self.encodingSize = stackSize, numHidden, encodingSize
+        self.dimReduce = nn.Linear(numFeatures, hiddenSize)
+        self._hidden = self._add_layers("hidden", [(hiddenSize, hiddenSize)] * numHidden)
+        self.last = nn.Linear(hiddenSize, encodingSize)
+        self.apply(_xavier)
+
+    def forward(self, x):
+        x = torch.tanh(self.dimReduce(x))
+        for h in self._hidden:
+            x = x + torch.tanh(h(x))
+        return torch.tanh(self.last(x))
+
+
+def _head_features(flatten, offerEncodings, *rest):
+    x = torch.tanh(flatten(offerEncodings).squeeze(-1))
+    return torch.cat([x, *rest], dim=-1)
+
+
+class PurchaseNet(_Hidden):
+    """decisionNets.cpp:91-146.  [B,S,enc],[B,U],[B,1],[B,1],[B,G] -> probabilities [B,S]"""
+
+    def __init__(self, offerEncoder, numUtilParams, numGoods, hiddenSize, numHidden):
+        super().__init__()
+        assert numHidden >= 1
+        self.flatten = nn.Linear(offerEncoder.encodingSize, 1)
+        nf = offerEncoder.stackSize + numUtilParams + numGoods + 2
+        self._hidden = self._add_layers("hidden", [(nf if i == 0 else hiddenSize, hiddenSize) for i in range(numHidden)])
+        self.last = nn.Linear(hiddenSize, offerEncoder.stackSize)
+        self.apply(_xavier)
+        self.offerEncoder = offerEncoder   # registered after apply(), as in the reference (:121)
+
+    def forward(self, offerEncodings, utilParams, budget, labor, inventory):
+        x = _head_features(self.flatten, offerEncodings, utilParams, budget, labor, inventory)
+        x = torch.tanh(self._hidden[0](x))
+        for h in self._hidden[1:]:
+            x = x + torch.tanh(h(x))
+        return torch.sigmoid(self.last(x))
+
+
+class ConsumptionNet(_Hidden):
+    """decisionNets.cpp:157-197.  -> [B, G, 2] (mu, log sigma); the reference reshapes to {G,2}"""
+
+    def __init__(self, numUtilParams, numGoods, hiddenSize, numHidden):
+        super().__init__()
+        self.numGoods = numGoods
+        self.first = nn.Linear(numUtilParams + numGoods + 2, hiddenSize)
+        self._hidden = self._add_layers("hidden", [(hiddenSize, hiddenSize)] * numHidden)
+        self.last = nn.Linear(hiddenSize, numGoods * 2)
+        self.apply(_xavier)
+
+    def forward(self, utilParams, money, labor, inventory):
+        x = torch.tanh(self.first(torch.cat([utilParams, money, labor, inventory], dim=-1)))
+        for h in self._hidden:
+            x = x + torch.tanh(h(x))
+        return self.last(x).reshape(*x.shape[:-1], self.numGoods, 2)
+
+
+class OfferNet(_Hidden):
+    """decisionNets.cpp:208-300.  -> [B, G, 4] (prop_mu, prop_logsigma, price_mu, price_logsigma)"""
+
+    def __init__(self, offerEncoder, numUtilParams, numGoods, hiddenSize_firstStage, hiddenSize_secondStage,
+                 numHidden_firstStage, numHidden_secondStage):
+        super().__init__()
+        assert numHidden_firstStage >= 1 and numHidden_secondStage >= 1
+        self.numGoods = numGoods
+        self.flatten = nn.Linear(offerEncoder.encodingSize, 1)
+        nf = offerEncoder.stackSize + numUtilParams + numGoods + 2
+        h1, h2 = hiddenSize_firstStage, hiddenSize_secondStage
+        self._first = self._add_layers("hidden_firstStage", [(nf if i == 0 else h1, h1) for i in range(numHidden_firstStage)])
+        sizes2 = [(h1 if i == 0 else h2, h2) for i in range(numHidden_secondStage)]
+        # the reference registers a_i and b_i alternately (decisionNets.cpp:245-260)
+        self._a, self._b = [], []
+        for i, (a, b) in enumerate(sizes2):
+            la, lb = nn.Linear(a, b), nn.Linear(a, b)
+            self.add_module(f"hidden_secondStage_a{i}", la)
+            self.add_module(f"hidden_secondStage_b{i}", lb)
+            self._a.append(la)
+            self._b.append(lb)
+        self.last_a = nn.Linear(h2, numGoods * 2)
+        self.last_b = nn.Linear(h2, numGoods * 2)
+        self.apply(_xavier)
+        self.offerEncoder = offerEncoder
+
+    def forward(self, offerEncodings, utilParams, money, labor, inventory):
+        x = _head_features(self.flatten, offerEncodings, utilParams, money, labor, inventory)
+        x = torch.tanh(self._first[0](x))
+        for h in self._first[1:]:
+            x = x + torch.tanh(h(x))
+        xa = x + torch.tanh(self._a[0](x))
+        xb = x + torch.tanh(self._b[0](x))
+        for ha, hb in zip(self._a[1:], self._b[1:]):
+            xa = xa + torch.tanh(ha(xa))
+            xb = xb + torch.tanh(hb(xb))
+        xa = self.last_a(xa).reshape(*x.shape[:-1], self.numGoods, 2)
+        xb = self.last_b(xb).reshape(*x.shape[:-1], self.numGoods, 2)
+        return torch.cat([xa, xb], dim=-1)
+
+
+class JobOfferNet(_Hidden):
+    """decisionNets.cpp:318-376.  -> [B, 4] (labor_mu, labor_logsigma, wage_mu, wage_logsigma).
+    The reference does NOT register its encoder as a sub-module (:352)."""
+
+    def __init__(self, offerEncoder, numUtilParams, numGoods, hiddenSize, numHidden):
+        super().__init__()
+        assert numHidden >= 1
+        self.flatten = nn.Linear(offerEncoder.encodingSize, 1)
+        nf = offerEncoder.stackSize + numUtilParams + numGoods + 2
+        self._hidden = self._add_layers("hidden", [(nf if i == 0 else hiddenSize, hiddenSize) for i in range(numHidden)])
+        self.last = nn.Linear(hiddenSize, 4)
+        self.apply(_xavier)
+        object.__setattr__(self, "offerEncoder", offerEncoder)   # plain attribute: not in named_parameters()
+
+    def forward(self, offerEncodings, utilParams, money, labor, inventory):
+        x = _head_features(self.flatten, offerEncodings, utilParams, money, labor, inventory)
+        x = torch.tanh(self._hidden[0](x))
+        for h in self._hidden[1:]:
+            x = x + torch.tanh(h(x))
+        return self.last(x)
+
+
+class ValueNet(_Hidden):
+    """decisionNets.cpp:387-447.  -> [B, 1]"""
+
+    def __init__(self, offerEncoder, jobOfferEncoder, numUtilParams, numGoods, hiddenSize, numHidden):
+        super().__init__()
+        assert numHidden >= 1
+        self.offerFlatten = nn.Linear(offerEncoder.encodingSize, 1)
+        self.jobOfferFlatten = nn.Linear(jobOfferEncoder.encodingSize, 1)
+        nf = offerEncoder.stackSize + jobOfferEncoder.stackSize + numUtilParams + numGoods + 2
+        self._hidden = self._add_layers("hidden", [(nf if i == 0 else hiddenSize, hiddenSize) for i in range(numHidden)])
+        self.last = nn.Linear(hiddenSize, 1)
+        self.apply(_xavier)
+        self.offerEncoder = offerEncoder
+        self.jobOfferEncoder = jobOfferEncoder
+
+    def forward(self, offerEncodings, jobOfferEncodings, utilParams, money, labor, inventory):
+        ox = torch.tanh(self.offerFlatten(offerEncodings).squeeze(-1))
+        jx = torch.tanh(self.jobOfferFlatten(jobOfferEncodings).squeeze(-1))
+        x = torch.cat([ox, jx, utilParams, money, labor, inventory], dim=-1)
+        x = torch.tanh(self._hidden[0](x))
+        for h in self._hidden[1:]:
+            x = x + torch.tanh(h(x))
+        return self.last(x)
+
+
+NET_NAMES = ["offerEncoder", "jobOfferEncoder", "purchaseNet", "firmPurchaseNet", "laborSearchNet", "consumptionNet",
+             "productionNet", "offerNet", "jobOfferNet", "valueNet", "firmValueNet"]
+
+
+class DecisionNets(nn.Module):
+    """The 11 networks of DecisionNetHandler (decisionNetHandler.cpp:126-222), sharing the two encoders."""
+
+    def __init__(self, numGoods=2, stackSize=10, encodingSize=10, hiddenSize=100, nHidden=12, nHiddenSmall=6):
+        super().__init__()
+        G = numGoods
+        self.numGoods, self.stackSize, self.encodingSize = G, stackSize, encodingSize
+        U, PF = G + 3, (G + 3) * G
+        self.offerEncoder = OfferEncoder(stackSize, G + 1, hiddenSize, nHidden, encodingSize)
+        self.jobOfferEncoder = OfferEncoder(stackSize, 2, hiddenSize, nHidden, encodingSize)
+        self.purchaseNet = PurchaseNet(self.offerEncoder, U, G, hiddenSize, nHidden)
+        self.firmPurchaseNet = PurchaseNet(self.offerEncoder, PF, G, hiddenSize, nHidden)
+        self.laborSearchNet = PurchaseNet(self.jobOfferEncoder, U, G, hiddenSize, nHidden)
+        self.consumptionNet = ConsumptionNet(U, G, hiddenSize, nHidden)
+        self.productionNet = ConsumptionNet(PF, G, hiddenSize, nHidden)
+        self.offerNet = OfferNet(self.offerEncoder, PF, G, hiddenSize, hiddenSize, nHidden, nHiddenSmall)
+        self.jobOfferNet = JobOfferNet(self.jobOfferEncoder, PF, G, hiddenSize, nHidden)
+        self.valueNet = ValueNet(self.offerEncoder, self.jobOfferEncoder, U, G, hiddenSize, nHidden)
+        self.firmValueNet = ValueNet(self.offerEncoder, self.jobOfferEncoder, PF, G, hiddenSize, nHidden)
+
+    def net(self, name):
+        return getattr(self, name)
+
+    def load_reference_parameters(self, named):
+        """named: {"<net>/<reference parameter name>": array}; copies into the matching tensors."""
+        with torch.no_grad():
+            for key, value in named.items():
+                net, pname = key.split("/", 1)
+                dict(self.net(net).named_parameters())[pname].copy_(torch.as_tensor(value))
+
+
+# ---- sampling rules (decisionNetHandler.cpp:27-46, 368-387) ---------------------------
+def sample_normal(params, noise=None):
+    """params[..., 0] = mu, params[..., 1] = log sigma.  Returns (x, log p(x)) with the reference's
+    log-density -0.5*((x-mu)/sigma)^2 - log(sigma*sqrt(2*pi))."""
+    mu, sigma = params[..., 0], torch.exp(params[..., 1])
+    if noise is None:
+        noise = torch.randn_like(mu)
+    x = noise * sigma + mu
+    logp = -0.5 * ((x - mu) / sigma) ** 2 - torch.log(sigma * SQRT2PI)
+    return x, logp
+
+
+def sample_logit_normal(params, noise=None):
+    x, logp = sample_normal(params, noise)
+    return torch.sigmoid(x), logp       # no Jacobian term, as in the reference (:38-41)
+
+
+def sample_log_normal(params, noise=None):
+    x, logp = sample_normal(params, noise)
+    return torch.exp(x), logp           # no Jacobian term (:43-46)
+
+
+def sample_bernoulli(probas, uniform=None):
+    """take_i = u_i < p_i ; log pi = sum_i log p_i or log(1-p_i)  (decisionNetHandler.cpp:368-387)"""
+    if uniform is None:
+        uniform = torch.rand_like(probas)
+    take = uniform < probas
+    logp = torch.where(take, torch.log(probas), torch.log(1 - probas)).sum(dim=-1)
+    return take, logp
+
+
+# ---- batched decision step over a BatchedEconomy -----------------------------------------------------
+class BatchedPolicy:
+    """Runs the 7 decisions of every agent of every economy at once and writes the action tensors
+    of one env step (fastace_actions_t layout).
+
+    Semantics note (documented deviation): the reference asks the nets in the middle
+    of an agent's turn, so e.g. a person's purchase decision sees its money after its job search.
+    A batched forward cannot interleave with the matching inside one fused env step, so here all
+    decisions of a step are taken from the state at the start of the step (labour input 0 for
+    persons, as in the reference's first decision of a turn).  The networks, the index draws, the
+    sampling rules and the action decode are the reference's."""
+
+    def __init__(self, env, nets, generator=None, autocast_dtype=None):
+        self.env, self.nets, self.gen, self.autocast_dtype = env, nets, generator, autocast_dtype
+        self.E, self.P, self.F, self.G, self.S = env.dims.tuple
+        self.state = env.device_state_tensors()
+        self.dev = self.state["p_money"].device
+        self.actions = env.alloc_actions()
+        self.packed = env.pack_device("actions", self.actions)
+
+    def _rand(self, *shape):
+        return torch.rand(*shape, device=self.dev, generator=self.gen)
+
+    def _randn(self, *shape):
+        return torch.randn(*shape, device=self.dev, generator=self.gen)
+
+    def _draw_indices(self, count, n_agents):
+        """torch::randint(0, count, S) per agent (decisionNetHandler.cpp:327-365); count==0 -> no decision"""
+        u = self._rand(self.E, n_agents, self.S)
+        c = count.clamp(min=1).view(self.E, 1, 1)
+        return torch.minimum((u * c.to(u.dtype)).long(), c - 1)
+
+    @torch.no_grad()
+    def decide(self, perms):
+        """Fill self.actions for one step.  perms = (perm_person, perm_firm) int32 [E,P] / [E,F] (host or device).
+        Returns a dict with log-probabilities and state values (device tensors) for a trainer."""
+        E, P, F, G, S = self.E, self.P, self.F, self.G, self.S
+        st, nets, a = self.state, self.nets, self.actions
+        f32 = torch.float32
+        ctx = torch.autocast("cuda", dtype=self.autocast_dtype) if self.autocast_dtype is not None else _NullCtx()
+        with ctx:
+            # --- market snapshot + encoder forward (update_encodedOffers / JobOffers, :236-275)
+            capM = F * G
+            nM, nJ = st["m_count"].long(), st["j_count"].long()
+            good = st["m_good"].long().clamp(0, G - 1)
+            qty = torch.nn.functional.one_hot(good, G).to(f32)                       # quantities = e_g * 1.0
+            feats = torch.cat([qty, st["m_price"].to(f32).unsqueeze(-1)], dim=-1)    # [E, capM, G+1]
+            encM = nets.offerEncoder(feats)                                          # [E, capM, enc]
+            jfeat = torch.stack([torch.full_like(st["j_wage"], 0.5), st["j_wage"]], dim=-1).to(f32)
+            encJ = nets.jobOfferEncoder(jfeat)                                       # [E, F, enc]
+            validM = (nM > 0).view(E, 1, 1)
+            validJ = (nJ > 0).view(E, 1, 1)
+
+            def gather(enc, idx, valid):    # enc [E,N,enc], idx [E,A,S] -> [E,A,S,enc]; zeros when the market is empty (:542-565)
+                out = torch.gather(enc.unsqueeze(1).expand(-1, idx.shape[1], -1, -1), 2,
+                                   idx.unsqueeze(-1).expand(-1, -1, -1, enc.shape[-1]))
+                return out * valid.unsqueeze(-1).to(out.dtype)
+
+            # --- persons
+            pidxM, pidxJ = self._draw_indices(nM, P), self._draw_indices(nJ, P)
+            util = torch.cat([st["p_util_tfp"].unsqueeze(1), st["p_util_share"], st["p_util_rho"].unsqueeze(1)], dim=1)
+            util = util.permute(0, 2, 1).to(f32)                                     # [E,P,G+3]: tfp, shares, rho (:30-38)
+            money = st["p_money"].to(f32).unsqueeze(-1)
+            labor0 = torch.zeros_like(money)                                          # laborSupplied was just reset (person.cpp:24)
+            inv = st["p_inv"].permute(0, 2, 1).to(f32)
+            eM, eJ = gather(encM, pidxM, validM), gather(encJ, pidxJ, validJ)
+            p_value = nets.valueNet(eM, eJ, util, money, labor0, inv).squeeze(-1)
+            p_job_p = nets.laborSearchNet(eJ, util, money, labor0, inv)
+            p_good_p = nets.purchaseNet(eM, util, money, labor0, inv)
+            cons = nets.consumptionNet(util, money, labor0, inv)
+            # --- firms
+            fidxM, fidxJ = self._draw_indices(nM, F), self._draw_indices(nJ, F)
+            pf = torch.cat([st["f_prod_tfp"].unsqueeze(2), st["f_prod_share"], st["f_prod_rho"].unsqueeze(2)], dim=2)
+            pf = pf.permute(0, 3, 1, 2).reshape(E, F, G * (G + 3)).to(f32)           # per good: tfp, shares, rho (:36-48)
+            fmoney = st["f_money"].to(f32).unsqueeze(-1)
+            flabor = st["f_labor"].to(f32).unsqueeze(-1)
+            finv = st["f_inv"].permute(0, 2, 1).to(f32)
+            feM, feJ = gather(encM, fidxM, validM), gather(encJ, fidxJ, validJ)
+            f_value = nets.firmValueNet(feM, feJ, pf, fmoney, flabor, finv).squeeze(-1)
+            f_good_p = nets.firmPurchaseNet(feM, pf, fmoney, flabor, finv)
+            prod = nets.productionNet(pf, fmoney, flabor, finv)
+            offer = nets.offerNet(feM, pf, fmoney, flabor, finv)
+            job = nets.jobOfferNet(feJ, pf, fmoney, flabor, finv)
+        # --- sampling (fp32) and action decode into the env layout
+        p_job_take, lp_job = sample_bernoulli(p_job_p.float(), self._rand(E, P, S))
+        p_good_take, lp_good = sample_bernoulli(p_good_p.float(), self._rand(E, P, S))
+        f_good_take, lp_fgood = sample_bernoulli(f_good_p.float(), self._rand(E, F, S))
+        cons_x, lp_cons = sample_logit_normal(cons.float(), self._randn(E, P, G))
+        prod_x, lp_prod = sample_logit_normal(prod.float(), self._randn(E, F, G))
+        amt_x, lp_amt = sample_logit_normal(offer.float()[..., 0:2], self._randn(E, F, G))
+        price_x, lp_price = sample_log_normal(offer.float()[..., 2:4], self._randn(E, F, G))
+        lab_x, lp_lab = sample_log_normal(job.float()[..., 0:2], self._randn(E, F))
+        wage_x, lp_wage = sample_log_normal(job.float()[..., 2:4], self._randn(E, F))
+        a["perm_person"].copy_(torch.as_tensor(perms[0]))
+        a["perm_firm"].copy_(torch.as_tensor(perms[1]))
+        a["p_job_idx"].copy_(pidxJ.permute(0, 2, 1))
+        a["p_job_take"].copy_((p_job_take & validJ).permute(0, 2, 1))
+        a["p_good_idx"].copy_(pidxM.permute(0, 2, 1))
+        a["p_good_take"].copy_((p_good_take & validM).permute(0, 2, 1))
+        a["p_consume"].copy_(cons_x.permute(0, 2, 1))
+        a["f_good_idx"].copy_(fidxM.permute(0, 2, 1))
+        a["f_good_take"].copy_((f_good_take & validM).permute(0, 2, 1))
+        a["f_prod"].copy_(prod_x.permute(0, 2, 1))
+        a["f_offer_amt"].copy_(amt_x.permute(0, 2, 1))
+        a["f_offer_price"].copy_(price_x.permute(0, 2, 1))
+        a["f_job_labor"].copy_(lab_x)
+        a["f_job_wage"].copy_(wage_x)
+        nan = torch.full_like(lp_good, float("nan"))
+        return {
+            "value_person": p_value.float(), "value_firm": f_value.float(),
+            # empty market: purchase log-prob NaN = "no decision", job search 0.0 (decisionNetHandler.cpp:398-403, 476-480)
+            "logp_purchase": torch.where(validM.view(E, 1), lp_good, nan),
+            "logp_laborSearch": torch.where(validJ.view(E, 1), lp_job, torch.zeros_like(lp_job)),
+            "logp_consumption": lp_cons.sum(-1),
+            "logp_firmPurchase": torch.where(validM.view(E, 1), lp_fgood, torch.full_like(lp_fgood, float("nan"))),
+            "logp_production": lp_prod.sum(-1),
+            "logp_offer": lp_amt.sum(-1) + lp_price.sum(-1),
+            "logp_jobOffer": lp_lab + lp_wage,
+        }
+
+    def step(self, perms, out, flags=0):
+        """decide + one env step (device path, current stream)."""
+        info = self.decide(perms)
+        self.env.time_step(self.packed, out, flags=flags)
+        return info
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
