@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FASTACE_OK = 0
 IDX_ABSOLUTE = 0
 IDX_MODULO = 1
@@ -16,6 +16,7 @@ STEP_SERIAL = 2
 STEP_PROFILE = 4
 STEP_ASYNC = 8
 MAX_GOODS = 8
+FN_CES, FN_COBB_DOUGLAS, FN_STONE_GEARY, FN_LEONTIEF, FN_LINEAR = range(5)
 MAX_STACK = 16
 
 _dp = C.POINTER(C.c_double)
@@ -70,6 +71,8 @@ STATE_FIELDS = [
     ("j_left", _up, np.uint32, lambda E, P, F, G, S: (E, F)),
     ("j_taken", _up, np.uint32, lambda E, P, F, G, S: (E, F)),
     ("j_wage", _dp, np.float64, lambda E, P, F, G, S: (E, F)),
+    ("p_util_theta", _dp, np.float64, lambda E, P, F, G, S: (E, G + 1, P)),
+    ("f_prod_theta", _dp, np.float64, lambda E, P, F, G, S: (E, G, G + 1, F)),
 ]
 
 ACTION_FIELDS = [

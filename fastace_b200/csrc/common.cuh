@@ -11,6 +11,7 @@ struct StepParams {
     int E, P, F, S;
     uint32_t flags;
     uint32_t time_before;
+    int util_kind, prod_kind;       // fastace_function_kind_t of the persons' utility / the firms' production
     int compact;                    // 1: decisions come from `cz` (index/take/order arrays) + the float arrays of `ac`
     fastace_state_t st;
     fastace_actions_t ac;           // continuous actions are always read from here
@@ -60,6 +61,37 @@ __device__ __forceinline__ double pow_reward(double x, double y) { return exp(y 
 // One goods request by a buyer whose money/inventory live at (money, inv[g*istride]).
 // Agent::respond_to_offer -> review_offer_response -> accept_offer_response
 // (base/agent.cpp:99-161), fp64 updates in the reference's order.
+
+// VecToScalar::f of a function family over N inputs (functions/vecToScalar.cpp:30-32, 45-47, 67-69, 80-82,
+// 112-118), fp64, in the reference's operation order.  kReward selects the cheaper exp(y*log x) power for
+// CES utilities (reward only, 1e-5 tolerance); every other use takes the accurate fp64 pow.
+template <int N, bool kReward>
+__device__ __forceinline__ double eval_function(int kind, double tfp, const double (&share)[N], const double (&theta)[N],
+                                                double rho, const double (&x)[N]) {
+    if (kind == FASTACE_FN_CES) {
+        double inner = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++) inner += share[i] * (kReward ? pow_reward(x[i] + kEps, rho) : pow(x[i] + kEps, rho));
+        return tfp * (kReward ? pow_reward(inner, 1 / rho) : pow(inner, 1 / rho));
+    }
+    if (kind == FASTACE_FN_LINEAR) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++) s += share[i] * x[i];
+        return s;
+    }
+    if (kind == FASTACE_FN_LEONTIEF) {
+        double m = x[0] * share[0];
+#pragma unroll
+        for (int i = 1; i < N; i++) { const double v = x[i] * share[i]; if (v < m) m = v; }
+        return m;
+    }
+    // Cobb-Douglas / Stone-Geary
+    double p = 1.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) p *= pow(kind == FASTACE_FN_STONE_GEARY ? x[i] - theta[i] : x[i], share[i]);
+    return tfp * p;
+}
 
 // floor(x) as a lot count: how many times `inventory >= 1.0; inventory -= 1.0` succeeds
 // (agent.cpp:140,156; the subtraction is exact for x < 2^53).  NaN never compares "short".

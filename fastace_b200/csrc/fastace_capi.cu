@@ -50,6 +50,8 @@ static std::vector<FieldDesc> state_fields(const fastace_dims_t& d) {
         {offsetof(fastace_state_t, j_left), 4, E * F},
         {offsetof(fastace_state_t, j_taken), 4, E * F},
         {offsetof(fastace_state_t, j_wage), 8, E * F},
+        {offsetof(fastace_state_t, p_util_theta), 8, E * (G + 1) * P},
+        {offsetof(fastace_state_t, f_prod_theta), 8, E * G * (G + 1) * F},
     };
 }
 
@@ -122,6 +124,7 @@ struct fastace_env {
     fastace_dims_t dims;
     int device;
     uint32_t time;
+    int util_kind, prod_kind;
     uint64_t launches;
     void* state_block;      // one allocation holding every state array
     fastace_state_t dstate; // device pointers into state_block
@@ -288,6 +291,15 @@ int fastace_env_destroy(fastace_env_t* env) {
     return FASTACE_OK;
 }
 
+int fastace_env_set_function_kinds(fastace_env_t* env, int util_kind, int prod_kind) {
+    if (!env) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    if (util_kind < 0 || util_kind > FASTACE_FN_LINEAR || prod_kind < 0 || prod_kind > FASTACE_FN_LINEAR) {
+        set_error("unknown function kind"); return FASTACE_ERR_INVALID;
+    }
+    env->util_kind = util_kind; env->prod_kind = prod_kind;
+    return FASTACE_OK;
+}
+
 int fastace_env_dims(const fastace_env_t* env, fastace_dims_t* out_dims) {
     if (!env || !out_dims) { set_error("null argument"); return FASTACE_ERR_INVALID; }
     *out_dims = env->dims;
@@ -349,6 +361,7 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
     sp.E = env->dims.num_econ; sp.P = env->dims.num_persons; sp.F = env->dims.num_firms; sp.S = env->dims.stack_size;
     sp.flags = flags;
     sp.time_before = env->time;
+    sp.util_kind = env->util_kind; sp.prod_kind = env->prod_kind;
     sp.st = env->dstate;
     if (dcz) {
         sp.compact = 1;

@@ -400,7 +400,10 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
                             double sales = 0.0;   // income from goods sold to lower lanes of this window
 #pragma unroll
                             for (int g = 0; g < G; g++)
-                                if (g < cnt) sales += rec_price(first + g) * (double)min(pre[g], s_dord[NJ + first + g]);
+                                if (g < cnt) {
+                                    const int sold = min(pre[g], s_dord[NJ + first + g]);
+                                    if (sold > 0) sales += rec_price(first + g) * (double)sold;
+                                }
                             for (int k = 0; k < c; k++) {
                                 if (h >= d) { done = true; break; }                                  // firm.cpp:64
                                 if ((m0 + sales) - w * (double)h < w) { d = h; done = true; break; } // firm.cpp:80
@@ -469,11 +472,14 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
             const int j = s_fjob[f];
             if (j != kNone) {
                 const int h = s_tot[j];
-                m = m - s_jwage[j] * (double)h;
+                if (h > 0) m = m - s_jwage[j] * (double)h;
                 s_fnh[f] += (uint32_t)h;
             }
             const int first = s_ffirst[f], cnt = s_fcnt[f];
-            for (int o = first; o < first + cnt; o++) m = m + rec_price(o) * (double)s_tot[NJ + o];
+            for (int o = first; o < first + cnt; o++) {
+                const int sold = s_tot[NJ + o];
+                if (sold > 0) m = m + rec_price(o) * (double)sold;   // (an unsold offer may carry an inf/NaN price)
+            }
             s_fmoney[f] = m;
         }
         __syncwarp();
@@ -631,12 +637,13 @@ __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateP
             x[g + 1] = c;
             inv[g] = v - c;                                                 // utilMaxer.cpp:91
         }
-        const double rho = p.st.p_util_rho[t];
-        double inner = 0.0;                                                 // vecToScalar.cpp:112-114
+        double share[G + 1], theta[G + 1];
 #pragma unroll
-        for (int i = 0; i <= G; i++)
-            inner += p.st.p_util_share[((size_t)e * (G + 1) + i) * P + pid] * pow_reward(x[i] + kEps, rho);
-        p.out.p_reward[t] = p.st.p_util_tfp[t] * pow_reward(inner, 1 / rho);  // vecToScalar.cpp:116-118
+        for (int i = 0; i <= G; i++) {
+            share[i] = p.st.p_util_share[((size_t)e * (G + 1) + i) * P + pid];
+            theta[i] = (p.util_kind == FASTACE_FN_STONE_GEARY) ? p.st.p_util_theta[((size_t)e * (G + 1) + i) * P + pid] : 0.0;
+        }
+        p.out.p_reward[t] = eval_function<G + 1, true>(p.util_kind, p.st.p_util_tfp[t], share, theta, p.st.p_util_rho[t], x);
         p.st.p_labor[t] = labor;
 #pragma unroll
         for (int g = 0; g < G; g++) p.st.p_inv[((size_t)e * G + g) * P + pid] = inv[g];
@@ -673,12 +680,14 @@ __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateP
                 if (k == g) { xg = xk; invg = iv; }
             }
             const size_t ag = ((size_t)e * G + g) * F + f;
-            const double rho = p.st.f_prod_rho[ag];
-            double inner = 0.0;                                             // vecToScalar.cpp:112-114
+            double share[G + 1], theta[G + 1];
 #pragma unroll
-            for (int i = 0; i <= G; i++)
-                inner += p.st.f_prod_share[(((size_t)e * G + g) * (G + 1) + i) * F + f] * pow(in[i] + kEps, rho);
-            const double outg = p.st.f_prod_tfp[ag] * pow(inner, 1 / rho);
+            for (int i = 0; i <= G; i++) {
+                const size_t k = (((size_t)e * G + g) * (G + 1) + i) * F + f;
+                share[i] = p.st.f_prod_share[k];
+                theta[i] = (p.prod_kind == FASTACE_FN_STONE_GEARY) ? p.st.f_prod_theta[k] : 0.0;
+            }
+            const double outg = eval_function<G + 1, false>(p.prod_kind, p.st.f_prod_tfp[ag], share, theta, p.st.f_prod_rho[ag], in);
             newinv = invg + (outg - xg);                                    // profitMaxer.cpp:71
             // decisionNetHandler.cpp:591 amounts = proportion * inventory; neuralFirmDecisionMaker.cpp:129
             const double amount = (double)p.ac.f_offer_amt[ag] * newinv;

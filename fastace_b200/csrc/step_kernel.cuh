@@ -263,12 +263,13 @@ __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
             x[g + 1] = c[g];
             inv[g] = v - c[g];                                         // utilMaxer.cpp:91
         }
-        const double rho = p.st.p_util_rho[eP + pid];
-        double inner = 0.0;                                            // vecToScalar.cpp:112-114
+        double share[G + 1], theta[G + 1];
 #pragma unroll
-        for (int i = 0; i <= G; i++)
-            inner += p.st.p_util_share[((size_t)e * (G + 1) + i) * P + pid] * pow_reward(x[i] + kEps, rho);
-        const double util = p.st.p_util_tfp[eP + pid] * pow_reward(inner, 1 / rho);  // vecToScalar.cpp:116-118
+        for (int i = 0; i <= G; i++) {
+            share[i] = p.st.p_util_share[((size_t)e * (G + 1) + i) * P + pid];
+            theta[i] = (p.util_kind == FASTACE_FN_STONE_GEARY) ? p.st.p_util_theta[((size_t)e * (G + 1) + i) * P + pid] : 0.0;
+        }
+        const double util = eval_function<G + 1, true>(p.util_kind, p.st.p_util_tfp[eP + pid], share, theta, p.st.p_util_rho[eP + pid], x);
         p.out.p_reward[eP + pid] = util;
         p.st.p_money[eP + pid] = s_pmoney[pid];
         p.st.p_labor[eP + pid] = labor;
@@ -376,12 +377,15 @@ __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
             }
 #pragma unroll
             for (int g = 0; g < G; g++) {
-                const double rho = p.st.f_prod_rho[((size_t)e * G + g) * F + f];
-                double inner = 0.0;
+                double share[G + 1], theta[G + 1];
 #pragma unroll
-                for (int i = 0; i <= G; i++)
-                    inner += p.st.f_prod_share[(((size_t)e * G + g) * (G + 1) + i) * F + f] * pow(in[i] + kEps, rho);
-                const double outg = p.st.f_prod_tfp[((size_t)e * G + g) * F + f] * pow(inner, 1 / rho);
+                for (int i = 0; i <= G; i++) {
+                    const size_t k = (((size_t)e * G + g) * (G + 1) + i) * F + f;
+                    share[i] = p.st.f_prod_share[k];
+                    theta[i] = (p.prod_kind == FASTACE_FN_STONE_GEARY) ? p.st.f_prod_theta[k] : 0.0;
+                }
+                const double outg = eval_function<G + 1, false>(p.prod_kind, p.st.f_prod_tfp[((size_t)e * G + g) * F + f], share, theta,
+                                                                p.st.f_prod_rho[((size_t)e * G + g) * F + f], in);
                 inv[g] += (outg - x[g]);                               // profitMaxer.cpp:71
             }
 #pragma unroll

@@ -63,6 +63,10 @@ class BatchedEconomy:
     def get_numGoods(self):
         return self.dims.num_goods
 
+    def set_function_kinds(self, util_kind=_abi.FN_CES, prod_kind=_abi.FN_CES):
+        """VecToScalar family of the persons' utility / the firms' per-good production functions."""
+        lib.check(self._lib.fastace_env_set_function_kinds(self._h, int(util_kind), int(prod_kind)))
+
     def launch_count(self):
         n = C.c_uint64()
         lib.check(self._lib.fastace_env_launch_count(self._h, C.byref(n)))

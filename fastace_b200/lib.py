@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libfastace_b200.so")
 # every symbol include/fastace_b200.h declares
 EXPORTED_SYMBOLS = [
     "fastace_abi_version", "fastace_last_error", "fastace_device_count",
-    "fastace_env_create", "fastace_env_destroy", "fastace_env_dims", "fastace_env_time",
+    "fastace_env_create", "fastace_env_destroy", "fastace_env_dims", "fastace_env_time", "fastace_env_set_function_kinds",
     "fastace_env_set_state", "fastace_env_get_state", "fastace_env_device_state",
     "fastace_env_step_device", "fastace_env_step_host", "fastace_env_step_device_compact",
     "fastace_env_step_host_compact", "fastace_env_sync", "fastace_env_launch_count", "fastace_env_kernel_times",
@@ -51,6 +51,8 @@ def load():
     L.fastace_env_destroy.argtypes = [vp]
     L.fastace_env_dims.restype = C.c_int
     L.fastace_env_dims.argtypes = [vp, C.POINTER(_abi.Dims)]
+    L.fastace_env_set_function_kinds.restype = C.c_int
+    L.fastace_env_set_function_kinds.argtypes = [vp, C.c_int, C.c_int]
     L.fastace_env_time.restype = C.c_int
     L.fastace_env_time.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.fastace_env_set_state.restype = C.c_int

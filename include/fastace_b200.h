@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FASTACE_ABI_VERSION 1
+#define FASTACE_ABI_VERSION 2
 
 typedef enum fastace_status {
     FASTACE_OK = 0,
@@ -51,6 +51,27 @@ typedef enum fastace_status {
 /* Limits of the warp-per-economy kernel (one economy = one warp, books in shared memory). */
 #define FASTACE_MAX_GOODS 8
 #define FASTACE_MAX_STACK 16
+
+/*
+ * Function plugins (VecToScalar::f, src/functions/vecToScalar.h:13-106).  A person's utility is one
+ * VecToScalar over (1 - labor, consumption); a firm's production is one VecToScalar per output good
+ * over (laborHired, inputs) (SumOfVecToVec of VToVFromVToS, src/functions/vecToVec.h:27-73).
+ * The kind is chosen per env; the parameter arrays of fastace_state_t are read as:
+ *   CES           tfp, share (normalised), rho              tfp*(sum share_i (x_i+1e-8)^rho)^(1/rho)  vecToScalar.cpp:112-118
+ *   COBB_DOUGLAS  tfp, share = elasticities                 tfp*prod x_i^e_i                          :45-47
+ *                 (CobbDouglasCRS = elasticities normalised by the caller, :54-56)
+ *   STONE_GEARY   tfp, share = elasticities, theta          tfp*prod (x_i-theta_i)^e_i                :67-69
+ *   LEONTIEF      share = productivities                    min_i x_i*p_i                             :80-82
+ *   LINEAR        share = productivities                    sum_i p_i*x_i                             :30-32
+ * (`df`, ProfitFunc and the ifopt solvers are never called from Economy::time_step.)
+ */
+typedef enum fastace_function_kind {
+    FASTACE_FN_CES = 0,
+    FASTACE_FN_COBB_DOUGLAS = 1,
+    FASTACE_FN_STONE_GEARY = 2,
+    FASTACE_FN_LEONTIEF = 3,
+    FASTACE_FN_LINEAR = 4
+} fastace_function_kind_t;
 
 typedef struct fastace_dims {
     int32_t num_econ;    /* E  independent economies in this env (this rank's shard)      */
@@ -111,6 +132,9 @@ typedef struct fastace_state {
     uint32_t* j_left;       /* [E][F]                                   */
     uint32_t* j_taken;      /* [E][F]                                   */
     double*   j_wage;       /* [E][F]       wage per job lot (= wage/0.5) */
+    /* StoneGeary thresholds (only read for FASTACE_FN_STONE_GEARY; zero after env creation) */
+    double*   p_util_theta; /* [E][G+1][P]                              */
+    double*   f_prod_theta; /* [E][G][G+1][F]                           */
 } fastace_state_t;
 
 /*
@@ -232,6 +256,10 @@ int fastace_env_destroy(fastace_env_t* env);
 int fastace_env_dims(const fastace_env_t* env, fastace_dims_t* out_dims);
 /* Economy::get_time (base.h:91) — identical for all economies of an env */
 int fastace_env_time(const fastace_env_t* env, uint32_t* out_time);
+
+/* Utility / production function families of this env (default: CES / CES, the only pair the shipped
+ * neural plugins support, neuralPersonDecisionMaker.cpp:34, neuralFirmDecisionMaker.cpp:40-45). */
+int fastace_env_set_function_kinds(fastace_env_t* env, int util_kind, int prod_kind);
 
 /* ---- state I/O --------------------------------------------------------------------- */
 /* Host -> device.  NULL members are left untouched.  Also sets the env time. */

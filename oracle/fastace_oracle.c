@@ -61,6 +61,44 @@ double fastace_oracle_cobb_douglas_f(double tfp, const double* elast, const doub
     return tfp * prod;
 }
 
+static int g_util_kind = FASTACE_FN_CES, g_prod_kind = FASTACE_FN_CES;
+void fastace_oracle_set_function_kinds(int util_kind, int prod_kind) { g_util_kind = util_kind; g_prod_kind = prod_kind; }
+
+/* VecToScalar::f by family, each in the reference's operation order (Eigen reductions over a
+ * handful of elements evaluate left to right):
+ *   Linear::f (productivities*quantities).sum()                      functions/vecToScalar.cpp:30-32
+ *   CobbDouglas::f tfp*pow(quantities, elasticities).prod()            :45-47
+ *   StoneGeary::f  tfp*pow(quantities - thresholds, elasticities).prod() :67-69
+ *   Leontief::f    (quantities*productivities).minCoeff()              :80-82
+ *   CES::f                                                             :112-118 */
+double fastace_oracle_function_f(int kind, double tfp, const double* share, const double* theta, double rho,
+                                 const double* x, int n, int stride) {
+    switch (kind) {
+        case FASTACE_FN_LINEAR: {
+            double s = 0.0;
+            for (int i = 0; i < n; i++) s += share[(size_t)i * stride] * x[i];
+            return s;
+        }
+        case FASTACE_FN_COBB_DOUGLAS: {
+            double p = 1.0;
+            for (int i = 0; i < n; i++) p *= pow(x[i], share[(size_t)i * stride]);
+            return tfp * p;
+        }
+        case FASTACE_FN_STONE_GEARY: {
+            double p = 1.0;
+            for (int i = 0; i < n; i++) p *= pow(x[i] - (theta ? theta[(size_t)i * stride] : 0.0), share[(size_t)i * stride]);
+            return tfp * p;
+        }
+        case FASTACE_FN_LEONTIEF: {
+            double m = x[0] * share[0];
+            for (int i = 1; i < n; i++) { double v = x[i] * share[(size_t)i * stride]; if (v < m) m = v; }
+            return m;
+        }
+        default:
+            return fastace_oracle_ces_f(tfp, share, rho, x, n, stride);
+    }
+}
+
 typedef struct {
     int P, F, G, S, cap; /* cap = F*G */
     uint32_t flags;
@@ -251,7 +289,9 @@ static void step_economy(const fastace_dims_t* d, fastace_state_t* st, const fas
             c[g] = ec.p_inv[(size_t)g * P + p] * (double)p_consume[(size_t)g * P + p];
             x[g + 1] = c[g];
         }
-        double util = fastace_oracle_ces_f(ec.p_tfp[p], ec.p_share + p, ec.p_rho[p], x, G + 1, P);
+        double util = fastace_oracle_function_f(g_util_kind, ec.p_tfp[p], ec.p_share + p,
+                                                st->p_util_theta ? st->p_util_theta + (size_t)e * (G + 1) * P + p : NULL,
+                                                ec.p_rho[p], x, G + 1, P);
         out->p_reward[(size_t)e * P + p] = util;
         for (int g = 0; g < G; g++) ec.p_inv[(size_t)g * P + p] -= c[g];
     }
@@ -306,8 +346,9 @@ static void step_economy(const fastace_dims_t* d, fastace_state_t* st, const fas
             in[g + 1] = x[g];
         }
         for (int g = 0; g < G; g++)
-            prod[g] = fastace_oracle_ces_f(ec.f_tfp[(size_t)g * F + f], ec.f_share + (size_t)g * (G + 1) * F + f,
-                                           ec.f_rho[(size_t)g * F + f], in, G + 1, F);
+            prod[g] = fastace_oracle_function_f(g_prod_kind, ec.f_tfp[(size_t)g * F + f], ec.f_share + (size_t)g * (G + 1) * F + f,
+                                                st->f_prod_theta ? st->f_prod_theta + ((size_t)e * G + g) * (G + 1) * F + f : NULL,
+                                                ec.f_rho[(size_t)g * F + f], in, G + 1, F);
         for (int g = 0; g < G; g++) ec.f_inv[(size_t)g * F + f] += (prod[g] - x[g]);
 
         /* ProfitMaxer::sell_goods (profitMaxer.cpp:74-86): choose_good_offers first

@@ -10,6 +10,12 @@ extern "C" {
 /* One Economy::time_step() for every economy, in place on HOST arrays.
  * Economies e with first_econ <= e < first_econ + count are stepped (so callers can
  * spread economies over threads); returns 0, or -1 on invalid dims. */
+/* function families used by the next step calls (process-wide; default CES / CES) */
+void fastace_oracle_set_function_kinds(int util_kind, int prod_kind);
+/* VecToScalar::f of the given family; share/theta read with `stride` (theta may be NULL) */
+double fastace_oracle_function_f(int kind, double tfp, const double* share, const double* theta, double rho,
+                                 const double* x, int n, int stride);
+
 int fastace_oracle_step(const fastace_dims_t* dims, fastace_state_t* state,
                         const fastace_actions_t* actions, const fastace_step_out_t* out,
                         uint32_t flags, uint32_t time_before, int first_econ, int count);

@@ -52,6 +52,11 @@ class Oracle:
         L.fastace_oracle_ces_params.argtypes = [C.POINTER(C.c_double), C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.fastace_oracle_cobb_douglas_f.restype = C.c_double
         L.fastace_oracle_cobb_douglas_f.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+        L.fastace_oracle_set_function_kinds.restype = None
+        L.fastace_oracle_set_function_kinds.argtypes = [C.c_int, C.c_int]
+        L.fastace_oracle_function_f.restype = C.c_double
+        L.fastace_oracle_function_f.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                                                C.POINTER(C.c_double), C.c_int, C.c_int]
         L.fastace_oracle_double_to_int.restype = C.c_int32
         L.fastace_oracle_double_to_int.argtypes = [C.c_double]
 
@@ -67,6 +72,17 @@ class Oracle:
             rc = self.lib.fastace_oracle_step(C.byref(d), C.byref(st), C.byref(ac), C.byref(ou), flags, time_before, 0, d.num_econ)
         if rc != 0:
             raise RuntimeError("fastace_oracle_step failed")
+
+    def set_function_kinds(self, util_kind=0, prod_kind=0):
+        self.lib.fastace_oracle_set_function_kinds(int(util_kind), int(prod_kind))
+
+    def function_f(self, kind, tfp, share, theta, rho, x):
+        s = np.ascontiguousarray(share, dtype=np.float64)
+        th = np.ascontiguousarray(theta if theta is not None else np.zeros_like(s), dtype=np.float64)
+        q = np.ascontiguousarray(x, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        return self.lib.fastace_oracle_function_f(int(kind), tfp, s.ctypes.data_as(dp), th.ctypes.data_as(dp), rho,
+                                                  q.ctypes.data_as(dp), len(q), 1)
 
     def ces_f(self, tfp, share_norm, rho, x):
         s = np.ascontiguousarray(share_norm, dtype=np.float64)
@@ -92,11 +108,13 @@ class Oracle:
 class Reference:
     """The reference's own Economy objects behind the same array interface."""
 
-    def __init__(self, dims, state, seed):
+    def __init__(self, dims, state, seed, util_kind=0, prod_kind=0):
         if not have_reference():
             raise FileNotFoundError(REF_SO)
         self.lib = C.CDLL(REF_SO)
         L = self.lib
+        L.fastace_ref_set_function_kinds.argtypes = [C.c_int, C.c_int]
+        L.fastace_ref_set_function_kinds(int(util_kind), int(prod_kind))
         L.fastace_ref_create.restype = C.c_void_p
         L.fastace_ref_create.argtypes = [C.POINTER(_abi.Dims), C.POINTER(_abi.State), C.c_uint32]
         L.fastace_ref_destroy.argtypes = [C.c_void_p]

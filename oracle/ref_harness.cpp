@@ -313,7 +313,27 @@ static int firm_id(const RefEconomyBox& b, const Agent* f) {
     return -1;
 }
 
+static int g_ref_util_kind = FASTACE_FN_CES, g_ref_prod_kind = FASTACE_FN_CES;
+
+// the reference's own function objects for a family, parameters written through public members
+static std::shared_ptr<VecToScalar> make_function(int kind, double tfp, const Eigen::ArrayXd& share,
+                                                  const Eigen::ArrayXd& theta, double rho) {
+    switch (kind) {
+        case FASTACE_FN_LINEAR: return std::make_shared<Linear>(share);
+        case FASTACE_FN_COBB_DOUGLAS: return std::make_shared<CobbDouglas>(tfp, share);
+        case FASTACE_FN_STONE_GEARY: return std::make_shared<StoneGeary>(tfp, share, theta);
+        case FASTACE_FN_LEONTIEF: return std::make_shared<Leontief>(share);
+        default: {
+            auto ces = std::make_shared<CES>(1.0, share, 0.5);
+            ces->tfp = tfp; ces->shareParams = share; ces->substitutionParam = rho;
+            return ces;
+        }
+    }
+}
+
 extern "C" {
+
+void fastace_ref_set_function_kinds(int util_kind, int prod_kind) { g_ref_util_kind = util_kind; g_ref_prod_kind = prod_kind; }
 
 // Builds E reference economies from a host fastace_state_t (markets must be empty: the
 // reference has no way to load a mid-episode book).  Economy e's rng is seeded with
@@ -334,10 +354,11 @@ fastace_ref* fastace_ref_create(const fastace_dims_t* dims, const fastace_state_
             Eigen::ArrayXd inv(G), share(G + 1);
             for (int g = 0; g < G; g++) inv(g) = st->p_inv[((size_t)e * G + g) * P + p];
             for (int i = 0; i <= G; i++) share(i) = st->p_util_share[((size_t)e * (G + 1) + i) * P + p];
-            auto ces = std::make_shared<CES>(1.0, share, 0.5);
-            ces->tfp = st->p_util_tfp[(size_t)e * P + p];
-            ces->shareParams = share;
-            ces->substitutionParam = st->p_util_rho[(size_t)e * P + p];
+            Eigen::ArrayXd theta = Eigen::ArrayXd::Zero(G + 1);
+            if (st->p_util_theta)
+                for (int i = 0; i <= G; i++) theta(i) = st->p_util_theta[((size_t)e * (G + 1) + i) * P + p];
+            std::shared_ptr<VecToScalar> ces = make_function(g_ref_util_kind, st->p_util_tfp[(size_t)e * P + p], share, theta,
+                                                             st->p_util_rho[(size_t)e * P + p]);
             auto person = UtilMaxer::init(
                 b.economy.get(), inv, st->p_money[(size_t)e * P + p], ces, 0.9,
                 std::make_shared<ReplayPerson>(&b.ctx, p));
@@ -353,13 +374,17 @@ fastace_ref* fastace_ref_create(const fastace_dims_t* dims, const fastace_state_
                 for (int i = 0; i <= G; i++) s(i) = st->f_prod_share[(((size_t)e * G + g) * (G + 1) + i) * F + f];
                 shares.push_back(s);
             }
-            auto prod = create_CES_VecToVec(tfps, shares, elast);
+            // one VecToScalar per output good, summed (create_CES_VecToVec pattern, vecToVec.cpp:34-53)
+            std::vector<std::shared_ptr<VecToVec>> inner(G);
             for (int g = 0; g < G; g++) {
-                auto ces = std::static_pointer_cast<VToVFromVToS<CES>>(prod->innerFunctions[g])->vecToScalar;
-                ces->tfp = st->f_prod_tfp[((size_t)e * G + g) * F + f];
-                ces->shareParams = shares[g];
-                ces->substitutionParam = st->f_prod_rho[((size_t)e * G + g) * F + f];
+                Eigen::ArrayXd theta = Eigen::ArrayXd::Zero(G + 1);
+                if (st->f_prod_theta)
+                    for (int i = 0; i <= G; i++) theta(i) = st->f_prod_theta[(((size_t)e * G + g) * (G + 1) + i) * F + f];
+                inner[g] = std::make_shared<VToVFromVToS<VecToScalar>>(
+                    make_function(g_ref_prod_kind, st->f_prod_tfp[((size_t)e * G + g) * F + f], shares[g], theta,
+                                  st->f_prod_rho[((size_t)e * G + g) * F + f]), G, g);
             }
+            auto prod = std::make_shared<SumOfVecToVec>(inner);
             auto dm = std::make_shared<ReplayFirm>(&b.ctx, f);
             auto firm = ProfitMaxer::init(
                 b.economy.get(), std::vector<std::shared_ptr<Agent>>(), inv,
@@ -453,11 +478,13 @@ int fastace_ref_get_state(const fastace_ref* h, fastace_state_t* st, uint32_t* t
             if (st->p_labor) st->p_labor[(size_t)e * P + p] = person->get_laborSupplied();
             for (int g = 0; g < G; g++)
                 if (st->p_inv) st->p_inv[((size_t)e * G + g) * P + p] = person->get_inventory()(g);
-            auto ces = std::static_pointer_cast<const CES>(person->get_utilFunc());
-            if (st->p_util_tfp) st->p_util_tfp[(size_t)e * P + p] = ces->tfp;
-            if (st->p_util_rho) st->p_util_rho[(size_t)e * P + p] = ces->substitutionParam;
-            for (int i = 0; i <= G; i++)
-                if (st->p_util_share) st->p_util_share[((size_t)e * (G + 1) + i) * P + p] = ces->shareParams(i);
+            auto ces = std::dynamic_pointer_cast<const CES>(person->get_utilFunc());
+            if (ces) {
+                if (st->p_util_tfp) st->p_util_tfp[(size_t)e * P + p] = ces->tfp;
+                if (st->p_util_rho) st->p_util_rho[(size_t)e * P + p] = ces->substitutionParam;
+                for (int i = 0; i <= G; i++)
+                    if (st->p_util_share) st->p_util_share[((size_t)e * (G + 1) + i) * P + p] = ces->shareParams(i);
+            }
         }
         for (int f = 0; f < F; f++) {
             const auto& firm = b.firms[f];
@@ -468,7 +495,9 @@ int fastace_ref_get_state(const fastace_ref* h, fastace_state_t* st, uint32_t* t
                 if (st->f_inv) st->f_inv[((size_t)e * G + g) * F + f] = firm->get_inventory()(g);
             auto prod = std::static_pointer_cast<const SumOfVecToVec>(firm->get_prodFunc());
             for (int g = 0; g < G; g++) {
-                auto ces = std::static_pointer_cast<const VToVFromVToS<CES>>(prod->innerFunctions[g])->vecToScalar;
+                auto ces = std::dynamic_pointer_cast<CES>(
+                    std::static_pointer_cast<const VToVFromVToS<VecToScalar>>(prod->innerFunctions[g])->vecToScalar);
+                if (!ces) continue;
                 if (st->f_prod_tfp) st->f_prod_tfp[((size_t)e * G + g) * F + f] = ces->tfp;
                 if (st->f_prod_rho) st->f_prod_rho[((size_t)e * G + g) * F + f] = ces->substitutionParam;
                 for (int i = 0; i <= G; i++)

@@ -116,6 +116,9 @@ def test_extreme_actions(oracle):
         act["f_job_labor"][3, :2] = np.inf
         act["f_offer_amt"][0] = 1.0
         act["f_offer_price"][0] = 1e-3
+        act["f_offer_price"][1, 0, :2] = np.inf     # exp() overflow of a policy net: nobody can afford it
+        act["f_offer_price"][1, 1, 2:4] = np.nan    # never compares affordable
+        act["f_job_wage"][3, 2:4] = np.inf          # clipped to 1e8
         act["p_consume"][1] = 0.0
         act["p_consume"][2] = 1.0
         if t % 3 == 0:
