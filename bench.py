@@ -351,6 +351,48 @@ def run_ours(args):
         rollout = {"unit": METRIC, "policy": "11 decision nets (hidden 100 x 12 layers), random init, batched over all agents via torch",
                    "semantics": "decisions taken from the state at the start of the step (DESIGN.md §7)", **results}
 
+    # ---- training (row f-2): T-step rollout with recording + one advantage actor-critic update -----------
+    training = None
+    if args.train:
+        from fastace_b200 import policy, trainer
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.manual_seed(0)                     # identical initial replicas on every rank
+        tnets = policy.DecisionNets(numGoods=G, stackSize=S).to(dev)
+        a2c = trainer.AdvantageActorCritic(tnets, adam_kwargs=dict(fused=True))
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(4321 + rank)
+        pol = policy.BatchedPolicy(env, tnets, generator=gen)
+        perm_dev = [(torch.from_numpy(a["perm_person"]).to(dev), torch.from_numpy(a["perm_firm"]).to(dev)) for a in acts]
+
+        class _Orders:
+            k = 0
+            def next(self):
+                self.k += 1
+                return perm_dev[self.k % len(perm_dev)]
+
+        T_train = args.train_steps
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for it in range(2):                      # 1 warm-up update, 1 timed
+            reset_state(0)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            evs[0].record()
+            ep = trainer.run_episode(pol, _Orders(), douts, T_train, flags=_abi.IDX_ABSOLUTE)
+            evs[1].record()
+            loss = a2c.train_on_episode(ep)
+            evs[2].record()
+            torch.cuda.synchronize()
+        t_t = torch.tensor([evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_t, op=dist.ReduceOp.MAX)
+        roll_ms, upd_ms = (float(x) for x in t_t.tolist())
+        training = {"unit": METRIC, "episode_steps": T_train, "economies": world * E, "rollout_ms": roll_ms, "update_ms": upd_ms,
+                    "value": world * E * (P + F) * T_train / ((roll_ms + upd_ms) * 1e-3), "loss": loss,
+                    "economies_dropped_non_finite_rank0": a2c.last_dropped,
+                    "gradient_allreduce": "nccl, one flat bucket" if world > 1 else None, "precision": "tf32 matmul, fp32 params",
+                    "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
+
     if rank == 0:
         peak, peak_src = peaks()
         avg_step_s = total_ms / args.steps * 1e-3  # rank 0's own steps
@@ -386,6 +428,8 @@ def run_ours(args):
         }
         if rollout is not None:
             line["full_rollout"] = rollout
+        if training is not None:
+            line["training"] = training
         if world == 1 and not args.no_cpu:
             base = cpu_baseline(args.cpu_sample, EPISODE)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -405,6 +449,8 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (diagnostic)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--train", action="store_true", help="also time one A2C update (rollout + re-evaluation backward + Adam)")
+    ap.add_argument("--train-steps", type=int, default=20, help="episode length of the --train leg (DEFAULT_EPISODE_LENGTH)")
     ap.add_argument("--rollout", action="store_true", help="also time the full rollout with the batched policy forward")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -226,24 +226,27 @@ class DecisionNets(nn.Module):
 
 
 # ---- sampling rules (decisionNetHandler.cpp:27-46, 368-387) ---------------------------
-def sample_normal(params, noise=None):
+def sample_normal(params, noise=None, detach=False):
     """params[..., 0] = mu, params[..., 1] = log sigma.  Returns (x, log p(x)) with the reference's
-    log-density -0.5*((x-mu)/sigma)^2 - log(sigma*sqrt(2*pi))."""
+    log-density -0.5*((x-mu)/sigma)^2 - log(sigma*sqrt(2*pi)).  detach=False keeps x = eps*sigma + mu in
+    the autograd graph like the reference does."""
     mu, sigma = params[..., 0], torch.exp(params[..., 1])
     if noise is None:
         noise = torch.randn_like(mu)
     x = noise * sigma + mu
+    if detach:
+        x = x.detach()
     logp = -0.5 * ((x - mu) / sigma) ** 2 - torch.log(sigma * SQRT2PI)
     return x, logp
 
 
-def sample_logit_normal(params, noise=None):
-    x, logp = sample_normal(params, noise)
+def sample_logit_normal(params, noise=None, detach=False):
+    x, logp = sample_normal(params, noise, detach)
     return torch.sigmoid(x), logp       # no Jacobian term, as in the reference (:38-41)
 
 
-def sample_log_normal(params, noise=None):
-    x, logp = sample_normal(params, noise)
+def sample_log_normal(params, noise=None, detach=False):
+    x, logp = sample_normal(params, noise, detach)
     return torch.exp(x), logp           # no Jacobian term (:43-46)
 
 
@@ -256,7 +259,136 @@ def sample_bernoulli(probas, uniform=None):
     return take, logp
 
 
-# ---- batched decision step over a BatchedEconomy -----------------------------------------------------
+# ---- batched decisions: snapshot -> draws -> evaluate ------------------------------------------------
+SNAPSHOT_KEYS = ("m_count", "m_good", "m_price", "j_count", "j_wage",
+                 "p_money", "p_inv", "p_util_tfp", "p_util_share", "p_util_rho",
+                 "f_money", "f_labor", "f_inv", "f_prod_tfp", "f_prod_share", "f_prod_rho")
+
+
+def snapshot(state):
+    """Copy of the state tensors (env layout, fastace_state_t) the decisions of one step read."""
+    return {k: state[k].clone() for k in SNAPSHOT_KEYS}
+
+
+def snapshot_dims(snap):
+    E, G, P = snap["p_inv"].shape
+    return E, P, snap["f_money"].shape[1], G
+
+
+def draw(snap, stackSize, generator=None):
+    """All random numbers of one step: offer indices (torch::randint(0, count, S) per agent,
+    decisionNetHandler.cpp:327-365), the uniforms of the Bernoulli takes (:372, 450) and the standard
+    normals of sample_normal (:31).  count == 0 -> index 0 (masked out by `valid` in evaluate)."""
+    E, P, F, G = snapshot_dims(snap)
+    S, dev = stackSize, snap["p_money"].device
+    rand = lambda *shape: torch.rand(*shape, device=dev, generator=generator)
+    randn = lambda *shape: torch.randn(*shape, device=dev, generator=generator)
+
+    def indices(count, n_agents):
+        c = count.long().clamp(min=1).view(E, 1, 1)
+        u = rand(E, n_agents, S)
+        return torch.minimum((u * c.to(u.dtype)).long(), c - 1)
+
+    nM, nJ = snap["m_count"], snap["j_count"]
+    return {
+        "pidxM": indices(nM, P), "pidxJ": indices(nJ, P), "fidxM": indices(nM, F), "fidxJ": indices(nJ, F),
+        "u_job": rand(E, P, S), "u_good": rand(E, P, S), "u_fgood": rand(E, F, S),
+        "n_cons": randn(E, P, G), "n_prod": randn(E, F, G), "n_amt": randn(E, F, G), "n_price": randn(E, F, G),
+        "n_lab": randn(E, F), "n_wage": randn(E, F),
+    }
+
+
+def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference"):
+    """Forward of the 11 nets for every agent of every economy + sampling with the given draws.
+    Differentiable when autograd is enabled (the trainer re-evaluates recorded steps with it).
+
+    sample_grad: "reference" keeps the reparameterised sample attached to the graph exactly as the
+    reference does (decisionNetHandler.cpp:31-32: the quadratic term of the log-density then has zero
+    gradient, only -log sigma trains); "score_function" detaches the sample (the textbook estimator).
+
+    Returns (decoded, info): decoded = agent-major action tensors, info = log-probabilities [E,agents]
+    and state values."""
+    E, P, F, G = snapshot_dims(snap)
+    S = draws["pidxM"].shape[-1]
+    st = snap
+    f32 = torch.float32
+    ctx = torch.autocast("cuda", dtype=autocast_dtype) if autocast_dtype is not None else _NullCtx()
+    with ctx:
+        # --- market snapshot + encoder forward (update_encodedOffers / JobOffers, :236-275)
+        nM, nJ = st["m_count"].long(), st["j_count"].long()
+        good = st["m_good"].long().clamp(0, G - 1)
+        qty = torch.nn.functional.one_hot(good, G).to(f32)                       # quantities = e_g * 1.0
+        feats = torch.cat([qty, st["m_price"].to(f32).unsqueeze(-1)], dim=-1)    # [E, capM, G+1]
+        encM = nets.offerEncoder(feats)                                          # [E, capM, enc]
+        jfeat = torch.stack([torch.full_like(st["j_wage"], 0.5), st["j_wage"]], dim=-1).to(f32)
+        encJ = nets.jobOfferEncoder(jfeat)                                       # [E, F, enc]
+        validM = (nM > 0).view(E, 1, 1)
+        validJ = (nJ > 0).view(E, 1, 1)
+
+        def gather(enc, idx, valid):    # enc [E,N,enc], idx [E,A,S] -> [E,A,S,enc]; zeros when the market is empty (:542-565)
+            out = torch.gather(enc.unsqueeze(1).expand(-1, idx.shape[1], -1, -1), 2,
+                               idx.unsqueeze(-1).expand(-1, -1, -1, enc.shape[-1]))
+            return out * valid.unsqueeze(-1).to(out.dtype)
+
+        # --- persons
+        pidxM, pidxJ = draws["pidxM"], draws["pidxJ"]
+        util = torch.cat([st["p_util_tfp"].unsqueeze(1), st["p_util_share"], st["p_util_rho"].unsqueeze(1)], dim=1)
+        util = util.permute(0, 2, 1).to(f32)                                     # [E,P,G+3]: tfp, shares, rho (:30-38)
+        money = st["p_money"].to(f32).unsqueeze(-1)
+        if "p_labor_input" in st:                                                 # tests inject it; the env path uses 0
+            labor0 = st["p_labor_input"].to(f32).unsqueeze(-1)
+        else:
+            labor0 = torch.zeros_like(money)                                      # laborSupplied was just reset (person.cpp:24)
+        inv = st["p_inv"].permute(0, 2, 1).to(f32)
+        eM, eJ = gather(encM, pidxM, validM), gather(encJ, pidxJ, validJ)
+        p_value = nets.valueNet(eM, eJ, util, money, labor0, inv).squeeze(-1)
+        p_job_p = nets.laborSearchNet(eJ, util, money, labor0, inv)
+        p_good_p = nets.purchaseNet(eM, util, money, labor0, inv)
+        cons = nets.consumptionNet(util, money, labor0, inv)
+        # --- firms
+        fidxM, fidxJ = draws["fidxM"], draws["fidxJ"]
+        pf = torch.cat([st["f_prod_tfp"].unsqueeze(2), st["f_prod_share"], st["f_prod_rho"].unsqueeze(2)], dim=2)
+        pf = pf.permute(0, 3, 1, 2).reshape(E, F, G * (G + 3)).to(f32)           # per good: tfp, shares, rho (:36-48)
+        fmoney = st["f_money"].to(f32).unsqueeze(-1)
+        flabor = st["f_labor"].to(f32).unsqueeze(-1)
+        finv = st["f_inv"].permute(0, 2, 1).to(f32)
+        feM, feJ = gather(encM, fidxM, validM), gather(encJ, fidxJ, validJ)
+        f_value = nets.firmValueNet(feM, feJ, pf, fmoney, flabor, finv).squeeze(-1)
+        f_good_p = nets.firmPurchaseNet(feM, pf, fmoney, flabor, finv)
+        prod = nets.productionNet(pf, fmoney, flabor, finv)
+        offer = nets.offerNet(feM, pf, fmoney, flabor, finv)
+        job = nets.jobOfferNet(feJ, pf, fmoney, flabor, finv)
+    # --- sampling (fp32)
+    detach = sample_grad != "reference"
+    p_job_take, lp_job = sample_bernoulli(p_job_p.float(), draws["u_job"])
+    p_good_take, lp_good = sample_bernoulli(p_good_p.float(), draws["u_good"])
+    f_good_take, lp_fgood = sample_bernoulli(f_good_p.float(), draws["u_fgood"])
+    cons_x, lp_cons = sample_logit_normal(cons.float(), draws["n_cons"], detach)
+    prod_x, lp_prod = sample_logit_normal(prod.float(), draws["n_prod"], detach)
+    amt_x, lp_amt = sample_logit_normal(offer.float()[..., 0:2], draws["n_amt"], detach)
+    price_x, lp_price = sample_log_normal(offer.float()[..., 2:4], draws["n_price"], detach)
+    lab_x, lp_lab = sample_log_normal(job.float()[..., 0:2], draws["n_lab"], detach)
+    wage_x, lp_wage = sample_log_normal(job.float()[..., 2:4], draws["n_wage"], detach)
+    decoded = {
+        "p_job_idx": pidxJ, "p_job_take": p_job_take & validJ, "p_good_idx": pidxM, "p_good_take": p_good_take & validM,
+        "p_consume": cons_x, "f_good_idx": fidxM, "f_good_take": f_good_take & validM, "f_prod": prod_x,
+        "f_offer_amt": amt_x, "f_offer_price": price_x, "f_job_labor": lab_x, "f_job_wage": wage_x,
+    }
+    nan = torch.full_like(lp_good, float("nan"))
+    info = {
+        "value_person": p_value.float(), "value_firm": f_value.float(),
+        # empty market: purchase log-prob NaN = "no decision", job search 0.0 (decisionNetHandler.cpp:398-403, 476-480)
+        "logp_purchase": torch.where(validM.view(E, 1), lp_good, nan),
+        "logp_laborSearch": torch.where(validJ.view(E, 1), lp_job, torch.zeros_like(lp_job)),
+        "logp_consumption": lp_cons.sum(-1),
+        "logp_firmPurchase": torch.where(validM.view(E, 1), lp_fgood, torch.full_like(lp_fgood, float("nan"))),
+        "logp_production": lp_prod.sum(-1),
+        "logp_offer": lp_amt.sum(-1) + lp_price.sum(-1),
+        "logp_jobOffer": lp_lab + lp_wage,
+    }
+    return decoded, info
+
+
 class BatchedPolicy:
     """Runs the 7 decisions of every agent of every economy at once and writes the action tensors
     of one env step (fastace_actions_t layout).
@@ -276,109 +408,26 @@ class BatchedPolicy:
         self.actions = env.alloc_actions()
         self.packed = env.pack_device("actions", self.actions)
 
-    def _rand(self, *shape):
-        return torch.rand(*shape, device=self.dev, generator=self.gen)
-
-    def _randn(self, *shape):
-        return torch.randn(*shape, device=self.dev, generator=self.gen)
-
-    def _draw_indices(self, count, n_agents):
-        """torch::randint(0, count, S) per agent (decisionNetHandler.cpp:327-365); count==0 -> no decision"""
-        u = self._rand(self.E, n_agents, self.S)
-        c = count.clamp(min=1).view(self.E, 1, 1)
-        return torch.minimum((u * c.to(u.dtype)).long(), c - 1)
-
     @torch.no_grad()
-    def decide(self, perms):
+    def decide(self, perms, record=None):
         """Fill self.actions for one step.  perms = (perm_person, perm_firm) int32 [E,P] / [E,F] (host or device).
-        Returns a dict with log-probabilities and state values (device tensors) for a trainer."""
-        E, P, F, G, S = self.E, self.P, self.F, self.G, self.S
-        st, nets, a = self.state, self.nets, self.actions
-        f32 = torch.float32
-        ctx = torch.autocast("cuda", dtype=self.autocast_dtype) if self.autocast_dtype is not None else _NullCtx()
-        with ctx:
-            # --- market snapshot + encoder forward (update_encodedOffers / JobOffers, :236-275)
-            capM = F * G
-            nM, nJ = st["m_count"].long(), st["j_count"].long()
-            good = st["m_good"].long().clamp(0, G - 1)
-            qty = torch.nn.functional.one_hot(good, G).to(f32)                       # quantities = e_g * 1.0
-            feats = torch.cat([qty, st["m_price"].to(f32).unsqueeze(-1)], dim=-1)    # [E, capM, G+1]
-            encM = nets.offerEncoder(feats)                                          # [E, capM, enc]
-            jfeat = torch.stack([torch.full_like(st["j_wage"], 0.5), st["j_wage"]], dim=-1).to(f32)
-            encJ = nets.jobOfferEncoder(jfeat)                                       # [E, F, enc]
-            validM = (nM > 0).view(E, 1, 1)
-            validJ = (nJ > 0).view(E, 1, 1)
-
-            def gather(enc, idx, valid):    # enc [E,N,enc], idx [E,A,S] -> [E,A,S,enc]; zeros when the market is empty (:542-565)
-                out = torch.gather(enc.unsqueeze(1).expand(-1, idx.shape[1], -1, -1), 2,
-                                   idx.unsqueeze(-1).expand(-1, -1, -1, enc.shape[-1]))
-                return out * valid.unsqueeze(-1).to(out.dtype)
-
-            # --- persons
-            pidxM, pidxJ = self._draw_indices(nM, P), self._draw_indices(nJ, P)
-            util = torch.cat([st["p_util_tfp"].unsqueeze(1), st["p_util_share"], st["p_util_rho"].unsqueeze(1)], dim=1)
-            util = util.permute(0, 2, 1).to(f32)                                     # [E,P,G+3]: tfp, shares, rho (:30-38)
-            money = st["p_money"].to(f32).unsqueeze(-1)
-            labor0 = torch.zeros_like(money)                                          # laborSupplied was just reset (person.cpp:24)
-            inv = st["p_inv"].permute(0, 2, 1).to(f32)
-            eM, eJ = gather(encM, pidxM, validM), gather(encJ, pidxJ, validJ)
-            p_value = nets.valueNet(eM, eJ, util, money, labor0, inv).squeeze(-1)
-            p_job_p = nets.laborSearchNet(eJ, util, money, labor0, inv)
-            p_good_p = nets.purchaseNet(eM, util, money, labor0, inv)
-            cons = nets.consumptionNet(util, money, labor0, inv)
-            # --- firms
-            fidxM, fidxJ = self._draw_indices(nM, F), self._draw_indices(nJ, F)
-            pf = torch.cat([st["f_prod_tfp"].unsqueeze(2), st["f_prod_share"], st["f_prod_rho"].unsqueeze(2)], dim=2)
-            pf = pf.permute(0, 3, 1, 2).reshape(E, F, G * (G + 3)).to(f32)           # per good: tfp, shares, rho (:36-48)
-            fmoney = st["f_money"].to(f32).unsqueeze(-1)
-            flabor = st["f_labor"].to(f32).unsqueeze(-1)
-            finv = st["f_inv"].permute(0, 2, 1).to(f32)
-            feM, feJ = gather(encM, fidxM, validM), gather(encJ, fidxJ, validJ)
-            f_value = nets.firmValueNet(feM, feJ, pf, fmoney, flabor, finv).squeeze(-1)
-            f_good_p = nets.firmPurchaseNet(feM, pf, fmoney, flabor, finv)
-            prod = nets.productionNet(pf, fmoney, flabor, finv)
-            offer = nets.offerNet(feM, pf, fmoney, flabor, finv)
-            job = nets.jobOfferNet(feJ, pf, fmoney, flabor, finv)
-        # --- sampling (fp32) and action decode into the env layout
-        p_job_take, lp_job = sample_bernoulli(p_job_p.float(), self._rand(E, P, S))
-        p_good_take, lp_good = sample_bernoulli(p_good_p.float(), self._rand(E, P, S))
-        f_good_take, lp_fgood = sample_bernoulli(f_good_p.float(), self._rand(E, F, S))
-        cons_x, lp_cons = sample_logit_normal(cons.float(), self._randn(E, P, G))
-        prod_x, lp_prod = sample_logit_normal(prod.float(), self._randn(E, F, G))
-        amt_x, lp_amt = sample_logit_normal(offer.float()[..., 0:2], self._randn(E, F, G))
-        price_x, lp_price = sample_log_normal(offer.float()[..., 2:4], self._randn(E, F, G))
-        lab_x, lp_lab = sample_log_normal(job.float()[..., 0:2], self._randn(E, F))
-        wage_x, lp_wage = sample_log_normal(job.float()[..., 2:4], self._randn(E, F))
+        Returns a dict with log-probabilities and state values (device tensors); when `record` is a list,
+        (snapshot, draws) of the step is appended to it so a trainer can re-evaluate the step with autograd."""
+        snap = snapshot(self.state) if record is not None else self.state
+        draws = draw(snap, self.S, self.gen)
+        decoded, info = evaluate(self.nets, snap, draws, self.autocast_dtype)
+        if record is not None:
+            record.append((snap, draws))
+        a = self.actions
         a["perm_person"].copy_(torch.as_tensor(perms[0]))
         a["perm_firm"].copy_(torch.as_tensor(perms[1]))
-        a["p_job_idx"].copy_(pidxJ.permute(0, 2, 1))
-        a["p_job_take"].copy_((p_job_take & validJ).permute(0, 2, 1))
-        a["p_good_idx"].copy_(pidxM.permute(0, 2, 1))
-        a["p_good_take"].copy_((p_good_take & validM).permute(0, 2, 1))
-        a["p_consume"].copy_(cons_x.permute(0, 2, 1))
-        a["f_good_idx"].copy_(fidxM.permute(0, 2, 1))
-        a["f_good_take"].copy_((f_good_take & validM).permute(0, 2, 1))
-        a["f_prod"].copy_(prod_x.permute(0, 2, 1))
-        a["f_offer_amt"].copy_(amt_x.permute(0, 2, 1))
-        a["f_offer_price"].copy_(price_x.permute(0, 2, 1))
-        a["f_job_labor"].copy_(lab_x)
-        a["f_job_wage"].copy_(wage_x)
-        nan = torch.full_like(lp_good, float("nan"))
-        return {
-            "value_person": p_value.float(), "value_firm": f_value.float(),
-            # empty market: purchase log-prob NaN = "no decision", job search 0.0 (decisionNetHandler.cpp:398-403, 476-480)
-            "logp_purchase": torch.where(validM.view(E, 1), lp_good, nan),
-            "logp_laborSearch": torch.where(validJ.view(E, 1), lp_job, torch.zeros_like(lp_job)),
-            "logp_consumption": lp_cons.sum(-1),
-            "logp_firmPurchase": torch.where(validM.view(E, 1), lp_fgood, torch.full_like(lp_fgood, float("nan"))),
-            "logp_production": lp_prod.sum(-1),
-            "logp_offer": lp_amt.sum(-1) + lp_price.sum(-1),
-            "logp_jobOffer": lp_lab + lp_wage,
-        }
+        for key, value in decoded.items():
+            a[key].copy_(value if value.dim() == 2 else value.permute(0, 2, 1))   # agent-major -> [E][slot|good][agent]
+        return info
 
-    def step(self, perms, out, flags=0):
+    def step(self, perms, out, flags=0, record=None):
         """decide + one env step (device path, current stream)."""
-        info = self.decide(perms)
+        info = self.decide(perms, record)
         self.env.time_step(self.packed, out, flags=flags)
         return info
 
