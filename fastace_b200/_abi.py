@@ -15,6 +15,7 @@ IDX_MODULO = 1
 STEP_SERIAL = 2
 STEP_PROFILE = 4
 STEP_ASYNC = 8
+STEP_LARGE = 16
 MAX_GOODS = 8
 FN_CES, FN_COBB_DOUGLAS, FN_STONE_GEARY, FN_LEONTIEF, FN_LINEAR = range(5)
 MAX_STACK = 16

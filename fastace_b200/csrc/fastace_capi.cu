@@ -13,6 +13,7 @@
 #include "fastace_internal.h"
 #include "step_kernel.cuh"
 #include "match_update_kernels.cuh"
+#include "large_economy.cuh"
 
 namespace fastace {
 
@@ -149,6 +150,12 @@ struct fastace_env {
     bool have_ev;
     double prof_match_ms, prof_update_ms;
     uint64_t prof_steps;
+    // large-economy path (large_economy.cuh)
+    bool large_only;          // dims beyond the warp-per-economy kernels: every step takes the large path
+    bool have_large;
+    void* large_block;
+    fastace::LargeScratch large_sc;
+    uint32_t large_rounds_person, large_rounds_firm;   // of the last large step (last economy)
 };
 
 #define FASTACE_CUDA_CHECK(expr)                                                              \
@@ -217,10 +224,11 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
         set_error("unsupported dims: need E>=1, F>=1, 1<=G<=8, 0<=S<=16");
         return FASTACE_ERR_INVALID;
     }
-    if (d.num_firms * d.num_goods > 254 || d.num_persons > 65535) {
-        set_error("warp-per-economy kernel needs F*G <= 254 and P <= 65535");
+    if (d.num_firms > 65534 || d.num_persons > (1 << 20) || (size_t)2 * d.stack_size * d.num_persons >= (size_t)1 << 27) {
+        set_error("unsupported dims: need F <= 65534, P <= 2^20");
         return FASTACE_ERR_INVALID;
     }
+    bool large_only = d.num_firms * d.num_goods > 254 || d.num_persons > 65535;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
         cudaGetLastError();
@@ -230,20 +238,23 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
     if (device < 0 || device >= ndev) { set_error("bad device index"); return FASTACE_ERR_INVALID; }
     FASTACE_CUDA_CHECK(cudaSetDevice(device));
 
-    const SmemLayout L = make_layout(d.num_persons, d.num_firms, d.num_goods, d.stack_size);
-    const MatchLayout ML = make_match_layout(d.num_persons, d.num_firms, d.num_goods, d.stack_size);
-    int max_optin = 0;
-    FASTACE_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    if (L.total > max_optin || ML.total > max_optin) {
-        set_error("economy too large for the warp-per-economy kernel's shared-memory books");
-        return FASTACE_ERR_INVALID;
+    SmemLayout L; std::memset(&L, 0, sizeof(L));
+    MatchLayout ML; std::memset(&ML, 0, sizeof(ML));
+    if (!large_only) {
+        L = make_layout(d.num_persons, d.num_firms, d.num_goods, d.stack_size);
+        ML = make_match_layout(d.num_persons, d.num_firms, d.num_goods, d.stack_size);
+        int max_optin = 0;
+        FASTACE_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        if (L.total > max_optin || ML.total > max_optin) large_only = true;   // books do not fit shared memory
     }
-    const KernelSet ks = kernels_for_goods(d.num_goods);
-    if (L.total > 48 * 1024)
-        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.serial, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    if (ML.total > 48 * 1024) {
-        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match12, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
-        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match16, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
+    if (!large_only) {
+        const KernelSet ks = kernels_for_goods(d.num_goods);
+        if (L.total > 48 * 1024)
+            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.serial, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        if (ML.total > 48 * 1024) {
+            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match12, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
+            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match16, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
+        }
     }
 
     fastace_env* env = new (std::nothrow) fastace_env();
@@ -253,6 +264,7 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
     env->device = device;
     env->smem_bytes = (size_t)L.total;
     env->match_smem_bytes = (size_t)ML.total;
+    env->large_only = large_only;
     int rc = carve(state_fields(d), &env->dstate, &env->state_block, true);
     if (rc != FASTACE_OK) { delete env; return rc; }
     {
@@ -287,6 +299,8 @@ int fastace_env_destroy(fastace_env_t* env) {
     if (env->have_ev) for (int i = 0; i < 3; i++) cudaEventDestroy(env->ev[i]);
     if (env->scr_pnh) cudaFree(env->scr_pnh);
     if (env->scr_pnb) cudaFree(env->scr_pnb);
+    if (env->large_block) cudaFree(env->large_block);
+    if (env->large_sc.cub_temp) cudaFree(env->large_sc.cub_temp);
     delete env;
     return FASTACE_OK;
 }
@@ -342,6 +356,179 @@ int fastace_env_device_state(const fastace_env_t* env, fastace_state_t* out_devi
     return FASTACE_OK;
 }
 
+}  // extern "C"
+
+// ---- large-economy path ------------------------------------------------------------------------------------
+struct LargeKernels {
+    void (*person_pass)(const LargeParams);
+    void (*firm_pass)(const LargeParams);
+    void (*finalize_persons)(const LargeParams);
+    void (*firm_phase_pass)(const LargeParams);
+    void (*finalize_firms)(const LargeParams);
+};
+template <int G>
+static LargeKernels large_kernels_of() {
+    return {large_person_pass<G>, large_firm_pass<G>, large_finalize_persons<G>, large_firm_phase_pass<G>, large_finalize_firms<G>};
+}
+static LargeKernels large_kernels_for_goods(int G) {
+    switch (G) {
+        case 1: return large_kernels_of<1>();
+        case 2: return large_kernels_of<2>();
+        case 3: return large_kernels_of<3>();
+        case 4: return large_kernels_of<4>();
+        case 5: return large_kernels_of<5>();
+        case 6: return large_kernels_of<6>();
+        case 7: return large_kernels_of<7>();
+        default: return large_kernels_of<8>();
+    }
+}
+
+static int ensure_large_scratch(fastace_env_t* env) {
+    if (env->have_large) return FASTACE_OK;
+    const size_t P = env->dims.num_persons, F = env->dims.num_firms, G = env->dims.num_goods, S = env->dims.stack_size;
+    const size_t R = 2 * S * P, RF = S * F, cap = F * G;
+    LargeScratch& sc = env->large_sc;
+    struct Item { void** ptr; size_t bytes; };
+    std::vector<Item> items = {
+        {(void**)&sc.rank_f, 4 * F}, {(void**)&sc.own_offer, 4 * cap}, {(void**)&sc.own_job, 4 * F},
+        {(void**)&sc.req_n, 4 * R}, {(void**)&sc.want, R}, {(void**)&sc.ok, R},
+        {(void**)&sc.key_in, 2 * R}, {(void**)&sc.key_out, 2 * R}, {(void**)&sc.val_in, 4 * R}, {(void**)&sc.val_out, 4 * R},
+        {(void**)&sc.hist, 4 * F}, {(void**)&sc.seg, 4 * (F + 1)},
+        {(void**)&sc.pm_money, 8 * P}, {(void**)&sc.pm_hires, P}, {(void**)&sc.pm_bought, G * P},
+        {(void**)&sc.fm_money, 8 * F}, {(void**)&sc.fm_labor, 8 * F}, {(void**)&sc.fm_inv, 8 * G * F},
+        {(void**)&sc.fm_left, 4 * cap}, {(void**)&sc.fm_taken, 4 * cap}, {(void**)&sc.fm_jleft, 4 * F}, {(void**)&sc.fm_jtaken, 4 * F},
+        {(void**)&sc.freq_n, 4 * RF}, {(void**)&sc.fwant, RF}, {(void**)&sc.fok, RF},
+        {(void**)&sc.fkey_in, 2 * RF}, {(void**)&sc.fkey_out, 2 * RF}, {(void**)&sc.fval_in, 4 * RF}, {(void**)&sc.fval_out, 4 * RF},
+        {(void**)&sc.fhist, 4 * F}, {(void**)&sc.fseg, 4 * (F + 1)},
+        {(void**)&sc.ff_profit, 8 * F}, {(void**)&sc.ff_money, 8 * F}, {(void**)&sc.ff_last, 8 * F}, {(void**)&sc.ff_inv, 8 * G * F},
+        {(void**)&sc.ff_left, 4 * cap}, {(void**)&sc.ff_taken, 4 * cap},
+        {(void**)&sc.post_lots, 4 * cap}, {(void**)&sc.post_jlots, 4 * F}, {(void**)&sc.changed, 4},
+    };
+    size_t total = 0;
+    for (auto& it : items) total += align_up(it.bytes ? it.bytes : 1, 256);
+    FASTACE_CUDA_CHECK(cudaMalloc(&env->large_block, total));
+    FASTACE_CUDA_CHECK(cudaMemset(env->large_block, 0, total));
+    size_t off = 0;
+    for (auto& it : items) { *it.ptr = static_cast<char*>(env->large_block) + off; off += align_up(it.bytes ? it.bytes : 1, 256); }
+    size_t need = 0;
+    const int n_max = (int)(R > RF ? R : RF);
+    FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, need, sc.key_in, sc.key_out, sc.val_in, sc.val_out, n_max > 0 ? n_max : 1, 0, 16));
+    sc.cub_bytes = need ? need : 1;
+    FASTACE_CUDA_CHECK(cudaMalloc(&sc.cub_temp, sc.cub_bytes));
+    env->have_large = true;
+    return FASTACE_OK;
+}
+
+// pointer members of a [E][...] struct moved to economy e
+template <typename StructT>
+static void offset_to_economy(const std::vector<FieldDesc>& fields, StructT* s, int e, int E) {
+    for (auto& f : fields) {
+        void*& m = member(s, f.offset);
+        if (m) m = static_cast<char*>(m) + (size_t)e * (f.count / (size_t)E) * f.elem;
+    }
+}
+
+static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, const fastace_step_out_t* dout,
+                             uint32_t flags, cudaStream_t stream) {
+    int rc = ensure_large_scratch(env);
+    if (rc != FASTACE_OK) return rc;
+    const fastace_dims_t d = env->dims;
+    const int P = d.num_persons, F = d.num_firms, G = d.num_goods, S = d.stack_size, cap = F * G;
+    const LargeKernels lk = large_kernels_for_goods(G);
+    const int T = kLargeThreads;
+    auto blocks = [T](size_t n) { return (unsigned)((n + T - 1) / T); };
+    const int kMaxRounds = 1 << 16;
+    for (int e = 0; e < d.num_econ; e++) {
+        LargeParams lp;
+        std::memset(&lp, 0, sizeof(lp));
+        lp.sp.E = 1; lp.sp.P = P; lp.sp.F = F; lp.sp.S = S;
+        lp.sp.flags = flags; lp.sp.time_before = env->time;
+        lp.sp.util_kind = env->util_kind; lp.sp.prod_kind = env->prod_kind;
+        lp.sp.st = env->dstate; lp.sp.ac = *dact; lp.sp.out = *dout;
+        offset_to_economy(state_fields(d), &lp.sp.st, e, d.num_econ);
+        offset_to_economy(action_fields(d), const_cast<fastace_actions_t*>(&lp.sp.ac), e, d.num_econ);
+        offset_to_economy(out_fields(d), &lp.sp.out, e, d.num_econ);
+        lp.sc = env->large_sc;
+        lp.G = G;
+        const LargeScratch& sc = lp.sc;
+        large_index_books<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
+        large_index_books2<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
+        env->launches += 2;
+        // ---- person phase
+        const size_t R = (size_t)2 * S * P;
+        uint32_t rounds = 0;
+        if (R > 0) {
+            large_prep_persons<<<blocks(R), T, 0, stream>>>(lp);
+            size_t bytes = sc.cub_bytes;
+            FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sc.cub_temp, bytes, sc.key_in, sc.key_out, sc.val_in, sc.val_out,
+                                                               (int)R, 0, 16, stream));
+            large_scan<<<1, 1024, 0, stream>>>(sc.hist, sc.seg, F);
+            env->launches += 3;
+            int changed = 1;
+            while (changed) {
+                if ((int)rounds >= kMaxRounds) { set_error("large step: person phase did not settle"); return FASTACE_ERR_INVALID; }
+                FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed, 0, sizeof(int), stream));
+                lk.person_pass<<<blocks(P), T, 0, stream>>>(lp);
+                lk.firm_pass<<<blocks(F), T, 0, stream>>>(lp);
+                FASTACE_CUDA_CHECK(cudaMemcpyAsync(&changed, sc.changed, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                FASTACE_CUDA_CHECK(cudaStreamSynchronize(stream));
+                env->launches += 2;
+                rounds++;
+            }
+        } else {
+            // no requests at all: the firm pass still has to publish every firm's unchanged state
+            large_scan<<<1, 1024, 0, stream>>>(sc.hist, sc.seg, F);
+            lk.firm_pass<<<blocks(F), T, 0, stream>>>(lp);
+            env->launches += 2;
+        }
+        env->large_rounds_person = rounds;
+        if (P > 0) {
+            if (R == 0) lk.person_pass<<<blocks(P), T, 0, stream>>>(lp);
+            lk.finalize_persons<<<blocks(P), T, 0, stream>>>(lp);
+            env->launches += 1;
+        }
+        large_old_jobs<<<blocks(F), T, 0, stream>>>(lp);
+        env->launches += 1;
+        if (S > 0 && P > 0) {
+            if (lp.sp.out.p_job_ok) FASTACE_CUDA_CHECK(cudaMemcpyAsync(lp.sp.out.p_job_ok, sc.ok, (size_t)S * P, cudaMemcpyDeviceToDevice, stream));
+            if (lp.sp.out.p_good_ok) FASTACE_CUDA_CHECK(cudaMemcpyAsync(lp.sp.out.p_good_ok, sc.ok + (size_t)S * P, (size_t)S * P, cudaMemcpyDeviceToDevice, stream));
+        }
+        // ---- firm phase
+        const size_t RF = (size_t)S * F;
+        rounds = 0;
+        if (RF > 0) {
+            large_prep_firms<<<blocks(RF), T, 0, stream>>>(lp);
+            size_t bytes = sc.cub_bytes;
+            FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sc.cub_temp, bytes, sc.fkey_in, sc.fkey_out, sc.fval_in, sc.fval_out,
+                                                               (int)RF, 0, 16, stream));
+            env->launches += 2;
+        }
+        large_scan<<<1, 1024, 0, stream>>>(sc.fhist, sc.fseg, F);
+        env->launches += 1;
+        int changed = 1;
+        while (changed) {
+            if ((int)rounds >= kMaxRounds) { set_error("large step: firm phase did not settle"); return FASTACE_ERR_INVALID; }
+            FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed, 0, sizeof(int), stream));
+            lk.firm_phase_pass<<<blocks(F), T, 0, stream>>>(lp);
+            FASTACE_CUDA_CHECK(cudaMemcpyAsync(&changed, sc.changed, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            FASTACE_CUDA_CHECK(cudaStreamSynchronize(stream));
+            env->launches += 1;
+            rounds++;
+        }
+        env->large_rounds_firm = rounds;
+        if (RF > 0 && lp.sp.out.f_good_ok)
+            FASTACE_CUDA_CHECK(cudaMemcpyAsync(lp.sp.out.f_good_ok, sc.fok, RF, cudaMemcpyDeviceToDevice, stream));
+        lk.finalize_firms<<<blocks(F), T, 0, stream>>>(lp);
+        large_post<<<1, 1024, 0, stream>>>(lp);
+        env->launches += 2;
+        FASTACE_CUDA_CHECK(cudaGetLastError());
+    }
+    env->time += 1;
+    return FASTACE_OK;
+}
+
+extern "C" {
+
 static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const fastace_actions_compact_t* dcz,
                        const fastace_step_out_t* dout, uint32_t flags, cudaStream_t stream) {
     if (dcz) {
@@ -355,6 +542,10 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
     if ((env->dims.num_persons > 0 && !dout->p_reward) || !dout->f_profit) {
         set_error("out: p_reward and f_profit are mandatory");
         return FASTACE_ERR_INVALID;
+    }
+    if (env->large_only || (flags & FASTACE_STEP_LARGE)) {
+        if (dcz) { set_error("the large-economy path takes the int32 action encoding"); return FASTACE_ERR_INVALID; }
+        return launch_step_large(env, dact, dout, flags, stream);
     }
     StepParams sp;
     std::memset(&sp, 0, sizeof(sp));
@@ -509,6 +700,13 @@ int fastace_env_sync(fastace_env_t* env) {
         FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->stream));
         FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->copy_out));
     }
+    return FASTACE_OK;
+}
+
+int fastace_env_large_stats(const fastace_env_t* env, uint32_t* person_rounds, uint32_t* firm_rounds) {
+    if (!env) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    if (person_rounds) *person_rounds = env->large_rounds_person;
+    if (firm_rounds) *firm_rounds = env->large_rounds_firm;
     return FASTACE_OK;
 }
 

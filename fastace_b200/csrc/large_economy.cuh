@@ -1,0 +1,518 @@
+// Economy::time_step for ONE LARGE economy (BASELINE config D: 100 000 persons, 5 000 firms, 8 goods) — books far
+// beyond shared memory, and only one sequential visiting order to parallelise.
+//
+// Formulation.  The reference walks persons then firms in visiting order (economy.cpp:117-124); every request is
+// decided first-come-first-served against finite lots (agent.cpp:99-161, firm.cpp:56-113).  The outcome of a request
+// depends only on (i) the requester's own earlier requests of the step (its money / labour), and (ii) the earlier
+// events at the firm on the other side (lots left, inventory, and — for jobs — the firm's money, which earlier hires
+// lower and earlier sales raise).  So the step is the unique fixed point of two maps that are each embarrassingly
+// parallel:
+//   requester pass  one thread per person: walk the own S job + S goods requests in order, given which of them the
+//                   other side granted  ->  `want` (own-side conditions hold: labour <= 1, money >= price)
+//   firm pass       one thread per firm: walk ALL events at this firm in the reference's order (visiting rank, jobs
+//                   before goods, slot), given `want`  ->  `ok`; this is the segmented, stably sorted event list:
+//                   events keyed by firm, sorted by a radix sort (cub::DeviceRadixSort, the one library primitive
+//                   here) whose input is enumerated in (rank, phase, slot) order
+// iterated until no `ok` flag changes.  By induction over the global event order a fixed point IS the sequential
+// result, and round k finalises every event whose dependency chain crosses agents at most k times; measured 4-7
+// rounds at config D.  Each agent's fp64 money / inventory is updated inside ONE thread in the reference's order, so
+// unlike the warp-per-economy kernel there is no rounding-order caveat: firm money is bit-identical.
+// The firm phase (firms buying from firms, firm.cpp:23-46) is the same iteration over F*S requests, with the rule
+// that an offer is withdrawn once its owner's turn has passed (profitMaxer.cpp:79-81).
+//
+// Preconditions (true for every book the step itself produces): at most one live goods offer per (firm, good) and one
+// job offer per firm; inventories are non-negative.
+#pragma once
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace fastace {
+
+constexpr uint32_t kNoEntry = 0xFFFFFFFFu;
+constexpr uint32_t kReqMask = (1u << 27) - 1u;   // request id in the sort value; bits 27.. = 0 job, 1+g goods of good g
+constexpr int kLargeThreads = 256;
+
+struct LargeScratch {
+    int32_t* rank_f;       // [F]   visiting rank of firm f this step
+    int32_t* own_offer;    // [F*G] goods-book entry of (f,g) or -1
+    int32_t* own_job;      // [F]   job-book entry of f or -1
+    // person phase, request id = (phase*S + i)*P + p
+    uint32_t* req_n;       // [2SP] book entry the request refers to, or kNoEntry
+    uint8_t* want;         // [2SP]
+    uint8_t* ok;           // [2SP]
+    uint16_t *key_in, *key_out;   // [2SP] firm on the other side (0xFFFF = no request)
+    uint32_t *val_in, *val_out;   // [2SP]
+    uint32_t* hist;        // [F]
+    uint32_t* seg;         // [F+1]
+    double* pm_money;      // [P] person results of the last requester pass
+    uint8_t* pm_hires;     // [P]
+    uint8_t* pm_bought;    // [G][P]
+    // state of every firm after the person phase / after its own purchases
+    double* fm_money;      // [F]
+    double* fm_labor;      // [F]
+    double* fm_inv;        // [G][F]
+    uint32_t *fm_left, *fm_taken;    // [F*G] by (f,g)
+    uint32_t *fm_jleft, *fm_jtaken;  // [F]
+    // firm phase, request id = i*F + f
+    uint32_t* freq_n;      // [SF]
+    uint8_t *fwant, *fok;  // [SF]
+    uint16_t *fkey_in, *fkey_out;
+    uint32_t *fval_in, *fval_out;
+    uint32_t* fhist;       // [F]
+    uint32_t* fseg;        // [F+1]
+    double* ff_profit;     // [F]   firm results of the last firm-phase pass (after its own purchases)
+    double* ff_money;      // [F]
+    double* ff_last;       // [F]   money at the first decision of the step
+    double* ff_inv;        // [G][F]
+    uint32_t *ff_left, *ff_taken;    // [F*G]
+    int32_t* post_lots;    // [F*G]
+    int32_t* post_jlots;   // [F]
+    int* changed;
+    void* cub_temp;
+    size_t cub_bytes;
+};
+
+struct LargeParams {
+    StepParams sp;     // state / action / out pointers already offset to the economy being stepped (E = 1 view)
+    LargeScratch sc;
+    int G;
+};
+
+__device__ __forceinline__ uint32_t large_map_index(int32_t raw, int count, uint32_t flags) {
+    if (count <= 0) return kNoEntry;
+    if (flags & FASTACE_IDX_MODULO) return (uint32_t)raw % (uint32_t)count;
+    if (raw < 0 || raw >= count) return kNoEntry;
+    return (uint32_t)raw;
+}
+
+// ---- step prologue: who owns which entry, visiting ranks, cleared histograms ---------------------------------
+__global__ void large_index_books(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int F = p.F, G = lp.G, cap = F * G;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < cap) lp.sc.own_offer[t] = -1;
+    if (t < F) { lp.sc.own_job[t] = -1; lp.sc.hist[t] = 0; lp.sc.fhist[t] = 0; lp.sc.rank_f[p.ac.perm_firm[t]] = t; }
+}
+__global__ void large_index_books2(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int F = p.F, G = lp.G;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < p.st.m_count[0]) lp.sc.own_offer[p.st.m_owner[t] * G + p.st.m_good[t]] = t;
+    if (t < p.st.j_count[0]) lp.sc.own_job[p.st.j_owner[t]] = t;
+    (void)F;
+}
+
+// ---- person phase: requests enumerated in the reference's order (rank, jobs before goods, slot) --------------
+__global__ void large_prep_persons(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int P = p.P, S = p.S;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)2 * S * P) return;
+    const int r = (int)(t / (2 * S)), rem = (int)(t % (2 * S)), phase = rem / S, i = rem % S;
+    const int pid = p.ac.perm_person[r];
+    const size_t a = (size_t)i * P + pid;
+    const uint32_t req = (uint32_t)((size_t)(phase * S + i) * P + pid);
+    uint32_t n = kNoEntry;
+    if (phase == 0) { if (p.ac.p_job_take[a]) n = large_map_index(p.ac.p_job_idx[a], p.st.j_count[0], p.flags); }
+    else            { if (p.ac.p_good_take[a]) n = large_map_index(p.ac.p_good_idx[a], p.st.m_count[0], p.flags); }
+    lp.sc.req_n[req] = n;
+    lp.sc.want[req] = 0;
+    lp.sc.ok[req] = (n != kNoEntry);     // optimistic start
+    if (n == kNoEntry) { lp.sc.key_in[t] = 0xFFFFu; lp.sc.val_in[t] = req; return; }
+    const int firm = phase == 0 ? p.st.j_owner[n] : p.st.m_owner[n];
+    const uint32_t type = phase == 0 ? 0u : 1u + (uint32_t)p.st.m_good[n];
+    lp.sc.key_in[t] = (uint16_t)firm;
+    lp.sc.val_in[t] = req | (type << 27);
+    atomicAdd(&lp.sc.hist[firm], 1u);
+}
+
+// exclusive scan of hist[0..n) into seg[0..n], one block
+__global__ void large_scan(const uint32_t* hist, uint32_t* seg, int n) {
+    __shared__ uint32_t part[1024];
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    uint32_t s = 0;
+    for (int k = lo; k < hi; k++) s += hist[k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < (int)blockDim.x; d <<= 1) {
+        const uint32_t v = threadIdx.x >= (unsigned)d ? part[threadIdx.x - d] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    for (int k = lo; k < hi; k++) { seg[k] = run; run += hist[k]; }
+    if (threadIdx.x == blockDim.x - 1) seg[n] = part[blockDim.x - 1];
+}
+
+// requester pass (Person::time_step person.cpp:19-33; respond_to_jobOffer :36-54; respond_to_offer agent.cpp:99-116)
+template <int G>
+__global__ void large_person_pass(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int P = p.P, S = p.S;
+    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= P) return;
+    double money = p.st.p_money[pid];
+    double labor = 0.0;                                                    // person.cpp:24
+    int hires = 0;
+    for (int i = 0; i < S; i++) {
+        const size_t req = (size_t)i * P + pid;
+        const uint32_t n = lp.sc.req_n[req];
+        if (n == kNoEntry) continue;
+        const bool w = labor + kLaborPerOffer <= 1;                        // person.cpp:39
+        lp.sc.want[req] = w;
+        if (w && lp.sc.ok[req]) { labor += kLaborPerOffer; money += p.st.j_wage[n]; hires++; }   // person.cpp:48-49
+    }
+    uint8_t bought[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) bought[g] = 0;
+    for (int i = 0; i < S; i++) {
+        const size_t req = (size_t)(S + i) * P + pid;
+        const uint32_t n = lp.sc.req_n[req];
+        if (n == kNoEntry) continue;
+        const double price = p.st.m_price[n];
+        const bool w = money >= price;                                     // agent.cpp:102
+        lp.sc.want[req] = w;
+        if (w && lp.sc.ok[req]) {
+            money -= price;                                                // agent.cpp:105-111
+            const int good = p.st.m_good[n];
+#pragma unroll
+            for (int g = 0; g < G; g++) if (g == good) bought[g]++;
+        }
+    }
+    lp.sc.pm_money[pid] = money;
+    lp.sc.pm_hires[pid] = (uint8_t)hires;
+#pragma unroll
+    for (int g = 0; g < G; g++) lp.sc.pm_bought[(size_t)g * P + pid] = bought[g];
+}
+
+// (inventory < quantities).any() for one unit of `good` (agent.cpp:140)
+template <int G>
+__device__ __forceinline__ bool large_short(const double (&inv)[G], int good) {
+    bool s = false;
+#pragma unroll
+    for (int g = 0; g < G; g++) s |= inv[g] < (g == good ? kAmountPerOffer : 0.0);
+    return s;
+}
+
+// firm pass of the person phase: every event at firm f in the reference's order
+// (review_jobOffer_response firm.cpp:56-90, accept :106-113; review_offer_response agent.cpp:118-150, accept :152-161)
+template <int G>
+__global__ void large_firm_pass(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int F = p.F;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double money = p.st.f_money[f], labor = p.st.f_labor[f];
+    const int nj = lp.sc.own_job[f];
+    uint32_t jleft = 0, jtaken = 0;
+    double wage = 0.0;
+    if (nj >= 0) { jleft = p.st.j_left[nj]; jtaken = p.st.j_taken[nj]; wage = p.st.j_wage[nj]; }
+    double inv[G], price[G];
+    uint32_t left[G], taken[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        inv[g] = p.st.f_inv[(size_t)g * F + f];
+        const int n = lp.sc.own_offer[f * G + g];
+        left[g] = n >= 0 ? p.st.m_left[n] : 0u;
+        taken[g] = n >= 0 ? p.st.m_taken[n] : 0u;
+        price[g] = n >= 0 ? p.st.m_price[n] : 0.0;
+    }
+    bool changed = false;
+    const uint32_t lo = lp.sc.seg[f], hi = lp.sc.seg[f + 1];
+    for (uint32_t pos = lo; pos < hi; pos++) {
+        const uint32_t v = lp.sc.val_out[pos];
+        const uint32_t req = v & kReqMask, type = v >> 27;
+        uint8_t o = 0;
+        if (lp.sc.want[req]) {
+            if (type == 0) {
+                if (jleft > 0) {                                           // firm.cpp:64
+                    if (money < wage) jleft = 0;                           // firm.cpp:80-84
+                    else { money -= wage; labor += kLaborPerOffer; jleft--; jtaken++; o = 1; }   // firm.cpp:108-111
+                }
+            } else {
+                const int good = (int)type - 1;
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    if (g != good) continue;
+                    if (left[g] > 0) {                                     // agent.cpp:124
+                        if (large_short<G>(inv, g)) left[g] = 0;           // agent.cpp:140-143
+                        else { money += price[g]; inv[g] -= kAmountPerOffer; left[g]--; taken[g]++; o = 1; }
+                    }
+                }
+            }
+        }
+        if (lp.sc.ok[req] != o) { lp.sc.ok[req] = o; changed = true; }
+    }
+    lp.sc.fm_money[f] = money;
+    lp.sc.fm_labor[f] = labor;
+    lp.sc.fm_jleft[f] = jleft;
+    lp.sc.fm_jtaken[f] = jtaken;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        lp.sc.fm_inv[(size_t)g * F + f] = inv[g];
+        lp.sc.fm_left[f * G + g] = left[g];
+        lp.sc.fm_taken[f * G + g] = taken[g];
+    }
+    if (changed) *lp.sc.changed = 1;
+}
+
+// consume_goods + utility (utilMaxer.cpp:88-92, 54-62; neuralPersonDecisionMaker.cpp:93-111), persons' new state
+template <int G>
+__global__ void large_finalize_persons(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int P = p.P;
+    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= P) return;
+    const double labor = kLaborPerOffer * (double)lp.sc.pm_hires[pid];
+    double x[G + 1], inv[G];
+    x[0] = 1 - labor;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const size_t k = (size_t)g * P + pid;
+        double v = p.st.p_inv[k];
+        const int nb = lp.sc.pm_bought[k];
+        for (int q = 0; q < nb; q++) v += kAmountPerOffer;
+        const double c = v * (double)p.ac.p_consume[k];
+        x[g + 1] = c;
+        inv[g] = v - c;
+    }
+    double share[G + 1], theta[G + 1];
+#pragma unroll
+    for (int i = 0; i <= G; i++) {
+        share[i] = p.st.p_util_share[(size_t)i * P + pid];
+        theta[i] = (p.util_kind == FASTACE_FN_STONE_GEARY) ? p.st.p_util_theta[(size_t)i * P + pid] : 0.0;
+    }
+    p.out.p_reward[pid] = eval_function<G + 1, true>(p.util_kind, p.st.p_util_tfp[pid], share, theta, p.st.p_util_rho[pid], x);
+    p.st.p_money[pid] = lp.sc.pm_money[pid];
+    p.st.p_labor[pid] = labor;
+#pragma unroll
+    for (int g = 0; g < G; g++) p.st.p_inv[(size_t)g * P + pid] = inv[g];
+}
+
+// job counters are final after the person phase
+__global__ void large_old_jobs(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.st.j_count[0]) return;
+    const int f = p.st.j_owner[t];
+    if (p.out.old_j_left) p.out.old_j_left[t] = lp.sc.fm_jleft[f];
+    if (p.out.old_j_taken) p.out.old_j_taken[t] = lp.sc.fm_jtaken[f];
+}
+
+// ---- firm phase ----------------------------------------------------------------------------------------------
+__global__ void large_prep_firms(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int F = p.F, S = p.S;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * F) return;
+    const int q = t / S, i = t % S;
+    const int f = p.ac.perm_firm[q];
+    const uint32_t freq = (uint32_t)(i * F + f);
+    uint32_t n = kNoEntry;
+    if (p.ac.f_good_take[freq]) n = large_map_index(p.ac.f_good_idx[freq], p.st.m_count[0], p.flags);
+    lp.sc.freq_n[freq] = n;
+    lp.sc.fwant[freq] = 0;
+    lp.sc.fok[freq] = (n != kNoEntry);
+    if (n == kNoEntry) { lp.sc.fkey_in[t] = 0xFFFFu; lp.sc.fval_in[t] = freq; return; }
+    const int seller = p.st.m_owner[n];
+    lp.sc.fkey_in[t] = (uint16_t)seller;
+    lp.sc.fval_in[t] = freq | ((1u + (uint32_t)p.st.m_good[n]) << 27);
+    atomicAdd(&lp.sc.fhist[seller], 1u);
+}
+
+// One firm's turn given what the other firms currently claim (Firm::time_step firm.cpp:23-46): sales to the firms that
+// come earlier in the visiting order, check_my_offers (agent.cpp:54-97), profit record
+// (neuralFirmDecisionMaker.cpp:65-74), own purchases (profitMaxer.cpp:102-111; self-purchase is possible).
+template <int G>
+__global__ void large_firm_phase_pass(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int F = p.F, S = p.S;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int qf = lp.sc.rank_f[f];
+    double money = lp.sc.fm_money[f];
+    double inv[G], price[G];
+    uint32_t left[G], taken[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        inv[g] = lp.sc.fm_inv[(size_t)g * F + f];
+        left[g] = lp.sc.fm_left[f * G + g];
+        taken[g] = lp.sc.fm_taken[f * G + g];
+        const int n = lp.sc.own_offer[f * G + g];
+        price[g] = n >= 0 ? p.st.m_price[n] : 0.0;
+    }
+    bool changed = false;
+    const uint32_t lo = lp.sc.fseg[f], hi = lp.sc.fseg[f + 1];
+    for (uint32_t pos = lo; pos < hi; pos++) {
+        const uint32_t v = lp.sc.fval_out[pos];
+        const uint32_t freq = v & kReqMask;
+        const int good = (int)(v >> 27) - 1;
+        const int qb = lp.sc.rank_f[freq % (uint32_t)F];
+        if (qb == qf) continue;                       // own request: decided in the own turn below
+        uint8_t o = 0;
+        if (qb < qf && lp.sc.fwant[freq]) {           // later buyers find the offer withdrawn (profitMaxer.cpp:79-81)
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                if (g != good) continue;
+                if (left[g] > 0) {
+                    if (large_short<G>(inv, g)) left[g] = 0;
+                    else { money += price[g]; inv[g] -= kAmountPerOffer; left[g]--; taken[g]++; o = 1; }
+                }
+            }
+        }
+        if (lp.sc.fok[freq] != o) { lp.sc.fok[freq] = o; changed = true; }
+    }
+    // check_my_offers: shrink amountLeft until quantities*amountLeft fits the inventory (agent.cpp:54-97)
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        if ((double)left[g] > inv[g]) left[g] = inv[g] >= 0.0 ? (uint32_t)inv[g] : 0u;
+    }
+    // first decision of the step: last step's profit (neuralFirmDecisionMaker.cpp:20-33, 65-74)
+    const double profit = p.time_before > 0 ? money - p.st.f_last_money[f] : 0.0;
+    const double last = money;
+    for (int i = 0; i < S; i++) {
+        const uint32_t freq = (uint32_t)(i * F + f);
+        const uint32_t n = lp.sc.freq_n[freq];
+        if (n == kNoEntry) continue;
+        const int seller = p.st.m_owner[n], good = p.st.m_good[n];
+        const double pr = p.st.m_price[n];
+        const bool w = money >= pr;                                        // agent.cpp:102
+        if (seller == f) {
+            uint8_t o = 0;
+            if (w) {
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    if (g != good) continue;
+                    if (left[g] > 0) {
+                        if (large_short<G>(inv, g)) left[g] = 0;
+                        else {
+                            money += pr; inv[g] -= kAmountPerOffer; left[g]--; taken[g]++;   // seller side (agent.cpp:152-161)
+                            money -= pr; inv[g] += kAmountPerOffer;                          // buyer side (agent.cpp:105-111)
+                            o = 1;
+                        }
+                    }
+                }
+            }
+            if (lp.sc.fok[freq] != o) { lp.sc.fok[freq] = o; changed = true; }
+        } else {
+            if (lp.sc.fwant[freq] != (uint8_t)w) { lp.sc.fwant[freq] = (uint8_t)w; changed = true; }
+            if (w && lp.sc.fok[freq]) {
+                money -= pr;
+#pragma unroll
+                for (int g = 0; g < G; g++) if (g == good) inv[g] += kAmountPerOffer;
+            }
+        }
+    }
+    // results of the turn so far; production and posting follow once the iteration has settled
+    lp.sc.ff_profit[f] = profit;
+    lp.sc.ff_money[f] = money;
+    lp.sc.ff_last[f] = last;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        lp.sc.ff_inv[(size_t)g * F + f] = inv[g];
+        lp.sc.ff_left[f * G + g] = left[g];
+        lp.sc.ff_taken[f * G + g] = taken[g];
+    }
+    if (changed) *lp.sc.changed = 1;
+}
+
+// produce (profitMaxer.cpp:68-72), sell_goods / search_for_laborers decode (neuralFirmDecisionMaker.cpp:111-180)
+template <int G>
+__global__ void large_finalize_firms(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int F = p.F;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double in[G + 1], inv[G], xin[G];
+    in[0] = lp.sc.fm_labor[f];                                             // laborHired after the person phase
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        inv[g] = lp.sc.ff_inv[(size_t)g * F + f];
+        xin[g] = inv[g] * (double)p.ac.f_prod[(size_t)g * F + f];         // neuralFirmDecisionMaker.cpp:101
+        in[g + 1] = xin[g];
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const size_t ag = (size_t)g * F + f;
+        double share[G + 1], theta[G + 1];
+#pragma unroll
+        for (int i = 0; i <= G; i++) {
+            const size_t k = ((size_t)g * (G + 1) + i) * F + f;
+            share[i] = p.st.f_prod_share[k];
+            theta[i] = (p.prod_kind == FASTACE_FN_STONE_GEARY) ? p.st.f_prod_theta[k] : 0.0;
+        }
+        const double outg = eval_function<G + 1, false>(p.prod_kind, p.st.f_prod_tfp[ag], share, theta, p.st.f_prod_rho[ag], in);
+        const double newinv = inv[g] + (outg - xin[g]);                    // profitMaxer.cpp:71
+        p.st.f_inv[ag] = newinv;
+        const double amount = (double)p.ac.f_offer_amt[ag] * newinv;       // decisionNetHandler.cpp:591
+        lp.sc.post_lots[f * G + g] = x86_double_to_int(amount / kAmountPerOffer);
+        const int n = lp.sc.own_offer[f * G + g];
+        if (n >= 0) {   // counters of the old entry just before its owner withdraws it (profitMaxer.cpp:79-81)
+            if (p.out.old_m_left) p.out.old_m_left[n] = lp.sc.ff_left[f * G + g];
+            if (p.out.old_m_taken) p.out.old_m_taken[n] = lp.sc.ff_taken[f * G + g];
+        }
+    }
+    p.st.f_money[f] = lp.sc.ff_money[f];
+    p.st.f_last_money[f] = lp.sc.ff_last[f];
+    p.st.f_labor[f] = 0.0;                                                 // firm.cpp:41
+    p.out.f_profit[f] = lp.sc.ff_profit[f];
+    lp.sc.post_jlots[f] = x86_double_to_int((double)p.ac.f_job_labor[f] / kLaborPerOffer);
+}
+
+// new books in market order: firms in visiting order, goods ascending, lots > 0 (economy.cpp:52-59, 125-126)
+__global__ void large_post(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int F = p.F, G = lp.G, cap = F * G;
+    __shared__ uint32_t part_m[1024], part_j[1024];
+    const int per = (F + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int lo = min(F, (int)threadIdx.x * per), hi = min(F, lo + per);
+    uint32_t sm = 0, sj = 0;
+    for (int q = lo; q < hi; q++) {
+        const int f = p.ac.perm_firm[q];
+        for (int g = 0; g < G; g++) sm += lp.sc.post_lots[f * G + g] > 0;
+        sj += lp.sc.post_jlots[f] > 0;
+    }
+    part_m[threadIdx.x] = sm; part_j[threadIdx.x] = sj;
+    __syncthreads();
+    for (int d = 1; d < (int)blockDim.x; d <<= 1) {
+        const uint32_t a = threadIdx.x >= (unsigned)d ? part_m[threadIdx.x - d] : 0u;
+        const uint32_t b = threadIdx.x >= (unsigned)d ? part_j[threadIdx.x - d] : 0u;
+        __syncthreads();
+        part_m[threadIdx.x] += a; part_j[threadIdx.x] += b;
+        __syncthreads();
+    }
+    uint32_t bm = threadIdx.x ? part_m[threadIdx.x - 1] : 0u, bj = threadIdx.x ? part_j[threadIdx.x - 1] : 0u;
+    const uint32_t nm = part_m[blockDim.x - 1], nj = part_j[blockDim.x - 1];
+    __syncthreads();
+    // the old book is dead from here on: clear what the new one does not cover, then write the new entries
+    for (int n = (int)nm + (int)threadIdx.x; n < cap; n += blockDim.x) {
+        p.st.m_owner[n] = 0; p.st.m_good[n] = 0; p.st.m_left[n] = 0; p.st.m_taken[n] = 0; p.st.m_price[n] = 0.0;
+    }
+    for (int n = (int)nj + (int)threadIdx.x; n < F; n += blockDim.x) {
+        p.st.j_owner[n] = 0; p.st.j_left[n] = 0; p.st.j_taken[n] = 0; p.st.j_wage[n] = 0.0;
+    }
+    for (int q = lo; q < hi; q++) {
+        const int f = p.ac.perm_firm[q];
+        for (int g = 0; g < G; g++) {
+            const int lots = lp.sc.post_lots[f * G + g];
+            if (lots > 0) {                                                // neuralFirmDecisionMaker.cpp:135
+                p.st.m_owner[bm] = f; p.st.m_good[bm] = g; p.st.m_left[bm] = (uint32_t)lots; p.st.m_taken[bm] = 0;
+                p.st.m_price[bm] = (double)p.ac.f_offer_price[(size_t)g * F + f] / kAmountPerOffer;
+                bm++;
+            }
+        }
+        const int jl = lp.sc.post_jlots[f];
+        if (jl > 0) {
+            double wage = (double)p.ac.f_job_wage[f];
+            if (wage > kLargeNumber) wage = kLargeNumber;                   // decisionNetHandler.cpp:631-635
+            p.st.j_owner[bj] = f; p.st.j_left[bj] = (uint32_t)jl; p.st.j_taken[bj] = 0; p.st.j_wage[bj] = wage / kLaborPerOffer;
+            bj++;
+        }
+    }
+    if (threadIdx.x == 0) { p.st.m_count[0] = (int32_t)nm; p.st.j_count[0] = (int32_t)nj; }
+}
+
+}  // namespace fastace

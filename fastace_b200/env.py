@@ -184,6 +184,12 @@ class BatchedEconomy:
         ac = actions if isinstance(actions, _abi.Actions) else _abi.struct_from_numpy("actions", actions, self.dims)
         lib.check(self._lib.fastace_env_step_host(self._h, C.byref(ac), C.byref(ou), int(flags)))
 
+    def large_stats(self):
+        """(person-phase rounds, firm-phase rounds) of the last large-economy step"""
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        lib.check(self._lib.fastace_env_large_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def sync(self):
         """Wait for every step enqueued by time_step_host(..., flags | STEP_ASYNC)."""
         lib.check(self._lib.fastace_env_sync(self._h))

@@ -48,7 +48,8 @@ typedef enum fastace_status {
     FASTACE_ERR_ALLOC = -4
 } fastace_status_t;
 
-/* Limits of the warp-per-economy kernel (one economy = one warp, books in shared memory). */
+/* Limits of every path; the warp-per-economy kernels (one economy = one warp, books in shared memory) additionally
+ * need F*G <= 254 and P <= 65535, beyond which the env uses the large-economy path (F <= 65534, P <= 2^20). */
 #define FASTACE_MAX_GOODS 8
 #define FASTACE_MAX_STACK 16
 
@@ -238,6 +239,13 @@ typedef struct fastace_step_out {
  * an asynchronous call must stay valid, and outputs are complete, only after fastace_env_sync. */
 #define FASTACE_STEP_ASYNC   8u
 
+/* Take the large-economy path (csrc/large_economy.cuh: request/firm fixed-point iteration over stably sorted
+ * per-firm event lists, books in global memory) even when the economy fits the warp-per-economy kernels.  Envs whose
+ * dims exceed those kernels (F*G > 254, P > 65535, or books beyond shared memory — BASELINE config D) always take
+ * it.  Every fp64 update is made in the reference's order (no rounding-order caveat); the call synchronises the
+ * stream once per iteration round. */
+#define FASTACE_STEP_LARGE   16u
+
 typedef struct fastace_env fastace_env_t;
 
 /* ---- library ---------------------------------------------------------------------- */
@@ -294,6 +302,9 @@ int fastace_env_launch_count(const fastace_env_t* env, uint64_t* out_count);
 /* Accumulated device time (milliseconds, CUDA events) of the steps run with FASTACE_STEP_PROFILE:
  * match_kernel, update_kernel, and the number of such steps.  Resets the accumulators. */
 int fastace_env_kernel_times(fastace_env_t* env, double* match_ms, double* update_ms, uint64_t* steps);
+
+/* Iteration rounds of the last large-economy step (person phase, firm phase). */
+int fastace_env_large_stats(const fastace_env_t* env, uint32_t* person_rounds, uint32_t* firm_rounds);
 
 /* ---- legacy entry points of libpybindings.so (src/pybindings.h:8-28) ------------------ */
 /* Byte-identical layouts of neural::CustomScenarioParams (344 B) and
