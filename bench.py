@@ -148,6 +148,50 @@ def cpu_baseline(sample_econ, steps, want_kind=None):
             "seconds": dt}
 
 
+BYTES_PER_AGENT_STEP_D = 427.0      # config D, G = 8 (person 384 B, firm 1290 B per step)
+
+
+def bench_config_d(dev, with_cpu, steps=14, warm=3):
+    """BASELINE config D through the large-economy path: device-resident injected actions, CUDA events around every
+    step (each step synchronises the stream once per two iteration rounds, so the events see the whole step)."""
+    import torch
+    from fastace_b200.env import BatchedEconomy
+    dims = (1, 100000, 5000, 8, 10)
+    envd = BatchedEconomy(dims, device=dev.index)
+    state = scenario.generic_initial_state(dims, 21)
+    envd.set_state(state)
+    orders = scenario.OrderStream(dims, 38)
+    host_acts = [scenario.synthetic_actions(dims, seed=22, step=t, perms=orders.next(), **scenario.BENCH_PRESET) for t in range(steps)]
+    packed = [envd.pack_device("actions", envd.alloc_actions(a)) for a in host_acts]
+    outs = envd.alloc_outputs()
+    pout = envd.pack_device("out", outs)
+    ms, rounds = [], []
+    for t in range(steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); envd.time_step(packed[t], pout, flags=_abi.IDX_MODULO); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1)); rounds.append(list(envd.large_stats()))
+    envd.close()
+    timed = ms[warm:]
+    mean_ms = float(np.mean(timed))
+    res = {"workload": "config D: 1 economy x (100000 persons + 5000 firms), 8 goods, stack 10, fixed injected actions, IDX_MODULO",
+           "unit": METRIC, "steps": len(timed), "warmup": warm, "ms_per_step": mean_ms, "value": 105000 / (mean_ms * 1e-3),
+           "iteration_rounds_person_firm_last_step": rounds[-1], "scaling": "replicas only (one economy does not shard)"}
+    if with_cpu:
+        from oracle.loader import Oracle
+        orc = Oracle()
+        ost = {k: v.copy() for k, v in state.items()}
+        t0 = time.perf_counter()
+        for t in range(4):
+            oo = _abi.alloc_host("out", dims, names=("p_reward", "f_profit"))
+            orc.step(dims, ost, host_acts[t], oo, flags=_abi.IDX_MODULO, time_before=t)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 105000 * 4 / dt, "unit": METRIC, "cores": 1, "kind": "port",
+                               "sample": "first 4 steps of the same episode, C oracle, single thread (one economy has one visiting order)"}
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -393,6 +437,11 @@ def run_ours(args):
                     "gradient_allreduce": "nccl, one flat bucket" if world > 1 else None, "precision": "tf32 matmul, fp32 params",
                     "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
 
+    # ---- config D: ONE economy of 100 000 persons + 5 000 firms, 8 goods (large-economy path; replicas only) ----
+    config_d = None
+    if args.config_d and rank == 0:
+        config_d = bench_config_d(dev, with_cpu=not args.no_cpu)
+
     if rank == 0:
         peak, peak_src = peaks()
         avg_step_s = total_ms / args.steps * 1e-3  # rank 0's own steps
@@ -430,6 +479,9 @@ def run_ours(args):
             line["full_rollout"] = rollout
         if training is not None:
             line["training"] = training
+        if config_d is not None:
+            config_d["roofline_frac_hbm"] = config_d["value"] * BYTES_PER_AGENT_STEP_D / (peak * 1e9)
+            line["config_d"] = config_d
         if world == 1 and not args.no_cpu:
             base = cpu_baseline(args.cpu_sample, EPISODE)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -449,6 +501,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (diagnostic)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--config-d", action="store_true", help="also time BASELINE config D (one 105k-agent economy, large-economy path)")
     ap.add_argument("--train", action="store_true", help="also time one A2C update (rollout + re-evaluation backward + Adam)")
     ap.add_argument("--train-steps", type=int, default=20, help="episode length of the --train leg (DEFAULT_EPISODE_LENGTH)")
     ap.add_argument("--rollout", action="store_true", help="also time the full rollout with the batched policy forward")

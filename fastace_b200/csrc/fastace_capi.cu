@@ -3,6 +3,7 @@
 // There is NO CPU fallback anywhere in this file: without a CUDA device every env call fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -403,6 +404,8 @@ static int ensure_large_scratch(fastace_env_t* env) {
         {(void**)&sc.ff_profit, 8 * F}, {(void**)&sc.ff_money, 8 * F}, {(void**)&sc.ff_last, 8 * F}, {(void**)&sc.ff_inv, 8 * G * F},
         {(void**)&sc.ff_left, 4 * cap}, {(void**)&sc.ff_taken, 4 * cap},
         {(void**)&sc.post_lots, 4 * cap}, {(void**)&sc.post_jlots, 4 * F}, {(void**)&sc.changed, 4},
+        {(void**)&sc.req_firm, 2 * R}, {(void**)&sc.dirty_person, P}, {(void**)&sc.dirty_firm, F},
+        {(void**)&sc.post_base_m, 4 * F}, {(void**)&sc.post_base_j, 4 * F},
     };
     size_t total = 0;
     for (auto& it : items) total += align_up(it.bytes ? it.bytes : 1, 256);
@@ -451,7 +454,8 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
         lp.sc = env->large_sc;
         lp.G = G;
         const LargeScratch& sc = lp.sc;
-        large_index_books<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
+        const size_t n_index = std::max((size_t)(cap > F ? cap : F), (size_t)P);
+        large_index_books<<<blocks(n_index), T, 0, stream>>>(lp);
         large_index_books2<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
         env->launches += 2;
         // ---- person phase
@@ -468,17 +472,20 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
             while (changed) {
                 if ((int)rounds >= kMaxRounds) { set_error("large step: person phase did not settle"); return FASTACE_ERR_INVALID; }
                 FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed, 0, sizeof(int), stream));
-                lk.person_pass<<<blocks(P), T, 0, stream>>>(lp);
-                lk.firm_pass<<<blocks(F), T, 0, stream>>>(lp);
+                // two rounds per host check: a settled iteration is idempotent, and skipped agents cost nothing
+                for (int k = 0; k < 2; k++) {
+                    lk.person_pass<<<blocks(P), T, 0, stream>>>(lp);
+                    lk.firm_pass<<<blocks((size_t)F * 32), T, 0, stream>>>(lp);
+                }
                 FASTACE_CUDA_CHECK(cudaMemcpyAsync(&changed, sc.changed, sizeof(int), cudaMemcpyDeviceToHost, stream));
                 FASTACE_CUDA_CHECK(cudaStreamSynchronize(stream));
-                env->launches += 2;
-                rounds++;
+                env->launches += 4;
+                rounds += 2;
             }
         } else {
             // no requests at all: the firm pass still has to publish every firm's unchanged state
             large_scan<<<1, 1024, 0, stream>>>(sc.hist, sc.seg, F);
-            lk.firm_pass<<<blocks(F), T, 0, stream>>>(lp);
+            lk.firm_pass<<<blocks((size_t)F * 32), T, 0, stream>>>(lp);
             env->launches += 2;
         }
         env->large_rounds_person = rounds;
@@ -489,9 +496,9 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
         }
         large_old_jobs<<<blocks(F), T, 0, stream>>>(lp);
         env->launches += 1;
-        if (S > 0 && P > 0) {
-            if (lp.sp.out.p_job_ok) FASTACE_CUDA_CHECK(cudaMemcpyAsync(lp.sp.out.p_job_ok, sc.ok, (size_t)S * P, cudaMemcpyDeviceToDevice, stream));
-            if (lp.sp.out.p_good_ok) FASTACE_CUDA_CHECK(cudaMemcpyAsync(lp.sp.out.p_good_ok, sc.ok + (size_t)S * P, (size_t)S * P, cudaMemcpyDeviceToDevice, stream));
+        if (S > 0 && P > 0 && (lp.sp.out.p_job_ok || lp.sp.out.p_good_ok)) {
+            large_person_flags<<<blocks((size_t)S * P), T, 0, stream>>>(lp);
+            env->launches += 1;
         }
         // ---- firm phase
         const size_t RF = (size_t)S * F;
@@ -518,9 +525,10 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
         env->large_rounds_firm = rounds;
         if (RF > 0 && lp.sp.out.f_good_ok)
             FASTACE_CUDA_CHECK(cudaMemcpyAsync(lp.sp.out.f_good_ok, sc.fok, RF, cudaMemcpyDeviceToDevice, stream));
-        lk.finalize_firms<<<blocks(F), T, 0, stream>>>(lp);
-        large_post<<<1, 1024, 0, stream>>>(lp);
-        env->launches += 2;
+        lk.finalize_firms<<<blocks(cap), T, 0, stream>>>(lp);
+        large_post_scan<<<1, 1024, 0, stream>>>(lp);
+        large_post_write<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
+        env->launches += 3;
         FASTACE_CUDA_CHECK(cudaGetLastError());
     }
     env->time += 1;

@@ -68,6 +68,10 @@ struct LargeScratch {
     uint32_t *ff_left, *ff_taken;    // [F*G]
     int32_t* post_lots;    // [F*G]
     int32_t* post_jlots;   // [F]
+    uint16_t* req_firm;    // [2SP] firm on the other side of the request
+    uint8_t* dirty_person; // [P]   some `ok` of this person changed since its last requester pass
+    uint8_t* dirty_firm;   // [F]   some `want` at this firm changed since its last firm pass
+    uint32_t *post_base_m, *post_base_j;   // [F] by visiting rank: first new-book slot of that firm
     int* changed;
     void* cub_temp;
     size_t cub_bytes;
@@ -92,7 +96,11 @@ __global__ void large_index_books(const LargeParams lp) {
     const int F = p.F, G = lp.G, cap = F * G;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < cap) lp.sc.own_offer[t] = -1;
-    if (t < F) { lp.sc.own_job[t] = -1; lp.sc.hist[t] = 0; lp.sc.fhist[t] = 0; lp.sc.rank_f[p.ac.perm_firm[t]] = t; }
+    if (t < F) {
+        lp.sc.own_job[t] = -1; lp.sc.hist[t] = 0; lp.sc.fhist[t] = 0; lp.sc.rank_f[p.ac.perm_firm[t]] = t;
+        lp.sc.dirty_firm[t] = 1;
+    }
+    if (t < p.P) lp.sc.dirty_person[t] = 1;
 }
 __global__ void large_index_books2(const LargeParams lp) {
     const StepParams& p = lp.sp;
@@ -124,6 +132,7 @@ __global__ void large_prep_persons(const LargeParams lp) {
     const uint32_t type = phase == 0 ? 0u : 1u + (uint32_t)p.st.m_good[n];
     lp.sc.key_in[t] = (uint16_t)firm;
     lp.sc.val_in[t] = req | (type << 27);
+    lp.sc.req_firm[req] = (uint16_t)firm;
     atomicAdd(&lp.sc.hist[firm], 1u);
 }
 
@@ -147,13 +156,16 @@ __global__ void large_scan(const uint32_t* hist, uint32_t* seg, int n) {
     if (threadIdx.x == blockDim.x - 1) seg[n] = part[blockDim.x - 1];
 }
 
-// requester pass (Person::time_step person.cpp:19-33; respond_to_jobOffer :36-54; respond_to_offer agent.cpp:99-116)
+// requester pass (Person::time_step person.cpp:19-33; respond_to_jobOffer :36-54; respond_to_offer agent.cpp:99-116).
+// Persons none of whose requests changed outcome since their last pass are skipped (their results stand).
 template <int G>
 __global__ void large_person_pass(const LargeParams lp) {
     const StepParams& p = lp.sp;
     const int P = p.P, S = p.S;
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= P) return;
+    if (!lp.sc.dirty_person[pid]) return;
+    lp.sc.dirty_person[pid] = 0;
     double money = p.st.p_money[pid];
     double labor = 0.0;                                                    // person.cpp:24
     int hires = 0;
@@ -161,8 +173,8 @@ __global__ void large_person_pass(const LargeParams lp) {
         const size_t req = (size_t)i * P + pid;
         const uint32_t n = lp.sc.req_n[req];
         if (n == kNoEntry) continue;
-        const bool w = labor + kLaborPerOffer <= 1;                        // person.cpp:39
-        lp.sc.want[req] = w;
+        const uint8_t w = labor + kLaborPerOffer <= 1;                     // person.cpp:39
+        if (lp.sc.want[req] != w) { lp.sc.want[req] = w; lp.sc.dirty_firm[lp.sc.req_firm[req]] = 1; }
         if (w && lp.sc.ok[req]) { labor += kLaborPerOffer; money += p.st.j_wage[n]; hires++; }   // person.cpp:48-49
     }
     uint8_t bought[G];
@@ -173,8 +185,8 @@ __global__ void large_person_pass(const LargeParams lp) {
         const uint32_t n = lp.sc.req_n[req];
         if (n == kNoEntry) continue;
         const double price = p.st.m_price[n];
-        const bool w = money >= price;                                     // agent.cpp:102
-        lp.sc.want[req] = w;
+        const uint8_t w = money >= price;                                  // agent.cpp:102
+        if (lp.sc.want[req] != w) { lp.sc.want[req] = w; lp.sc.dirty_firm[lp.sc.req_firm[req]] = 1; }
         if (w && lp.sc.ok[req]) {
             money -= price;                                                // agent.cpp:105-111
             const int good = p.st.m_good[n];
@@ -198,63 +210,101 @@ __device__ __forceinline__ bool large_short(const double (&inv)[G], int good) {
 }
 
 // firm pass of the person phase: every event at firm f in the reference's order
-// (review_jobOffer_response firm.cpp:56-90, accept :106-113; review_offer_response agent.cpp:118-150, accept :152-161)
+// (review_jobOffer_response firm.cpp:56-90, accept :106-113; review_offer_response agent.cpp:118-150, accept :152-161).
+// One warp per firm: the lanes fetch 32 events (sorted value + the requester's `want`) at a time, lane 0 walks them
+// with the firm's per-good state in shared memory, the lanes write back the flags that changed.  Firms none of whose
+// events changed `want` since their last pass are skipped.
 template <int G>
-__global__ void large_firm_pass(const LargeParams lp) {
+__global__ void __launch_bounds__(kLargeThreads) large_firm_pass(const LargeParams lp) {
+    constexpr int WPB = kLargeThreads / 32;
+    __shared__ double s_inv[WPB][G], s_price[WPB][G];
+    __shared__ uint32_t s_left[WPB][G], s_taken[WPB][G];
     const StepParams& p = lp.sp;
-    const int F = p.F;
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int F = p.F, P = p.P;
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * WPB + wib;
     if (f >= F) return;
+    if (!lp.sc.dirty_firm[f]) return;
+    __syncwarp();
+    if (lane == 0) lp.sc.dirty_firm[f] = 0;
+    if (lane < G) {
+        s_inv[wib][lane] = p.st.f_inv[(size_t)lane * F + f];
+        const int n = lp.sc.own_offer[f * G + lane];
+        s_left[wib][lane] = n >= 0 ? p.st.m_left[n] : 0u;
+        s_taken[wib][lane] = n >= 0 ? p.st.m_taken[n] : 0u;
+        s_price[wib][lane] = n >= 0 ? p.st.m_price[n] : 0.0;
+    }
+    __syncwarp();
     double money = p.st.f_money[f], labor = p.st.f_labor[f];
     const int nj = lp.sc.own_job[f];
     uint32_t jleft = 0, jtaken = 0;
     double wage = 0.0;
     if (nj >= 0) { jleft = p.st.j_left[nj]; jtaken = p.st.j_taken[nj]; wage = p.st.j_wage[nj]; }
-    double inv[G], price[G];
-    uint32_t left[G], taken[G];
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-        inv[g] = p.st.f_inv[(size_t)g * F + f];
-        const int n = lp.sc.own_offer[f * G + g];
-        left[g] = n >= 0 ? p.st.m_left[n] : 0u;
-        taken[g] = n >= 0 ? p.st.m_taken[n] : 0u;
-        price[g] = n >= 0 ? p.st.m_price[n] : 0.0;
-    }
+    // a good whose inventory is negative makes every sale of ANOTHER good short (agent.cpp:140 compares all goods);
+    // inventories only fall by sold units here, so that set is fixed for the pass
+    uint32_t negmask = 0;
+    for (int g = 0; g < G; g++) negmask |= (s_inv[wib][g] < 0.0 ? 1u : 0u) << g;
     bool changed = false;
     const uint32_t lo = lp.sc.seg[f], hi = lp.sc.seg[f + 1];
-    for (uint32_t pos = lo; pos < hi; pos++) {
-        const uint32_t v = lp.sc.val_out[pos];
-        const uint32_t req = v & kReqMask, type = v >> 27;
-        uint8_t o = 0;
-        if (lp.sc.want[req]) {
+    for (uint32_t base = lo; base < hi; base += 32) {
+        const uint32_t pos = base + lane;
+        const bool live = pos < hi;
+        const uint32_t v = live ? lp.sc.val_out[pos] : 0u;
+        const uint32_t req = v & kReqMask;
+        const uint32_t wmask = __ballot_sync(0xffffffffu, live && lp.sc.want[req]);
+        const uint8_t old = live ? lp.sc.ok[req] : 0;
+        const int n = min(32u, hi - base);
+        uint32_t okmask = 0;
+        for (int k = 0; k < n; k++) {
+            const uint32_t type = __shfl_sync(0xffffffffu, v, k) >> 27;
+            if (lane != 0) continue;
+            // A request its requester does not (currently) make is answered hypothetically, without side effects:
+            // should it be made in a later round, the requester already knows the answer.  This collapses the
+            // requester's own chain (slot i is only made once two earlier jobs failed, ...) into one round.
+            const bool made = (wmask >> k) & 1u;
             if (type == 0) {
                 if (jleft > 0) {                                           // firm.cpp:64
-                    if (money < wage) jleft = 0;                           // firm.cpp:80-84
-                    else { money -= wage; labor += kLaborPerOffer; jleft--; jtaken++; o = 1; }   // firm.cpp:108-111
+                    if (money < wage) { if (made) jleft = 0; }             // firm.cpp:80-84
+                    else {
+                        okmask |= 1u << k;
+                        if (made) { money -= wage; labor += kLaborPerOffer; jleft--; jtaken++; }   // firm.cpp:108-111
+                    }
                 }
             } else {
-                const int good = (int)type - 1;
-#pragma unroll
-                for (int g = 0; g < G; g++) {
-                    if (g != good) continue;
-                    if (left[g] > 0) {                                     // agent.cpp:124
-                        if (large_short<G>(inv, g)) left[g] = 0;           // agent.cpp:140-143
-                        else { money += price[g]; inv[g] -= kAmountPerOffer; left[g]--; taken[g]++; o = 1; }
+                const int g = (int)type - 1;
+                const uint32_t left = s_left[wib][g];
+                if (left > 0) {                                            // agent.cpp:124
+                    const double iv = s_inv[wib][g];
+                    if (iv < kAmountPerOffer || (negmask & ~(1u << g))) { if (made) s_left[wib][g] = 0; }   // agent.cpp:140-143
+                    else {                                                 // agent.cpp:152-161
+                        okmask |= 1u << k;
+                        if (made) {
+                            money += s_price[wib][g];
+                            s_inv[wib][g] = iv - kAmountPerOffer;
+                            s_left[wib][g] = left - 1;
+                            s_taken[wib][g]++;
+                        }
                     }
                 }
             }
         }
-        if (lp.sc.ok[req] != o) { lp.sc.ok[req] = o; changed = true; }
+        okmask = __shfl_sync(0xffffffffu, okmask, 0);
+        if (live) {
+            const uint8_t o = (okmask >> lane) & 1u;
+            if (o != old) { lp.sc.ok[req] = o; lp.sc.dirty_person[req % (uint32_t)P] = 1; changed = true; }
+        }
     }
-    lp.sc.fm_money[f] = money;
-    lp.sc.fm_labor[f] = labor;
-    lp.sc.fm_jleft[f] = jleft;
-    lp.sc.fm_jtaken[f] = jtaken;
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-        lp.sc.fm_inv[(size_t)g * F + f] = inv[g];
-        lp.sc.fm_left[f * G + g] = left[g];
-        lp.sc.fm_taken[f * G + g] = taken[g];
+    __syncwarp();
+    if (lane == 0) {
+        lp.sc.fm_money[f] = money;
+        lp.sc.fm_labor[f] = labor;
+        lp.sc.fm_jleft[f] = jleft;
+        lp.sc.fm_jtaken[f] = jtaken;
+    }
+    if (lane < G) {
+        lp.sc.fm_inv[(size_t)lane * F + f] = s_inv[wib][lane];
+        lp.sc.fm_left[f * G + lane] = s_left[wib][lane];
+        lp.sc.fm_taken[f * G + lane] = s_taken[wib][lane];
     }
     if (changed) *lp.sc.changed = 1;
 }
@@ -290,6 +340,16 @@ __global__ void large_finalize_persons(const LargeParams lp) {
     p.st.p_labor[pid] = labor;
 #pragma unroll
     for (int g = 0; g < G; g++) p.st.p_inv[(size_t)g * P + pid] = inv[g];
+}
+
+// success flags of the person phase: a request was transacted iff it was made and granted
+__global__ void large_person_flags(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const size_t n = (size_t)p.S * p.P;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    if (p.out.p_job_ok) p.out.p_job_ok[t] = lp.sc.want[t] & lp.sc.ok[t];
+    if (p.out.p_good_ok) p.out.p_good_ok[t] = lp.sc.want[n + t] & lp.sc.ok[n + t];
 }
 
 // job counters are final after the person phase
@@ -419,53 +479,57 @@ __global__ void large_firm_phase_pass(const LargeParams lp) {
     if (changed) *lp.sc.changed = 1;
 }
 
-// produce (profitMaxer.cpp:68-72), sell_goods / search_for_laborers decode (neuralFirmDecisionMaker.cpp:111-180)
+// produce (profitMaxer.cpp:68-72), sell_goods / search_for_laborers decode (neuralFirmDecisionMaker.cpp:111-180);
+// one thread per (firm, output good)
 template <int G>
 __global__ void large_finalize_firms(const LargeParams lp) {
     const StepParams& p = lp.sp;
     const int F = p.F;
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    double in[G + 1], inv[G], xin[G];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= F * G) return;
+    const int g = t / F, f = t % F;
+    double in[G + 1];
     in[0] = lp.sc.fm_labor[f];                                             // laborHired after the person phase
+    double inv_g = 0.0, x_g = 0.0;
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-        inv[g] = lp.sc.ff_inv[(size_t)g * F + f];
-        xin[g] = inv[g] * (double)p.ac.f_prod[(size_t)g * F + f];         // neuralFirmDecisionMaker.cpp:101
-        in[g + 1] = xin[g];
+    for (int k = 0; k < G; k++) {
+        const double iv = lp.sc.ff_inv[(size_t)k * F + f];
+        const double xk = iv * (double)p.ac.f_prod[(size_t)k * F + f];    // neuralFirmDecisionMaker.cpp:101
+        in[k + 1] = xk;
+        if (k == g) { inv_g = iv; x_g = xk; }
     }
+    const size_t ag = (size_t)g * F + f;
+    double share[G + 1], theta[G + 1];
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-        const size_t ag = (size_t)g * F + f;
-        double share[G + 1], theta[G + 1];
-#pragma unroll
-        for (int i = 0; i <= G; i++) {
-            const size_t k = ((size_t)g * (G + 1) + i) * F + f;
-            share[i] = p.st.f_prod_share[k];
-            theta[i] = (p.prod_kind == FASTACE_FN_STONE_GEARY) ? p.st.f_prod_theta[k] : 0.0;
-        }
-        const double outg = eval_function<G + 1, false>(p.prod_kind, p.st.f_prod_tfp[ag], share, theta, p.st.f_prod_rho[ag], in);
-        const double newinv = inv[g] + (outg - xin[g]);                    // profitMaxer.cpp:71
-        p.st.f_inv[ag] = newinv;
-        const double amount = (double)p.ac.f_offer_amt[ag] * newinv;       // decisionNetHandler.cpp:591
-        lp.sc.post_lots[f * G + g] = x86_double_to_int(amount / kAmountPerOffer);
-        const int n = lp.sc.own_offer[f * G + g];
-        if (n >= 0) {   // counters of the old entry just before its owner withdraws it (profitMaxer.cpp:79-81)
-            if (p.out.old_m_left) p.out.old_m_left[n] = lp.sc.ff_left[f * G + g];
-            if (p.out.old_m_taken) p.out.old_m_taken[n] = lp.sc.ff_taken[f * G + g];
-        }
+    for (int i = 0; i <= G; i++) {
+        const size_t k = ((size_t)g * (G + 1) + i) * F + f;
+        share[i] = p.st.f_prod_share[k];
+        theta[i] = (p.prod_kind == FASTACE_FN_STONE_GEARY) ? p.st.f_prod_theta[k] : 0.0;
     }
-    p.st.f_money[f] = lp.sc.ff_money[f];
-    p.st.f_last_money[f] = lp.sc.ff_last[f];
-    p.st.f_labor[f] = 0.0;                                                 // firm.cpp:41
-    p.out.f_profit[f] = lp.sc.ff_profit[f];
-    lp.sc.post_jlots[f] = x86_double_to_int((double)p.ac.f_job_labor[f] / kLaborPerOffer);
+    const double outg = eval_function<G + 1, false>(p.prod_kind, p.st.f_prod_tfp[ag], share, theta, p.st.f_prod_rho[ag], in);
+    const double newinv = inv_g + (outg - x_g);                            // profitMaxer.cpp:71
+    p.st.f_inv[ag] = newinv;
+    const double amount = (double)p.ac.f_offer_amt[ag] * newinv;           // decisionNetHandler.cpp:591
+    lp.sc.post_lots[f * G + g] = x86_double_to_int(amount / kAmountPerOffer);
+    const int n = lp.sc.own_offer[f * G + g];
+    if (n >= 0) {   // counters of the old entry just before its owner withdraws it (profitMaxer.cpp:79-81)
+        if (p.out.old_m_left) p.out.old_m_left[n] = lp.sc.ff_left[f * G + g];
+        if (p.out.old_m_taken) p.out.old_m_taken[n] = lp.sc.ff_taken[f * G + g];
+    }
+    if (g == 0) {
+        p.st.f_money[f] = lp.sc.ff_money[f];
+        p.st.f_last_money[f] = lp.sc.ff_last[f];
+        p.st.f_labor[f] = 0.0;                                             // firm.cpp:41
+        p.out.f_profit[f] = lp.sc.ff_profit[f];
+        lp.sc.post_jlots[f] = x86_double_to_int((double)p.ac.f_job_labor[f] / kLaborPerOffer);
+    }
 }
 
-// new books in market order: firms in visiting order, goods ascending, lots > 0 (economy.cpp:52-59, 125-126)
-__global__ void large_post(const LargeParams lp) {
+// new books in market order: firms in visiting order, goods ascending, lots > 0 (economy.cpp:52-59, 125-126).
+// One block scans the per-rank offer counts ...
+__global__ void large_post_scan(const LargeParams lp) {
     const StepParams& p = lp.sp;
-    const int F = p.F, G = lp.G, cap = F * G;
+    const int F = p.F, G = lp.G;
     __shared__ uint32_t part_m[1024], part_j[1024];
     const int per = (F + (int)blockDim.x - 1) / (int)blockDim.x;
     const int lo = min(F, (int)threadIdx.x * per), hi = min(F, lo + per);
@@ -485,34 +549,40 @@ __global__ void large_post(const LargeParams lp) {
         __syncthreads();
     }
     uint32_t bm = threadIdx.x ? part_m[threadIdx.x - 1] : 0u, bj = threadIdx.x ? part_j[threadIdx.x - 1] : 0u;
-    const uint32_t nm = part_m[blockDim.x - 1], nj = part_j[blockDim.x - 1];
-    __syncthreads();
-    // the old book is dead from here on: clear what the new one does not cover, then write the new entries
-    for (int n = (int)nm + (int)threadIdx.x; n < cap; n += blockDim.x) {
-        p.st.m_owner[n] = 0; p.st.m_good[n] = 0; p.st.m_left[n] = 0; p.st.m_taken[n] = 0; p.st.m_price[n] = 0.0;
-    }
-    for (int n = (int)nj + (int)threadIdx.x; n < F; n += blockDim.x) {
-        p.st.j_owner[n] = 0; p.st.j_left[n] = 0; p.st.j_taken[n] = 0; p.st.j_wage[n] = 0.0;
-    }
     for (int q = lo; q < hi; q++) {
         const int f = p.ac.perm_firm[q];
-        for (int g = 0; g < G; g++) {
-            const int lots = lp.sc.post_lots[f * G + g];
-            if (lots > 0) {                                                // neuralFirmDecisionMaker.cpp:135
-                p.st.m_owner[bm] = f; p.st.m_good[bm] = g; p.st.m_left[bm] = (uint32_t)lots; p.st.m_taken[bm] = 0;
-                p.st.m_price[bm] = (double)p.ac.f_offer_price[(size_t)g * F + f] / kAmountPerOffer;
-                bm++;
-            }
-        }
-        const int jl = lp.sc.post_jlots[f];
-        if (jl > 0) {
-            double wage = (double)p.ac.f_job_wage[f];
-            if (wage > kLargeNumber) wage = kLargeNumber;                   // decisionNetHandler.cpp:631-635
-            p.st.j_owner[bj] = f; p.st.j_left[bj] = (uint32_t)jl; p.st.j_taken[bj] = 0; p.st.j_wage[bj] = wage / kLaborPerOffer;
-            bj++;
+        lp.sc.post_base_m[q] = bm; lp.sc.post_base_j[q] = bj;
+        for (int g = 0; g < G; g++) bm += lp.sc.post_lots[f * G + g] > 0;
+        bj += lp.sc.post_jlots[f] > 0;
+    }
+    if (threadIdx.x == blockDim.x - 1) { p.st.m_count[0] = (int32_t)part_m[blockDim.x - 1]; p.st.j_count[0] = (int32_t)part_j[blockDim.x - 1]; }
+}
+// ... then every firm writes its entries, and what the new books do not cover is cleared (the old books are dead).
+__global__ void large_post_write(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int F = p.F, G = lp.G, cap = F * G;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nm = p.st.m_count[0], nj = p.st.j_count[0];
+    if (t >= nm && t < cap) { p.st.m_owner[t] = 0; p.st.m_good[t] = 0; p.st.m_left[t] = 0; p.st.m_taken[t] = 0; p.st.m_price[t] = 0.0; }
+    if (t >= nj && t < F) { p.st.j_owner[t] = 0; p.st.j_left[t] = 0; p.st.j_taken[t] = 0; p.st.j_wage[t] = 0.0; }
+    if (t >= F) return;
+    const int q = t, f = p.ac.perm_firm[q];
+    uint32_t bm = lp.sc.post_base_m[q];
+    for (int g = 0; g < G; g++) {
+        const int lots = lp.sc.post_lots[f * G + g];
+        if (lots > 0) {                                                    // neuralFirmDecisionMaker.cpp:135
+            p.st.m_owner[bm] = f; p.st.m_good[bm] = g; p.st.m_left[bm] = (uint32_t)lots; p.st.m_taken[bm] = 0;
+            p.st.m_price[bm] = (double)p.ac.f_offer_price[(size_t)g * F + f] / kAmountPerOffer;
+            bm++;
         }
     }
-    if (threadIdx.x == 0) { p.st.m_count[0] = (int32_t)nm; p.st.j_count[0] = (int32_t)nj; }
+    const int jl = lp.sc.post_jlots[f];
+    if (jl > 0) {
+        double wage = (double)p.ac.f_job_wage[f];
+        if (wage > kLargeNumber) wage = kLargeNumber;                       // decisionNetHandler.cpp:631-635
+        const uint32_t bj = lp.sc.post_base_j[q];
+        p.st.j_owner[bj] = f; p.st.j_left[bj] = (uint32_t)jl; p.st.j_taken[bj] = 0; p.st.j_wage[bj] = wage / kLaborPerOffer;
+    }
 }
 
 }  // namespace fastace
