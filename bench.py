@@ -226,7 +226,19 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; fastace_b200 has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # communicator creation prints "NCCL version ..." on stdout: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     E = args.econ
     # economies shard by index: rank r owns global economies [r*E, (r+1)*E); distinct seeds per rank
     dims, state, acts = build_workload(E, seed=1 + rank * E)
@@ -402,6 +414,13 @@ def run_ours(args):
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.manual_seed(0)                     # identical initial replicas on every rank
         tnets = policy.DecisionNets(numGoods=G, stackSize=S).to(dev)
+        # Random-init heads fed with unnormalised money / inventories overflow exp() of the log-normal price and wage
+        # heads within a few steps (as they do in the reference, which then abandons the episode); the output layers
+        # are scaled by 0.05 so that the timed update trains on (nearly) all economies instead of dropping them.
+        with torch.no_grad():
+            for name, prm in tnets.named_parameters():
+                if ".last" in name and "offerEncoder" not in name and "jobOfferEncoder" not in name:
+                    prm.mul_(0.05)
         a2c = trainer.AdvantageActorCritic(tnets, adam_kwargs=dict(fused=True))
         gen = torch.Generator(device=dev)
         gen.manual_seed(4321 + rank)
