@@ -15,6 +15,7 @@
 #include "step_kernel.cuh"
 #include "match_update_kernels.cuh"
 #include "large_economy.cuh"
+#include "mlp_stack.cuh"
 
 namespace fastace {
 
@@ -709,6 +710,63 @@ int fastace_env_sync(fastace_env_t* env) {
         FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->copy_out));
     }
     return FASTACE_OK;
+}
+
+}  // extern "C"
+
+// ---- policy side: fused residual tanh stack (mlp_stack.cuh) ------------------------------------------------
+static int mlp_tiles_for(int hidden) {
+    const int need = (hidden + 7) / 8;
+    const int choices[] = {2, 4, 8, 13, 16};
+    for (int c : choices) if (need <= c) return c;
+    return 0;
+}
+template <int NT>
+static int launch_mlp_stack(const MlpParams& mp, cudaStream_t stream) {
+    using T = MlpTile<NT>;
+    static bool configured[64] = {};
+    int dev = 0;
+    FASTACE_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)mlp_residual_stack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
+        configured[dev] = true;
+    }
+    int sms = 0;
+    FASTACE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long rows_per_block = (long long)kMlpWarps * 16;
+    const long long nblocks = (mp.rows + rows_per_block - 1) / rows_per_block;
+    const int grid = (int)std::min<long long>(nblocks, (long long)sms);   // persistent: one CTA per SM
+    mlp_residual_stack_kernel<NT><<<grid, kMlpThreads, T::SMEM, stream>>>(mp);
+    FASTACE_CUDA_CHECK(cudaGetLastError());
+    return FASTACE_OK;
+}
+
+extern "C" {
+
+int fastace_mlp_stack_layout(int hidden, int* padded_out, int* padded_in) {
+    const int nt = mlp_tiles_for(hidden);
+    if (hidden < 2 || (hidden & 1) || nt == 0) { set_error("fused stack needs an even hidden size in [2, 128]"); return FASTACE_ERR_INVALID; }
+    if (padded_out) *padded_out = nt * 8;
+    if (padded_in) *padded_in = ((nt + 1) / 2) * 16 + 8;
+    return FASTACE_OK;
+}
+
+int fastace_mlp_residual_tanh_stack(const float* x, float* y, int64_t rows, int hidden, int layers,
+                                    const uint16_t* w_bf16, const float* bias, void* cuda_stream) {
+    if (!x || !y || !w_bf16 || !bias || rows < 0 || layers < 1) { set_error("bad argument"); return FASTACE_ERR_INVALID; }
+    const int nt = mlp_tiles_for(hidden);
+    if (hidden < 2 || (hidden & 1) || nt == 0) { set_error("fused stack needs an even hidden size in [2, 128]"); return FASTACE_ERR_INVALID; }
+    if (rows == 0) return FASTACE_OK;
+    MlpParams mp;
+    mp.x = x; mp.y = y; mp.rows = rows; mp.H = hidden; mp.L = layers; mp.w = w_bf16; mp.bias = bias;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    switch (nt) {
+        case 2: return launch_mlp_stack<2>(mp, stream);
+        case 4: return launch_mlp_stack<4>(mp, stream);
+        case 8: return launch_mlp_stack<8>(mp, stream);
+        case 13: return launch_mlp_stack<13>(mp, stream);
+        default: return launch_mlp_stack<16>(mp, stream);
+    }
 }
 
 int fastace_env_large_stats(const fastace_env_t* env, uint32_t* person_rounds, uint32_t* firm_rounds) {

@@ -28,6 +28,20 @@ def _xavier(module):
         nn.init.constant_(module.bias, 0.01)
 
 
+_FUSED = False    # set by BatchedPolicy(fused=True) around its no-grad forward: residual stacks run as one CUDA kernel
+
+
+def _residual_stack(x, layers):
+    """x <- x + tanh(h(x)) for every layer (the hidden stack of every decision net)"""
+    if (_FUSED and x.is_cuda and not torch.is_grad_enabled() and len(layers) > 0 and x.shape[-1] % 2 == 0
+            and x.shape[-1] <= 128 and all(h.in_features == h.out_features == x.shape[-1] for h in layers)):
+        from . import fused_mlp
+        return fused_mlp.residual_tanh_stack(x, layers)
+    for h in layers:
+        x = x + torch.tanh(h(x))
+    return x
+
+
 class _Hidden(nn.Module):
     """registers `hidden0..hiddenN-1` (or another prefix) as direct children, like the reference"""
 
@@ -53,8 +67,7 @@ class OfferEncoder(_Hidden):
 
     def forward(self, x):
         x = torch.tanh(self.dimReduce(x))
-        for h in self._hidden:
-            x = x + torch.tanh(h(x))
+        x = _residual_stack(x, self._hidden)
         return torch.tanh(self.last(x))
 
 
@@ -79,8 +92,7 @@ class PurchaseNet(_Hidden):
     def forward(self, offerEncodings, utilParams, budget, labor, inventory):
         x = _head_features(self.flatten, offerEncodings, utilParams, budget, labor, inventory)
         x = torch.tanh(self._hidden[0](x))
-        for h in self._hidden[1:]:
-            x = x + torch.tanh(h(x))
+        x = _residual_stack(x, self._hidden[1:])
         return torch.sigmoid(self.last(x))
 
 
@@ -97,8 +109,7 @@ class ConsumptionNet(_Hidden):
 
     def forward(self, utilParams, money, labor, inventory):
         x = torch.tanh(self.first(torch.cat([utilParams, money, labor, inventory], dim=-1)))
-        for h in self._hidden:
-            x = x + torch.tanh(h(x))
+        x = _residual_stack(x, self._hidden)
         return self.last(x).reshape(*x.shape[:-1], self.numGoods, 2)
 
 
@@ -131,13 +142,9 @@ class OfferNet(_Hidden):
     def forward(self, offerEncodings, utilParams, money, labor, inventory):
         x = _head_features(self.flatten, offerEncodings, utilParams, money, labor, inventory)
         x = torch.tanh(self._first[0](x))
-        for h in self._first[1:]:
-            x = x + torch.tanh(h(x))
-        xa = x + torch.tanh(self._a[0](x))
-        xb = x + torch.tanh(self._b[0](x))
-        for ha, hb in zip(self._a[1:], self._b[1:]):
-            xa = xa + torch.tanh(ha(xa))
-            xb = xb + torch.tanh(hb(xb))
+        x = _residual_stack(x, self._first[1:])
+        xa = _residual_stack(x, self._a)
+        xb = _residual_stack(x, self._b)
         xa = self.last_a(xa).reshape(*x.shape[:-1], self.numGoods, 2)
         xb = self.last_b(xb).reshape(*x.shape[:-1], self.numGoods, 2)
         return torch.cat([xa, xb], dim=-1)
@@ -160,8 +167,7 @@ class JobOfferNet(_Hidden):
     def forward(self, offerEncodings, utilParams, money, labor, inventory):
         x = _head_features(self.flatten, offerEncodings, utilParams, money, labor, inventory)
         x = torch.tanh(self._hidden[0](x))
-        for h in self._hidden[1:]:
-            x = x + torch.tanh(h(x))
+        x = _residual_stack(x, self._hidden[1:])
         return self.last(x)
 
 
@@ -185,8 +191,7 @@ class ValueNet(_Hidden):
         jx = torch.tanh(self.jobOfferFlatten(jobOfferEncodings).squeeze(-1))
         x = torch.cat([ox, jx, utilParams, money, labor, inventory], dim=-1)
         x = torch.tanh(self._hidden[0](x))
-        for h in self._hidden[1:]:
-            x = x + torch.tanh(h(x))
+        x = _residual_stack(x, self._hidden[1:])
         return self.last(x)
 
 
@@ -400,8 +405,10 @@ class BatchedPolicy:
     persons, as in the reference's first decision of a turn).  The networks, the index draws, the
     sampling rules and the action decode are the reference's."""
 
-    def __init__(self, env, nets, generator=None, autocast_dtype=None):
-        self.env, self.nets, self.gen, self.autocast_dtype = env, nets, generator, autocast_dtype
+    def __init__(self, env, nets, generator=None, autocast_dtype=None, fused=False):
+        """fused=True: the residual hidden stacks run through the hand-written kernel (csrc/mlp_stack.cuh, bf16
+        tensor-core operands, fp32 accumulate/residual) instead of eager torch — a rollout-only fast mode."""
+        self.env, self.nets, self.gen, self.autocast_dtype, self.fused = env, nets, generator, autocast_dtype, fused
         self.E, self.P, self.F, self.G, self.S = env.dims.tuple
         self.state = env.device_state_tensors()
         self.dev = self.state["p_money"].device
@@ -413,9 +420,14 @@ class BatchedPolicy:
         """Fill self.actions for one step.  perms = (perm_person, perm_firm) int32 [E,P] / [E,F] (host or device).
         Returns a dict with log-probabilities and state values (device tensors); when `record` is a list,
         (snapshot, draws) of the step is appended to it so a trainer can re-evaluate the step with autograd."""
+        global _FUSED
         snap = snapshot(self.state) if record is not None else self.state
         draws = draw(snap, self.S, self.gen)
-        decoded, info = evaluate(self.nets, snap, draws, self.autocast_dtype)
+        _FUSED = self.fused
+        try:
+            decoded, info = evaluate(self.nets, snap, draws, self.autocast_dtype)
+        finally:
+            _FUSED = False
         if record is not None:
             record.append((snap, draws))
         a = self.actions

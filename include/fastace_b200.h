@@ -306,6 +306,16 @@ int fastace_env_kernel_times(fastace_env_t* env, double* match_ms, double* updat
 /* Iteration rounds of the last large-economy step (person phase, firm phase). */
 int fastace_env_large_stats(const fastace_env_t* env, uint32_t* person_rounds, uint32_t* firm_rounds);
 
+/* ---- policy side: fused residual tanh stack ------------------------------------------------------------ */
+/* x <- x + tanh(x W_l^T + b_l) for l = 0..layers-1 on a DEVICE [rows][hidden] fp32 matrix: the hidden stack of the
+ * reference's decision networks (src/neural/decisionNets.cpp:66-70, 135-139, 186-190, 283-290, 368-372, 439-443) in
+ * one kernel, activations resident in registers (bf16 tensor-core operands, fp32 accumulate and residual).
+ * `w_bf16` is [layers][padded_out][padded_in] bf16 with W_l[out][in] zero-padded, `bias` [layers][padded_out] fp32
+ * zero-padded; the padded sizes come from fastace_mlp_stack_layout.  y may alias x.  Rollout-only (no gradient). */
+int fastace_mlp_stack_layout(int hidden, int* padded_out, int* padded_in);
+int fastace_mlp_residual_tanh_stack(const float* x, float* y, int64_t rows, int hidden, int layers,
+                                    const uint16_t* w_bf16, const float* bias, void* cuda_stream);
+
 /* ---- legacy entry points of libpybindings.so (src/pybindings.h:8-28) ------------------ */
 /* Byte-identical layouts of neural::CustomScenarioParams (344 B) and
  * neural::TrainingParams (136 B), src/neural/neuralScenarios.h:49-186, py/main.py:12-85. */
