@@ -735,7 +735,7 @@ static int launch_mlp_stack(const MlpParams& mp, cudaStream_t stream) {
     FASTACE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long rows_per_block = (long long)kMlpWarps * 16;
     const long long nblocks = (mp.rows + rows_per_block - 1) / rows_per_block;
-    const int grid = (int)std::min<long long>(nblocks, (long long)sms);   // persistent: one CTA per SM
+    const int grid = (int)std::min<long long>(nblocks, (long long)sms * kMlpBlocksPerSM);   // persistent
     mlp_residual_stack_kernel<NT><<<grid, kMlpThreads, T::SMEM, stream>>>(mp);
     FASTACE_CUDA_CHECK(cudaGetLastError());
     return FASTACE_OK;

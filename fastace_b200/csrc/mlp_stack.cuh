@@ -22,7 +22,8 @@
 
 namespace fastace {
 
-constexpr int kMlpWarps = 12;
+constexpr int kMlpWarps = 6;
+constexpr int kMlpBlocksPerSM = 2;   // two independent CTAs per SM: their mma / tanh phases interleave
 constexpr int kMlpThreads = kMlpWarps * 32;
 
 struct MlpParams {
@@ -68,7 +69,7 @@ struct MlpTile {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_residual_stack_kernel(const MlpParams mp) {
+__global__ void __launch_bounds__(kMlpThreads, kMlpBlocksPerSM) mlp_residual_stack_kernel(const MlpParams mp) {
     using T = MlpTile<NT>;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
