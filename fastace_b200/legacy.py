@@ -1,0 +1,160 @@
+"""`run` / `train` of the reference's Python front end (py/main.py:112-155 -> src/pybindings.cpp:78-114 ->
+neural::train, src/neural/neuralScenarios.cpp:205-327) on the batched env — §8 row (f-3).
+
+Same arguments as py/main.py's wrappers: the two ctypes structs (`CustomScenarioParams`, `TrainingParams`, byte-identical
+layouts, created by the library's own create_scenario_params / create_training_params), `fromPretrained`,
+`perturbationSize`; `train` returns the list of episode losses and writes the final learning rates back into
+`trainingParams`, checkpoints the 11 nets every `checkpointEveryNEpisodes`, reloads the last checkpoint when an episode's
+loss is NaN (or stops with "Training failed before first checkpoint"), prints the running average every
+`updateEveryNEpisodes`.  What differs, by construction: every "episode" is `numEconomies` economies stepped at once on
+the GPU (the reference steps one), so an episode loss is the mean over those economies.
+
+Checkpoints: `<saveDir>/<net>.pt` for the reference's eleven names (decisionNetHandler.cpp:726-757).  Files written
+here are torch state_dicts with the reference's parameter names; files written by the reference's torch::save (a
+TorchScript archive) are read through torch.jit.load."""
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _abi, policy, scenario, trainer
+from .env import BatchedEconomy
+
+DEFAULT_SAVE_DIR = "../models/"      # neuralConstants.h:32
+
+
+def save_models(nets, saveDir=DEFAULT_SAVE_DIR):
+    os.makedirs(saveDir, exist_ok=True)
+    for name in policy.NET_NAMES:
+        torch.save({k: v.detach().cpu() for k, v in nets.net(name).state_dict().items()}, os.path.join(saveDir, name + ".pt"))
+
+
+def load_models(nets, saveDir=DEFAULT_SAVE_DIR):
+    for name in policy.NET_NAMES:
+        path = os.path.join(saveDir, name + ".pt")
+        try:
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+        except Exception:
+            sd = {k: v.detach() for k, v in torch.jit.load(path, map_location="cpu").named_parameters()}   # reference's torch::save
+        own = dict(nets.net(name).named_parameters())
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k in own:
+                    own[k].copy_(v)
+
+
+def perturb_models(nets, pct, generator=None):
+    """DecisionNetHandler::perturb_models (decisionNetHandler.cpp:763-775): every Linear weight becomes
+    sqrt(1-pct) * W + sqrt(xavier_var * pct) * N(0,1) (perturb_layer, decisionNets.cpp:14-39); a net perturbs its own
+    layers, the two encoders are perturbed once each."""
+    assert 0.0 <= pct <= 1.0
+    seen = set()
+    with torch.no_grad():
+        for name in policy.NET_NAMES:
+            for mod_name, mod in nets.net(name).named_modules():
+                if not isinstance(mod, torch.nn.Linear) or id(mod) in seen:
+                    continue
+                if name not in ("offerEncoder", "jobOfferEncoder") and ("offerEncoder" in mod_name or "jobOfferEncoder" in mod_name):
+                    continue
+                seen.add(id(mod))
+                out_f, in_f = mod.weight.shape
+                std = math.sqrt(2.0 / (in_f + out_f) * pct)
+                noise = torch.randn(mod.weight.shape, generator=generator, device="cpu").to(mod.weight.device) * std
+                mod.weight.mul_(math.sqrt(1 - pct)).add_(noise)
+
+
+def _build(scenarioParams, trainingParams, numEconomies, device):
+    tp = trainingParams
+    dims = (numEconomies, int(scenarioParams.numPeople), int(scenarioParams.numFirms), 2, int(tp.stackSize))
+    env = BatchedEconomy(dims, device=device)
+    nets = policy.DecisionNets(numGoods=2, stackSize=int(tp.stackSize), encodingSize=int(tp.encodingSize),
+                               hiddenSize=int(tp.hiddenSize), nHidden=int(tp.nHidden), nHiddenSmall=int(tp.nHiddenSmall))
+    nets = nets.to(torch.device("cuda", device))
+    return dims, env, nets
+
+
+def market_info(env, economy=0, goods=("good1", "good2")):
+    """print_info of src/pybindings.cpp:20-75 for one economy: average price per good and average wage"""
+    st = env.get_state()
+    lines = [f"Time = {env.get_time()}:"]
+    n = int(st["m_count"][economy])
+    if n > 0:
+        for g, gname in enumerate(goods):
+            sel = st["m_good"][economy, :n] == g
+            if sel.any():
+                lines.append(f"{gname}: Avg. price = {float((1.0 / st['m_price'][economy, :n][sel]).mean()):g} (num. offers = {int(sel.sum())})")
+            else:
+                lines.append(f"{gname}: Avg. price = NA (num. offers = 0)")
+    else:
+        lines.append("[No offers]")
+    nj = int(st["j_count"][economy])
+    if nj > 0:
+        lines.append(f"Avg. wage per unit of labor = {float((st['j_wage'][economy, :nj] / 0.5).mean()):g} (num. offers = {nj})")
+    else:
+        lines.append("[No job offers]")
+    return "\n".join(lines)
+
+
+def run(scenarioParams, trainingParams, numEconomies=1, device=0, saveDir=DEFAULT_SAVE_DIR, seed=0, fused=True, quiet=False):
+    """lib.run: load the saved nets, step one episode without gradients, print the market after every step."""
+    dims, env, nets = _build(scenarioParams, trainingParams, numEconomies, device)
+    load_models(nets, saveDir)
+    env.set_state(scenario.custom_initial_state(dims, seed, scenarioParams)[0])
+    pol = policy.BatchedPolicy(env, nets.eval(), fused=fused)
+    orders = scenario.OrderStream(dims, seed + 1)
+    out = env.alloc_outputs()
+    log = []
+    for _ in range(int(trainingParams.episodeLength)):
+        pol.step(orders.next(), out, flags=_abi.IDX_ABSOLUTE)
+        log.append(market_info(env))
+        if not quiet:
+            print(log[-1])
+    env.close()
+    return log
+
+
+def train(scenarioParams, trainingParams, fromPretrained=False, perturbationSize=0.0, numEconomies=64, device=0,
+          saveDir=DEFAULT_SAVE_DIR, seed=0, quiet=False, trainer_kwargs=None):
+    """lib.train: returns the episode losses; learning rates are written back into trainingParams."""
+    tp = trainingParams
+    dims, env, nets = _build(scenarioParams, tp, numEconomies, device)
+    if fromPretrained:                                   # train_from_pretrained, neuralScenarios.cpp:313-327
+        load_models(nets, saveDir)
+        if perturbationSize > 0.0:
+            perturb_models(nets, perturbationSize)
+    lrs = {n: float(getattr(tp, n + "LR")) for n in trainer.NET_ORDER}
+    a2c = trainer.AdvantageActorCritic(
+        nets, lrs=lrs, episodeBatchSizeForLRDecay=int(tp.episodeBatchSizeForLRDecay), patienceForLRDecay=int(tp.patienceForLRDecay),
+        multiplierForLRDecay=float(tp.multiplierForLRDecay), cosinePeriod=int(tp.reverseAnnealingPeriod), **(trainer_kwargs or {}))
+    pol = policy.BatchedPolicy(env, nets)
+    out = env.alloc_outputs()
+    say = (lambda *a: None) if quiet else print
+    losses = [0.0] * int(tp.numEpisodes)
+    for i in range(int(tp.numEpisodes)):
+        state, discount = scenario.custom_initial_state(dims, seed + i * numEconomies, scenarioParams)   # scenario->setup()
+        env.set_state(state, time=0)
+        a2c.discount = torch.from_numpy(discount).to(torch.device("cuda", device))     # UtilMaxer::get_discountRate per person
+        orders = scenario.OrderStream(dims, seed + 7919 * (i + 1))
+        ep = trainer.run_episode(pol, orders, out, int(tp.episodeLength), flags=_abi.IDX_ABSOLUTE)
+        loss = a2c.train_on_episode(ep)
+        if math.isnan(loss):                              # neuralScenarios.cpp:229-243
+            if i >= int(tp.checkpointEveryNEpisodes):
+                say(f"In episode {i + 1}: NaN encountered; reverting to last checkpoint.")
+                load_models(nets, saveDir)
+                loss = losses[i - 1]
+            else:
+                say("Training failed before first checkpoint.")
+                break
+        elif (i + 1) % int(tp.checkpointEveryNEpisodes) == 0 or i == int(tp.numEpisodes) - 1:
+            save_models(nets, saveDir)
+        losses[i] = loss
+        every = int(tp.updateEveryNEpisodes)
+        if every != 0 and ((i + 1) % every == 0 or i + 1 == int(tp.numEpisodes)):
+            window = every if every <= int(tp.numEpisodes) else int(tp.numEpisodes)
+            avg = float(np.mean([losses[i - j] for j in range(window)]))
+            say(f"Episode {i + 1}: Average loss over past {window} episodes = {avg:.6e}")
+    for n, lr in a2c.learning_rates().items():            # neuralScenarios.cpp:264-272
+        setattr(tp, n + "LR", lr)
+    env.close()
+    return losses

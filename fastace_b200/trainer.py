@@ -178,14 +178,14 @@ class AdvantageActorCritic:
     def learning_rates(self):
         return {name: self.schedulers[name].get_lr() for name in NET_ORDER}
 
-    def returns_and_advantages(self, ep):
+    def returns_and_advantages(self, ep, discount=None):
         """q and advantage series (get_advantage_for_person / _for_firm, :269-299, :345-375): fp64 returns,
         advantages stored in fp32 like the reference's torch::empty(time) buffer."""
         T = len(ep)
         q = torch.zeros_like(ep.p_reward[0], dtype=torch.float64)
         q_p, adv_p = [None] * T, [None] * T
         for t in range(T - 1, -1, -1):
-            q = ep.p_reward[t].double() + self.discount * q
+            q = ep.p_reward[t].double() + (self.discount if discount is None else discount) * q
             q_p[t] = q
             adv_p[t] = (q - ep.value_person[t].double()).float()
         q = torch.zeros_like(ep.f_profit[0], dtype=torch.float64)
@@ -205,18 +205,21 @@ class AdvantageActorCritic:
         dev = ep.p_reward[0].device
         E_local = ep.p_reward[0].shape[0]
         self.last_dropped = 0
+        discount = self.discount        # a scalar, or one rate per person [E, P] (UtilMaxer::get_discountRate)
         if self.nan_policy == "drop_economy" and ep.finite is not None and not bool(ep.finite.all()):
             keep = ep.finite.nonzero().flatten()
             self.last_dropped = E_local - keep.numel()
             ep = ep.select(keep)
             E_local = keep.numel()
+            if torch.is_tensor(discount) and discount.dim() == 2:
+                discount = discount.index_select(0, keep)
         count = torch.tensor([float(E_local)], dtype=torch.float64, device=dev)
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(count, group=self.group)
         if count.item() == 0:
             return float("nan")                 # nothing usable: no step (the reference would reload its checkpoint)
         scale = 1.0 / count.item()
-        q_p, adv_p, q_f, adv_f = self.returns_and_advantages(ep)
+        q_p, adv_p, q_f, adv_f = self.returns_and_advantages(ep, discount)
         names = ("purchaseNet", "laborSearchNet", "consumptionNet", "firmPurchaseNet", "productionNet", "offerNet",
                  "jobOfferNet", "firmValueNet")
         sums = torch.zeros(len(names) + 1, dtype=torch.float64, device=dev)   # tracked policy losses + total loss
