@@ -195,6 +195,29 @@ def alloc_host(kind, dims, names=None):
     return out
 
 
+def alloc_host_block(kind, dims, names=None, pinned=False):
+    """Like alloc_host, but all arrays are views into ONE buffer laid out as the library's device staging block
+    (fields in struct order, each padded to 256 B): fastace_env_step_host* then moves the whole struct with a single
+    host<->device copy.  pinned=True page-locks the buffer (through torch).  Returns (dict of arrays, buffer)."""
+    table = [(n, dt, shp) for n, (dt, shp) in shapes(kind, dims).items() if names is None or n in names]
+    offs, total = [], 0
+    for n, dt, shp in table:
+        offs.append(total)
+        total += (int(np.prod(shp)) * np.dtype(dt).itemsize + 255) // 256 * 256
+    if pinned:
+        import torch
+        holder = torch.zeros(max(total, 1) + 256, dtype=torch.uint8).pin_memory()
+        buf = holder.numpy()
+    else:
+        holder = buf = np.zeros(max(total, 1) + 256, dtype=np.uint8)
+    base = (-buf.ctypes.data) % 256          # 256 B aligned start
+    out = {}
+    for (n, dt, shp), o in zip(table, offs):
+        nbytes = int(np.prod(shp)) * np.dtype(dt).itemsize
+        out[n] = buf[base + o: base + o + nbytes].view(dt).reshape(shp)
+    return out, holder
+
+
 def struct_from_numpy(kind, arrays, dims=None):
     """Build the ctypes struct from a dict of numpy arrays (missing names -> NULL).
     Arrays must be C-contiguous with the exact dtype; shapes are checked when dims given."""

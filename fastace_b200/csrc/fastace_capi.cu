@@ -658,10 +658,29 @@ static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::ve
     for (auto& f : fields)
         if (f.count && !member(actions, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
     if (env->buf_used[b]) FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->copy_in, env->kern_done[b], 0));
-    for (auto& f : fields)
-        if (f.count)
-            FASTACE_CUDA_CHECK(cudaMemcpyAsync(member(&dacts[b], f.offset), member(actions, f.offset), f.elem * f.count,
-                                               cudaMemcpyHostToDevice, env->copy_in));
+    {
+        // Host arrays that sit in one block with the staging buffer's own layout (fields in struct order, each
+        // padded to 256 B — what fastace_b200._abi.alloc_host_block hands out) travel as ONE copy instead of 14.
+        const char* run_h = nullptr; char* run_d = nullptr; size_t run_n = 0;
+        auto flush = [&]() -> cudaError_t {
+            cudaError_t e = run_n ? cudaMemcpyAsync(run_d, run_h, run_n, cudaMemcpyHostToDevice, env->copy_in) : cudaSuccess;
+            run_n = 0;
+            return e;
+        };
+        for (auto& f : fields) {
+            if (!f.count) continue;
+            const char* h = static_cast<const char*>(member(actions, f.offset));
+            char* d = static_cast<char*>(member(&dacts[b], f.offset));
+            const size_t bytes = f.elem * f.count;
+            if (run_n && h == run_h + align_up(run_n, 256) && d == run_d + align_up(run_n, 256)) {
+                run_n = align_up(run_n, 256) + bytes;
+            } else {
+                FASTACE_CUDA_CHECK(flush());
+                run_h = h; run_d = d; run_n = bytes;
+            }
+        }
+        FASTACE_CUDA_CHECK(flush());
+    }
     FASTACE_CUDA_CHECK(cudaEventRecord(env->h2d_done[b], env->copy_in));
     FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->stream, env->h2d_done[b], 0));
     if (env->buf_used[b]) FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->stream, env->d2h_done[b], 0));
@@ -674,11 +693,26 @@ static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::ve
     if (rc != FASTACE_OK) return rc;
     FASTACE_CUDA_CHECK(cudaEventRecord(env->kern_done[b], env->stream));
     FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->copy_out, env->kern_done[b], 0));
-    for (auto& f : out_fields(env->dims)) {
-        void* dst = member(out, f.offset);
-        if (dst && f.count)
-            FASTACE_CUDA_CHECK(cudaMemcpyAsync(dst, member(&env->dout[b], f.offset), f.elem * f.count,
-                                               cudaMemcpyDeviceToHost, env->copy_out));
+    {
+        char* run_h = nullptr; const char* run_d = nullptr; size_t run_n = 0;
+        auto flush = [&]() -> cudaError_t {
+            cudaError_t e = run_n ? cudaMemcpyAsync(run_h, run_d, run_n, cudaMemcpyDeviceToHost, env->copy_out) : cudaSuccess;
+            run_n = 0;
+            return e;
+        };
+        for (auto& f : out_fields(env->dims)) {
+            char* h = static_cast<char*>(member(out, f.offset));
+            if (!h || !f.count) continue;
+            const char* d = static_cast<const char*>(member(&env->dout[b], f.offset));
+            const size_t bytes = f.elem * f.count;
+            if (run_n && h == run_h + align_up(run_n, 256) && d == run_d + align_up(run_n, 256)) {
+                run_n = align_up(run_n, 256) + bytes;
+            } else {
+                FASTACE_CUDA_CHECK(flush());
+                run_h = h; run_d = d; run_n = bytes;
+            }
+        }
+        FASTACE_CUDA_CHECK(flush());
     }
     FASTACE_CUDA_CHECK(cudaEventRecord(env->d2h_done[b], env->copy_out));
     env->buf_used[b] = true;

@@ -197,3 +197,29 @@ def test_async_host_pipeline_equals_sync(oracle):
         assert np.array_equal(envs[0][k], envs[1][k]), k
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a["p_reward"], b["p_reward"]) and np.array_equal(a["f_profit"], b["f_profit"])
+
+
+@pytest.mark.parametrize("kind", ["actions", "compact"])
+def test_host_block_single_copy_path(oracle, kind):
+    """host arrays carved from one block (alloc_host_block) take the single-copy staging path; results unchanged"""
+    from fastace_b200.env import BatchedEconomy
+    dims = (6, 100, 10, 2, 10)
+    state = scenario.custom_initial_state(dims, 41)[0]
+    env = BatchedEconomy(dims)
+    env.set_state(state)
+    ost = H.copy_state(state)
+    orders = scenario.OrderStream(dims, 42)
+    for t in range(8):
+        act = scenario.synthetic_actions(dims, seed=43, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
+        before = H.copy_state(ost)
+        oout = _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=_abi.IDX_MODULO, time_before=t)
+        src = act if kind == "actions" else _abi.compact_actions_for_counts(act, before["j_count"], before["m_count"], True)
+        blk, _keep = _abi.alloc_host_block(kind, dims)
+        for k, v in src.items():
+            blk[k][...] = v
+        gout, _keep2 = _abi.alloc_host_block("out", dims)
+        env.time_step_host(_abi.struct_from_numpy(kind, blk, dims), gout, flags=_abi.IDX_MODULO)
+        H.compare_outputs(gout, oout, dims, before)
+        H.compare_states(env.get_state(), ost, dims)
+    env.close()

@@ -145,3 +145,21 @@ def test_env_create_rejects_bad_dims(native_lib):
     # without a GPU the call gets as far as the device check
     d = _abi.make_dims(1, 1000, 200, 2, 10)
     assert native_lib.fastace_env_create(C.byref(d), 0, C.byref(h)) in (0, -3)
+
+
+def test_host_block_layout_matches_staging_layout():
+    """alloc_host_block: fields in struct order, 256 B aligned and padded — the layout step_host copies in one piece"""
+    dims = (3, 11, 4, 2, 5)
+    for kind in ("actions", "compact", "out"):
+        blk, holder = _abi.alloc_host_block(kind, dims)
+        shp = _abi.shapes(kind, dims)
+        assert list(blk) == list(shp)
+        at = None
+        for n, (dt, shape) in shp.items():
+            a = blk[n]
+            assert a.dtype == dt and tuple(a.shape) == tuple(shape) and a.flags["C_CONTIGUOUS"]
+            assert a.ctypes.data % 256 == 0
+            if at is not None:
+                assert a.ctypes.data == at
+            at = a.ctypes.data + (a.nbytes + 255) // 256 * 256
+        _abi.struct_from_numpy(kind, blk, dims)      # accepted as is
