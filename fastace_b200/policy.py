@@ -71,8 +71,31 @@ class OfferEncoder(_Hidden):
         return torch.tanh(self.last(x))
 
 
+class IndexedEncodings:
+    """The stack of encodings an agent looks at, given as (table of all encoded offers of its economy, indices):
+    table [E, N, enc], idx [E, A, S], valid [E,1,1] (False = empty market, encodings are zeros,
+    decisionNetHandler.cpp:542-565).  `flatten` is linear, so flatten(gather(table)) == gather(flatten(table)): the
+    nets apply their Linear(enc -> 1) to the N table rows and gather scalars instead of gathering [E,A,S,enc] rows."""
+
+    def __init__(self, table, idx, valid, flat=False):
+        self.table, self.idx, self.valid, self.flat = table, idx, valid, flat   # flat: return [E*A, S] rows
+
+    def flattened(self, flatten):
+        flat = flatten(self.table).squeeze(-1)                               # [E, N]
+        A = self.idx.shape[1]
+        picked = torch.gather(flat.unsqueeze(1).expand(-1, A, -1), 2, self.idx)   # [E, A, S]
+        out = torch.where(self.valid, picked, flatten.bias.to(picked.dtype))       # flatten(0) = bias
+        return out.reshape(-1, out.shape[-1]) if self.flat else out
+
+
+def _flat(flatten, enc):
+    if isinstance(enc, IndexedEncodings):
+        return enc.flattened(flatten)
+    return flatten(enc).squeeze(-1)
+
+
 def _head_features(flatten, offerEncodings, *rest):
-    x = torch.tanh(flatten(offerEncodings).squeeze(-1))
+    x = torch.tanh(_flat(flatten, offerEncodings))
     return torch.cat([x, *rest], dim=-1)
 
 
@@ -187,8 +210,8 @@ class ValueNet(_Hidden):
         self.jobOfferEncoder = jobOfferEncoder
 
     def forward(self, offerEncodings, jobOfferEncodings, utilParams, money, labor, inventory):
-        ox = torch.tanh(self.offerFlatten(offerEncodings).squeeze(-1))
-        jx = torch.tanh(self.jobOfferFlatten(jobOfferEncodings).squeeze(-1))
+        ox = torch.tanh(_flat(self.offerFlatten, offerEncodings))
+        jx = torch.tanh(_flat(self.jobOfferFlatten, jobOfferEncodings))
         x = torch.cat([ox, jx, utilParams, money, labor, inventory], dim=-1)
         x = torch.tanh(self._hidden[0](x))
         x = _residual_stack(x, self._hidden[1:])
@@ -330,10 +353,11 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference"):
         validM = (nM > 0).view(E, 1, 1)
         validJ = (nJ > 0).view(E, 1, 1)
 
-        def gather(enc, idx, valid):    # enc [E,N,enc], idx [E,A,S] -> [E,A,S,enc]; zeros when the market is empty (:542-565)
-            out = torch.gather(enc.unsqueeze(1).expand(-1, idx.shape[1], -1, -1), 2,
-                               idx.unsqueeze(-1).expand(-1, -1, -1, enc.shape[-1]))
-            return out * valid.unsqueeze(-1).to(out.dtype)
+        def gather(enc, idx, valid):    # the agents' stacks of encodings, kept as (table, indices): see IndexedEncodings
+            return IndexedEncodings(enc, idx, valid, flat=True)
+
+        # agents as rows of 2-D matrices: nn.Linear then runs as ONE addmm with the bias in the GEMM epilogue
+        rows = lambda x: x.reshape(-1, x.shape[-1])
 
         # --- persons
         pidxM, pidxJ = draws["pidxM"], draws["pidxJ"]
@@ -346,10 +370,11 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference"):
             labor0 = torch.zeros_like(money)                                      # laborSupplied was just reset (person.cpp:24)
         inv = st["p_inv"].permute(0, 2, 1).to(f32)
         eM, eJ = gather(encM, pidxM, validM), gather(encJ, pidxJ, validJ)
-        p_value = nets.valueNet(eM, eJ, util, money, labor0, inv).squeeze(-1)
-        p_job_p = nets.laborSearchNet(eJ, util, money, labor0, inv)
-        p_good_p = nets.purchaseNet(eM, util, money, labor0, inv)
-        cons = nets.consumptionNet(util, money, labor0, inv)
+        util, money, labor0, inv = rows(util), rows(money), rows(labor0), rows(inv)
+        p_value = nets.valueNet(eM, eJ, util, money, labor0, inv).reshape(E, P)
+        p_job_p = nets.laborSearchNet(eJ, util, money, labor0, inv).reshape(E, P, S)
+        p_good_p = nets.purchaseNet(eM, util, money, labor0, inv).reshape(E, P, S)
+        cons = nets.consumptionNet(util, money, labor0, inv).reshape(E, P, G, 2)
         # --- firms
         fidxM, fidxJ = draws["fidxM"], draws["fidxJ"]
         pf = torch.cat([st["f_prod_tfp"].unsqueeze(2), st["f_prod_share"], st["f_prod_rho"].unsqueeze(2)], dim=2)
@@ -358,11 +383,12 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference"):
         flabor = st["f_labor"].to(f32).unsqueeze(-1)
         finv = st["f_inv"].permute(0, 2, 1).to(f32)
         feM, feJ = gather(encM, fidxM, validM), gather(encJ, fidxJ, validJ)
-        f_value = nets.firmValueNet(feM, feJ, pf, fmoney, flabor, finv).squeeze(-1)
-        f_good_p = nets.firmPurchaseNet(feM, pf, fmoney, flabor, finv)
-        prod = nets.productionNet(pf, fmoney, flabor, finv)
-        offer = nets.offerNet(feM, pf, fmoney, flabor, finv)
-        job = nets.jobOfferNet(feJ, pf, fmoney, flabor, finv)
+        pf, fmoney, flabor, finv = rows(pf), rows(fmoney), rows(flabor), rows(finv)
+        f_value = nets.firmValueNet(feM, feJ, pf, fmoney, flabor, finv).reshape(E, F)
+        f_good_p = nets.firmPurchaseNet(feM, pf, fmoney, flabor, finv).reshape(E, F, S)
+        prod = nets.productionNet(pf, fmoney, flabor, finv).reshape(E, F, G, 2)
+        offer = nets.offerNet(feM, pf, fmoney, flabor, finv).reshape(E, F, G, 4)
+        job = nets.jobOfferNet(feJ, pf, fmoney, flabor, finv).reshape(E, F, 4)
     # --- sampling (fp32)
     detach = sample_grad != "reference"
     p_job_take, lp_job = sample_bernoulli(p_job_p.float(), draws["u_job"])

@@ -299,8 +299,10 @@ def test_non_finite_economies_are_dropped(gold):
     n1, a1 = build(case, cfg)
     loss1 = a1.train_on_episode(good_ep)
     assert abs(loss - loss1) <= 1e-5 * abs(loss1)
+    init = _sub(case, "init/")
     for (k, p), (_, q) in zip(nets.named_parameters(), n1.named_parameters()):
-        torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-8)
+        step = (q.detach() - torch.from_numpy(init[k.replace(".", "/", 1)])).abs().max().item()
+        assert (p.detach() - q.detach()).abs().max().item() <= 2e-3 * step + 1e-7, k   # same bar as the Adam-step checks
     # propagate = the reference's behaviour: NaN loss
     n2, a2 = build(case, cfg)
     a2.nan_policy = "propagate"
