@@ -155,6 +155,7 @@ struct fastace_env {
     // large-economy path (large_economy.cuh)
     bool large_only;          // dims beyond the warp-per-economy kernels: every step takes the large path
     bool have_large;
+    int large_coop_blocks_p, large_coop_blocks_f;   // co-resident CTAs of the two cooperative iteration kernels
     void* large_block;
     fastace::LargeScratch large_sc;
     uint32_t large_rounds_person, large_rounds_firm;   // of the last large step (last economy)
@@ -362,15 +363,14 @@ int fastace_env_device_state(const fastace_env_t* env, fastace_state_t* out_devi
 
 // ---- large-economy path ------------------------------------------------------------------------------------
 struct LargeKernels {
-    void (*person_pass)(const LargeParams);
-    void (*firm_pass)(const LargeParams);
+    void (*iterate_persons)(const LargeParams, int);
     void (*finalize_persons)(const LargeParams);
-    void (*firm_phase_pass)(const LargeParams);
+    void (*iterate_firms)(const LargeParams, int);
     void (*finalize_firms)(const LargeParams);
 };
 template <int G>
 static LargeKernels large_kernels_of() {
-    return {large_person_pass<G>, large_firm_pass<G>, large_finalize_persons<G>, large_firm_phase_pass<G>, large_finalize_firms<G>};
+    return {large_iterate_persons<G>, large_finalize_persons<G>, large_iterate_firms<G>, large_finalize_firms<G>};
 }
 static LargeKernels large_kernels_for_goods(int G) {
     switch (G) {
@@ -404,8 +404,8 @@ static int ensure_large_scratch(fastace_env_t* env) {
         {(void**)&sc.fhist, 4 * F}, {(void**)&sc.fseg, 4 * (F + 1)},
         {(void**)&sc.ff_profit, 8 * F}, {(void**)&sc.ff_money, 8 * F}, {(void**)&sc.ff_last, 8 * F}, {(void**)&sc.ff_inv, 8 * G * F},
         {(void**)&sc.ff_left, 4 * cap}, {(void**)&sc.ff_taken, 4 * cap},
-        {(void**)&sc.post_lots, 4 * cap}, {(void**)&sc.post_jlots, 4 * F}, {(void**)&sc.changed, 4},
-        {(void**)&sc.req_firm, 2 * R}, {(void**)&sc.dirty_person, P}, {(void**)&sc.dirty_firm, F},
+        {(void**)&sc.post_lots, 4 * cap}, {(void**)&sc.post_jlots, 4 * F}, {(void**)&sc.changed, 32},
+        {(void**)&sc.req_firm, 2 * R}, {(void**)&sc.req_pos, 4 * R}, {(void**)&sc.want_sorted, R}, {(void**)&sc.ok_sorted, R}, {(void**)&sc.dirty_person, P}, {(void**)&sc.dirty_firm, F},
         {(void**)&sc.post_base_m, 4 * F}, {(void**)&sc.post_base_j, 4 * F},
     };
     size_t total = 0;
@@ -419,6 +419,16 @@ static int ensure_large_scratch(fastace_env_t* env) {
     FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, need, sc.key_in, sc.key_out, sc.val_in, sc.val_out, n_max > 0 ? n_max : 1, 0, 16));
     sc.cub_bytes = need ? need : 1;
     FASTACE_CUDA_CHECK(cudaMalloc(&sc.cub_temp, sc.cub_bytes));
+    {
+        const LargeKernels lk = large_kernels_for_goods(env->dims.num_goods);
+        int sms = 0, occ_p = 0, occ_f = 0;
+        FASTACE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->device));
+        FASTACE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, (const void*)lk.iterate_persons, kLargeThreads, 0));
+        FASTACE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, (const void*)lk.iterate_firms, kLargeThreads, 0));
+        if (occ_p < 1 || occ_f < 1) { set_error("large-economy iteration kernels do not fit an SM"); return FASTACE_ERR_CUDA; }
+        env->large_coop_blocks_p = sms * occ_p;
+        env->large_coop_blocks_f = sms * occ_f;
+    }
     env->have_large = true;
     return FASTACE_OK;
 }
@@ -461,37 +471,30 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
         env->launches += 2;
         // ---- person phase
         const size_t R = (size_t)2 * S * P;
-        uint32_t rounds = 0;
+        FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed, 0, 32, stream));
         if (R > 0) {
             large_prep_persons<<<blocks(R), T, 0, stream>>>(lp);
             size_t bytes = sc.cub_bytes;
             FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sc.cub_temp, bytes, sc.key_in, sc.key_out, sc.val_in, sc.val_out,
                                                                (int)R, 0, 16, stream));
-            large_scan<<<1, 1024, 0, stream>>>(sc.hist, sc.seg, F);
-            env->launches += 3;
-            int changed = 1;
-            while (changed) {
-                if ((int)rounds >= kMaxRounds) { set_error("large step: person phase did not settle"); return FASTACE_ERR_INVALID; }
-                FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed, 0, sizeof(int), stream));
-                // two rounds per host check: a settled iteration is idempotent, and skipped agents cost nothing
-                for (int k = 0; k < 2; k++) {
-                    lk.person_pass<<<blocks(P), T, 0, stream>>>(lp);
-                    lk.firm_pass<<<blocks((size_t)F * 32), T, 0, stream>>>(lp);
-                }
-                FASTACE_CUDA_CHECK(cudaMemcpyAsync(&changed, sc.changed, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                FASTACE_CUDA_CHECK(cudaStreamSynchronize(stream));
-                env->launches += 4;
-                rounds += 2;
-            }
-        } else {
-            // no requests at all: the firm pass still has to publish every firm's unchanged state
-            large_scan<<<1, 1024, 0, stream>>>(sc.hist, sc.seg, F);
-            lk.firm_pass<<<blocks((size_t)F * 32), T, 0, stream>>>(lp);
             env->launches += 2;
         }
-        env->large_rounds_person = rounds;
+        large_scan<<<1, 1024, 0, stream>>>(sc.hist, sc.seg, F);
+        env->launches += 1;
+        if (R > 0) {
+            large_index_events<<<blocks(R), T, 0, stream>>>(lp);
+            env->launches += 1;
+        }
+        {
+            // requester pass / firm pass rounds until nothing changes: ONE cooperative launch, no host round trip
+            int max_rounds = kMaxRounds;
+            void* args[] = {(void*)&lp, (void*)&max_rounds};
+            const size_t want_blocks = std::max<size_t>(blocks(P), blocks((size_t)F * 32));
+            const int grid = (int)std::min<size_t>(std::max<size_t>(want_blocks, 1), (size_t)env->large_coop_blocks_p);
+            FASTACE_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lk.iterate_persons, dim3(grid), dim3(T), args, 0, stream));
+            env->launches += 1;
+        }
         if (P > 0) {
-            if (R == 0) lk.person_pass<<<blocks(P), T, 0, stream>>>(lp);
             lk.finalize_persons<<<blocks(P), T, 0, stream>>>(lp);
             env->launches += 1;
         }
@@ -503,7 +506,6 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
         }
         // ---- firm phase
         const size_t RF = (size_t)S * F;
-        rounds = 0;
         if (RF > 0) {
             large_prep_firms<<<blocks(RF), T, 0, stream>>>(lp);
             size_t bytes = sc.cub_bytes;
@@ -512,18 +514,13 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
             env->launches += 2;
         }
         large_scan<<<1, 1024, 0, stream>>>(sc.fhist, sc.fseg, F);
-        env->launches += 1;
-        int changed = 1;
-        while (changed) {
-            if ((int)rounds >= kMaxRounds) { set_error("large step: firm phase did not settle"); return FASTACE_ERR_INVALID; }
-            FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed, 0, sizeof(int), stream));
-            lk.firm_phase_pass<<<blocks(F), T, 0, stream>>>(lp);
-            FASTACE_CUDA_CHECK(cudaMemcpyAsync(&changed, sc.changed, sizeof(int), cudaMemcpyDeviceToHost, stream));
-            FASTACE_CUDA_CHECK(cudaStreamSynchronize(stream));
-            env->launches += 1;
-            rounds++;
+        {
+            int max_rounds = kMaxRounds;
+            void* args[] = {(void*)&lp, (void*)&max_rounds};
+            const int grid = (int)std::min<size_t>(std::max<size_t>(blocks(F), 1), (size_t)env->large_coop_blocks_f);
+            FASTACE_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lk.iterate_firms, dim3(grid), dim3(T), args, 0, stream));
         }
-        env->large_rounds_firm = rounds;
+        env->launches += 2;
         if (RF > 0 && lp.sp.out.f_good_ok)
             FASTACE_CUDA_CHECK(cudaMemcpyAsync(lp.sp.out.f_good_ok, sc.fok, RF, cudaMemcpyDeviceToDevice, stream));
         lk.finalize_firms<<<blocks(cap), T, 0, stream>>>(lp);
@@ -805,8 +802,14 @@ int fastace_mlp_residual_tanh_stack(const float* x, float* y, int64_t rows, int 
 
 int fastace_env_large_stats(const fastace_env_t* env, uint32_t* person_rounds, uint32_t* firm_rounds) {
     if (!env) { set_error("null argument"); return FASTACE_ERR_INVALID; }
-    if (person_rounds) *person_rounds = env->large_rounds_person;
-    if (firm_rounds) *firm_rounds = env->large_rounds_firm;
+    int flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (env->have_large) {   // the iteration kernels leave their round counts on the device
+        FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+        FASTACE_CUDA_CHECK(cudaDeviceSynchronize());
+        FASTACE_CUDA_CHECK(cudaMemcpy(flags, env->large_sc.changed, sizeof(flags), cudaMemcpyDeviceToHost));
+    }
+    if (person_rounds) *person_rounds = (uint32_t)flags[3];
+    if (firm_rounds) *firm_rounds = (uint32_t)flags[7];
     return FASTACE_OK;
 }
 

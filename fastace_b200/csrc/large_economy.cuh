@@ -9,20 +9,23 @@
 // parallel:
 //   requester pass  one thread per person: walk the own S job + S goods requests in order, given which of them the
 //                   other side granted  ->  `want` (own-side conditions hold: labour <= 1, money >= price)
-//   firm pass       one thread per firm: walk ALL events at this firm in the reference's order (visiting rank, jobs
-//                   before goods, slot), given `want`  ->  `ok`; this is the segmented, stably sorted event list:
-//                   events keyed by firm, sorted by a radix sort (cub::DeviceRadixSort, the one library primitive
-//                   here) whose input is enumerated in (rank, phase, slot) order
-// iterated until no `ok` flag changes.  By induction over the global event order a fixed point IS the sequential
-// result, and round k finalises every event whose dependency chain crosses agents at most k times; measured 4-7
-// rounds at config D.  Each agent's fp64 money / inventory is updated inside ONE thread in the reference's order, so
-// unlike the warp-per-economy kernel there is no rounding-order caveat: firm money is bit-identical.
+//   firm pass       one warp per firm: ALL events at this firm in the reference's order (visiting rank, jobs before
+//                   goods, slot), given `want`  ->  `ok`; this is the segmented, stably sorted event list: events
+//                   keyed by firm, sorted by a radix sort (cub::DeviceRadixSort, the one library primitive here)
+//                   whose input is enumerated in (rank, phase, slot) order.  Goods events are per-good prefix counts
+//                   of `want` bits; only the firm's money (sales, hires) is walked sequentially.
+// iterated until no `ok` flag changes, inside ONE cooperative launch (grid.sync between the passes).  By induction
+// over the global event order a fixed point IS the sequential result, and round k finalises every event whose
+// dependency chain crosses agents at most k times; measured 8 rounds at config D.  Each agent's fp64 money /
+// inventory is updated in the reference's order, so unlike the warp-per-economy kernel there is no rounding-order
+// caveat: firm money is bit-identical.
 // The firm phase (firms buying from firms, firm.cpp:23-46) is the same iteration over F*S requests, with the rule
 // that an offer is withdrawn once its owner's turn has passed (profitMaxer.cpp:79-81).
 //
 // Preconditions (true for every book the step itself produces): at most one live goods offer per (firm, good) and one
 // job offer per firm; inventories are non-negative.
 #pragma once
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -69,6 +72,8 @@ struct LargeScratch {
     int32_t* post_lots;    // [F*G]
     int32_t* post_jlots;   // [F]
     uint16_t* req_firm;    // [2SP] firm on the other side of the request
+    uint32_t* req_pos;     // [2SP] position of the request in the sorted event list
+    uint8_t *want_sorted, *ok_sorted;   // [2SP] the same flags in event-list order: the firm pass streams them
     uint8_t* dirty_person; // [P]   some `ok` of this person changed since its last requester pass
     uint8_t* dirty_firm;   // [F]   some `want` at this firm changed since its last firm pass
     uint32_t *post_base_m, *post_base_j;   // [F] by visiting rank: first new-book slot of that firm
@@ -156,42 +161,84 @@ __global__ void large_scan(const uint32_t* hist, uint32_t* seg, int n) {
     if (threadIdx.x == blockDim.x - 1) seg[n] = part[blockDim.x - 1];
 }
 
+// event-list positions of the requests and the flags in event-list order (after the sort): the firm pass then reads
+// its segment as contiguous bytes instead of gathering one byte per event through the request id
+__global__ void large_index_events(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const size_t n = (size_t)2 * p.S * p.P;
+    const size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    const bool valid = lp.sc.key_out[pos] != 0xFFFFu;
+    lp.sc.want_sorted[pos] = 0;
+    lp.sc.ok_sorted[pos] = valid;
+    if (valid) lp.sc.req_pos[lp.sc.val_out[pos] & kReqMask] = (uint32_t)pos;
+}
+
 // requester pass (Person::time_step person.cpp:19-33; respond_to_jobOffer :36-54; respond_to_offer agent.cpp:99-116).
-// Persons none of whose requests changed outcome since their last pass are skipped (their results stand).
+// Persons none of whose requests changed outcome since their last pass are skipped (their results stand).  All
+// gathers of a chain are issued before the chain is walked, so the walk itself runs on registers.
 template <int G>
-__global__ void large_person_pass(const LargeParams lp) {
+__device__ __forceinline__ void large_person_body(const LargeParams& lp, int pid) {
     const StepParams& p = lp.sp;
     const int P = p.P, S = p.S;
-    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pid >= P) return;
     if (!lp.sc.dirty_person[pid]) return;
     lp.sc.dirty_person[pid] = 0;
     double money = p.st.p_money[pid];
     double labor = 0.0;                                                    // person.cpp:24
     int hires = 0;
-    for (int i = 0; i < S; i++) {
-        const size_t req = (size_t)i * P + pid;
-        const uint32_t n = lp.sc.req_n[req];
-        if (n == kNoEntry) continue;
-        const uint8_t w = labor + kLaborPerOffer <= 1;                     // person.cpp:39
-        if (lp.sc.want[req] != w) { lp.sc.want[req] = w; lp.sc.dirty_firm[lp.sc.req_firm[req]] = 1; }
-        if (w && lp.sc.ok[req]) { labor += kLaborPerOffer; money += p.st.j_wage[n]; hires++; }   // person.cpp:48-49
-    }
     uint8_t bought[G];
 #pragma unroll
     for (int g = 0; g < G; g++) bought[g] = 0;
-    for (int i = 0; i < S; i++) {
-        const size_t req = (size_t)(S + i) * P + pid;
-        const uint32_t n = lp.sc.req_n[req];
-        if (n == kNoEntry) continue;
-        const double price = p.st.m_price[n];
-        const uint8_t w = money >= price;                                  // agent.cpp:102
-        if (lp.sc.want[req] != w) { lp.sc.want[req] = w; lp.sc.dirty_firm[lp.sc.req_firm[req]] = 1; }
-        if (w && lp.sc.ok[req]) {
-            money -= price;                                                // agent.cpp:105-111
-            const int good = p.st.m_good[n];
 #pragma unroll
-            for (int g = 0; g < G; g++) if (g == good) bought[g]++;
+    for (int phase = 0; phase < 2; phase++) {
+        uint32_t n[kMaxStack];
+        double val[kMaxStack];        // wage (jobs) / price (goods) of the entry the slot refers to
+        int good[kMaxStack];
+        uint32_t okbits = 0, wantbits = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxStack; i++) {
+            n[i] = kNoEntry;
+            if (i < S) {
+                const size_t req = (size_t)(phase * S + i) * P + pid;
+                n[i] = lp.sc.req_n[req];
+                okbits |= (uint32_t)(lp.sc.ok[req] != 0) << i;
+                wantbits |= (uint32_t)(lp.sc.want[req] != 0) << i;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxStack; i++) {
+            val[i] = 0.0; good[i] = 0;
+            if (n[i] != kNoEntry) {
+                if (phase == 0) val[i] = p.st.j_wage[n[i]];
+                else { val[i] = p.st.m_price[n[i]]; good[i] = p.st.m_good[n[i]]; }
+            }
+        }
+        uint32_t neww = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxStack; i++) {
+            if (n[i] == kNoEntry) continue;
+            if (phase == 0) {
+                const bool w = labor + kLaborPerOffer <= 1;                // person.cpp:39
+                neww |= (uint32_t)w << i;
+                if (w && ((okbits >> i) & 1u)) { labor += kLaborPerOffer; money += val[i]; hires++; }   // person.cpp:48-49
+            } else {
+                const bool w = money >= val[i];                            // agent.cpp:102
+                neww |= (uint32_t)w << i;
+                if (w && ((okbits >> i) & 1u)) {
+                    money -= val[i];                                       // agent.cpp:105-111
+#pragma unroll
+                    for (int g = 0; g < G; g++) if (g == good[i]) bought[g]++;
+                }
+            }
+        }
+        uint32_t diff = neww ^ wantbits;
+        while (diff) {
+            const int i = __ffs(diff) - 1;
+            diff &= diff - 1;
+            const size_t req = (size_t)(phase * S + i) * P + pid;
+            lp.sc.want[req] = (neww >> i) & 1u;
+            lp.sc.want_sorted[lp.sc.req_pos[req]] = (neww >> i) & 1u;
+            lp.sc.dirty_firm[lp.sc.req_firm[req]] = 1;
         }
     }
     lp.sc.pm_money[pid] = money;
@@ -211,102 +258,147 @@ __device__ __forceinline__ bool large_short(const double (&inv)[G], int good) {
 
 // firm pass of the person phase: every event at firm f in the reference's order
 // (review_jobOffer_response firm.cpp:56-90, accept :106-113; review_offer_response agent.cpp:118-150, accept :152-161).
-// One warp per firm: the lanes fetch 32 events (sorted value + the requester's `want`) at a time, lane 0 walks them
-// with the firm's per-good state in shared memory, the lanes write back the flags that changed.  Firms none of whose
-// events changed `want` since their last pass are skipped.
+// One warp per firm, 32 events (sorted value + the requester's `want`) per batch:
+//   * goods events never look at the firm's money: a made request succeeds iff fewer than
+//     cap_g = min(amountLeft, units the inventory covers) made requests for the same good came before it — a prefix
+//     count of `want` bits per good (ballot + popc), no serial walk; the counters after the pass follow in closed form;
+//   * the firm's money is the one sequential quantity (sales raise it, hires lower it, a hire needs money >= wage):
+//     the warp walks, uniformly in all lanes, only the successful sales and the job events of the batch, in order,
+//     adding in fp64 exactly as the reference does.
+// Requests their requester does not currently make are answered hypothetically (no side effects).  Firms none of
+// whose events changed `want` since their last pass are skipped.
 template <int G>
-__global__ void __launch_bounds__(kLargeThreads) large_firm_pass(const LargeParams lp) {
-    constexpr int WPB = kLargeThreads / 32;
-    __shared__ double s_inv[WPB][G], s_price[WPB][G];
-    __shared__ uint32_t s_left[WPB][G], s_taken[WPB][G];
+__device__ __forceinline__ bool large_firm_body(const LargeParams& lp, int f, int lane) {
     const StepParams& p = lp.sp;
     const int F = p.F, P = p.P;
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = blockIdx.x * WPB + wib;
-    if (f >= F) return;
-    if (!lp.sc.dirty_firm[f]) return;
+    if (!lp.sc.dirty_firm[f]) return false;
     __syncwarp();
     if (lane == 0) lp.sc.dirty_firm[f] = 0;
-    if (lane < G) {
-        s_inv[wib][lane] = p.st.f_inv[(size_t)lane * F + f];
-        const int n = lp.sc.own_offer[f * G + lane];
-        s_left[wib][lane] = n >= 0 ? p.st.m_left[n] : 0u;
-        s_taken[wib][lane] = n >= 0 ? p.st.m_taken[n] : 0u;
-        s_price[wib][lane] = n >= 0 ? p.st.m_price[n] : 0.0;
+    // per-good state, uniform in all lanes (static indices: the loops over g are unrolled)
+    double inv[G];
+    uint32_t left[G], taken[G], cap[G], made[G];
+    bool anyneg = false;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        inv[g] = p.st.f_inv[(size_t)g * F + f];
+        const int n = lp.sc.own_offer[f * G + g];
+        left[g] = n >= 0 ? p.st.m_left[n] : 0u;
+        taken[g] = n >= 0 ? p.st.m_taken[n] : 0u;
+        made[g] = 0;
     }
-    __syncwarp();
+    // lane g keeps the price of good g for the money walk
+    double myprice = 0.0;
+    if (lane < G) { const int n = lp.sc.own_offer[f * G + lane]; myprice = n >= 0 ? p.st.m_price[n] : 0.0; }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        // a good whose inventory is negative makes every sale of ANOTHER good short (agent.cpp:140 compares all
+        // goods); inventories only fall by sold units here, so that set is fixed for the pass
+        bool other_neg = false;
+#pragma unroll
+        for (int h = 0; h < G; h++) if (h != g) other_neg |= inv[h] < 0.0;
+        cap[g] = other_neg ? 0u : min(left[g], unit_sales_possible(inv[g]));
+        anyneg |= other_neg;
+    }
+    (void)anyneg;
     double money = p.st.f_money[f], labor = p.st.f_labor[f];
     const int nj = lp.sc.own_job[f];
     uint32_t jleft = 0, jtaken = 0;
     double wage = 0.0;
     if (nj >= 0) { jleft = p.st.j_left[nj]; jtaken = p.st.j_taken[nj]; wage = p.st.j_wage[nj]; }
-    // a good whose inventory is negative makes every sale of ANOTHER good short (agent.cpp:140 compares all goods);
-    // inventories only fall by sold units here, so that set is fixed for the pass
-    uint32_t negmask = 0;
-    for (int g = 0; g < G; g++) negmask |= (s_inv[wib][g] < 0.0 ? 1u : 0u) << g;
+    const uint32_t lt = (1u << lane) - 1u;
     bool changed = false;
     const uint32_t lo = lp.sc.seg[f], hi = lp.sc.seg[f + 1];
+    // the next batch's three loads are in flight while the current batch is walked
+    uint32_t nv = 0u; uint8_t nw = 0, nold = 0;
+    if (lo + lane < hi) { nv = lp.sc.val_out[lo + lane]; nw = lp.sc.want_sorted[lo + lane]; nold = lp.sc.ok_sorted[lo + lane]; }
     for (uint32_t base = lo; base < hi; base += 32) {
         const uint32_t pos = base + lane;
         const bool live = pos < hi;
-        const uint32_t v = live ? lp.sc.val_out[pos] : 0u;
+        const uint32_t v = nv;
+        const uint8_t myw = nw, old = nold;
+        if (pos + 32 < hi) { nv = lp.sc.val_out[pos + 32]; nw = lp.sc.want_sorted[pos + 32]; nold = lp.sc.ok_sorted[pos + 32]; }
         const uint32_t req = v & kReqMask;
-        const uint32_t wmask = __ballot_sync(0xffffffffu, live && lp.sc.want[req]);
-        const uint8_t old = live ? lp.sc.ok[req] : 0;
-        const int n = min(32u, hi - base);
-        uint32_t okmask = 0;
-        for (int k = 0; k < n; k++) {
-            const uint32_t type = __shfl_sync(0xffffffffu, v, k) >> 27;
-            if (lane != 0) continue;
-            // A request its requester does not (currently) make is answered hypothetically, without side effects:
-            // should it be made in a later round, the requester already knows the answer.  This collapses the
-            // requester's own chain (slot i is only made once two earlier jobs failed, ...) into one round.
-            const bool made = (wmask >> k) & 1u;
-            if (type == 0) {
-                if (jleft > 0) {                                           // firm.cpp:64
-                    if (money < wage) { if (made) jleft = 0; }             // firm.cpp:80-84
-                    else {
-                        okmask |= 1u << k;
-                        if (made) { money -= wage; labor += kLaborPerOffer; jleft--; jtaken++; }   // firm.cpp:108-111
-                    }
-                }
-            } else {
-                const int g = (int)type - 1;
-                const uint32_t left = s_left[wib][g];
-                if (left > 0) {                                            // agent.cpp:124
-                    const double iv = s_inv[wib][g];
-                    if (iv < kAmountPerOffer || (negmask & ~(1u << g))) { if (made) s_left[wib][g] = 0; }   // agent.cpp:140-143
-                    else {                                                 // agent.cpp:152-161
-                        okmask |= 1u << k;
-                        if (made) {
-                            money += s_price[wib][g];
-                            s_inv[wib][g] = iv - kAmountPerOffer;
-                            s_left[wib][g] = left - 1;
-                            s_taken[wib][g]++;
-                        }
-                    }
+        const uint32_t type = live ? (v >> 27) : 0xFFu;
+        const uint32_t wmask = __ballot_sync(0xffffffffu, live && myw);
+        uint32_t okmask = 0, salemask = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, type == (uint32_t)(g + 1));
+            if (m == 0) continue;
+            const uint32_t wm = m & wmask;
+            const uint32_t before = made[g] + __popc(wm & lt);             // made requests for this good ahead of mine
+            const bool avail = before < cap[g];                            // agent.cpp:124, 140
+            const uint32_t am = __ballot_sync(0xffffffffu, avail) & m;
+            okmask |= am;
+            salemask |= am & wm;
+            made[g] += __popc(wm);
+        }
+        // the money walk: successful sales and job events of the batch, in order
+        const uint32_t jobmask = __ballot_sync(0xffffffffu, type == 0u);
+        uint32_t walk = salemask | jobmask;
+        while (walk) {
+            const int k = __ffs(walk) - 1;
+            walk &= walk - 1;
+            const uint32_t tk = __shfl_sync(0xffffffffu, type, k);
+            if (tk != 0u) {
+                money += __shfl_sync(0xffffffffu, myprice, (int)tk - 1);   // agent.cpp:153
+            } else if (jleft > 0) {                                        // firm.cpp:64
+                const bool is_made = (wmask >> k) & 1u;
+                if (money < wage) { if (is_made) jleft = 0; }              // firm.cpp:80-84
+                else {
+                    okmask |= 1u << k;
+                    if (is_made) { money -= wage; labor += kLaborPerOffer; jleft--; jtaken++; }   // firm.cpp:108-111
                 }
             }
         }
-        okmask = __shfl_sync(0xffffffffu, okmask, 0);
         if (live) {
             const uint8_t o = (okmask >> lane) & 1u;
-            if (o != old) { lp.sc.ok[req] = o; lp.sc.dirty_person[req % (uint32_t)P] = 1; changed = true; }
+            if (o != old) { lp.sc.ok_sorted[pos] = o; lp.sc.ok[req] = o; lp.sc.dirty_person[req % (uint32_t)P] = 1; changed = true; }
         }
     }
-    __syncwarp();
     if (lane == 0) {
         lp.sc.fm_money[f] = money;
         lp.sc.fm_labor[f] = labor;
         lp.sc.fm_jleft[f] = jleft;
         lp.sc.fm_jtaken[f] = jtaken;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            // closed form of the walk: the first cap[g] made requests are sales; one more made request finds the offer
+            // exhausted (amountLeft 0) or the inventory short (amountLeft <- 0, agent.cpp:143)
+            const uint32_t sold = min(made[g], cap[g]);
+            lp.sc.fm_inv[(size_t)g * F + f] = inv[g] - (double)sold;        // sold exact subtractions of 1.0
+            lp.sc.fm_left[f * G + g] = made[g] > cap[g] ? 0u : left[g] - sold;
+            lp.sc.fm_taken[f * G + g] = taken[g] + sold;
+        }
     }
-    if (lane < G) {
-        lp.sc.fm_inv[(size_t)lane * F + f] = s_inv[wib][lane];
-        lp.sc.fm_left[f * G + lane] = s_left[wib][lane];
-        lp.sc.fm_taken[f * G + lane] = s_taken[wib][lane];
+    return changed;
+}
+
+// The whole person-phase iteration as ONE cooperative launch: requester pass, grid sync, firm pass, grid sync, until a
+// round changes no flag.  No host round trip, no launch gaps between rounds.  flags: sc.changed[0..2] rotate (a flag
+// is cleared two rounds after it was last read), sc.changed[3] receives the number of rounds.
+template <int G>
+__global__ void __launch_bounds__(kLargeThreads, 3) large_iterate_persons(const LargeParams lp, int max_rounds) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const int warp = tid >> 5, nwarps = nthreads >> 5, lane = threadIdx.x & 31;
+    const int P = lp.sp.P, F = lp.sp.F;
+    volatile int* flags = lp.sc.changed;
+    int round = 0;
+    while (round < max_rounds) {
+        if (tid == 0) flags[(round + 1) % 3] = 0;
+        for (int pid = tid; pid < P; pid += nthreads) large_person_body<G>(lp, pid);
+        grid.sync();
+        bool ch = false;
+        for (int f = warp; f < F; f += nwarps) ch |= large_firm_body<G>(lp, f, lane);
+        if (ch) flags[round % 3] = 1;
+        grid.sync();
+        const int again = flags[round % 3];
+        round++;
+        if (!again) break;
     }
-    if (changed) *lp.sc.changed = 1;
+    if (tid == 0) flags[3] = round;
 }
 
 // consume_goods + utility (utilMaxer.cpp:88-92, 54-62; neuralPersonDecisionMaker.cpp:93-111), persons' new state
@@ -387,11 +479,9 @@ __global__ void large_prep_firms(const LargeParams lp) {
 // come earlier in the visiting order, check_my_offers (agent.cpp:54-97), profit record
 // (neuralFirmDecisionMaker.cpp:65-74), own purchases (profitMaxer.cpp:102-111; self-purchase is possible).
 template <int G>
-__global__ void large_firm_phase_pass(const LargeParams lp) {
+__device__ __forceinline__ bool large_firm_phase_body(const LargeParams& lp, int f) {
     const StepParams& p = lp.sp;
     const int F = p.F, S = p.S;
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
     const int qf = lp.sc.rank_f[f];
     double money = lp.sc.fm_money[f];
     double inv[G], price[G];
@@ -476,7 +566,29 @@ __global__ void large_firm_phase_pass(const LargeParams lp) {
         lp.sc.ff_left[f * G + g] = left[g];
         lp.sc.ff_taken[f * G + g] = taken[g];
     }
-    if (changed) *lp.sc.changed = 1;
+    return changed;
+}
+
+// the firm-phase iteration as one cooperative launch (flags as in large_iterate_persons; rounds -> sc.changed[7])
+template <int G>
+__global__ void __launch_bounds__(kLargeThreads) large_iterate_firms(const LargeParams lp, int max_rounds) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const int F = lp.sp.F;
+    volatile int* flags = lp.sc.changed + 4;
+    int round = 0;
+    while (round < max_rounds) {
+        if (tid == 0) flags[(round + 1) % 3] = 0;
+        bool ch = false;
+        for (int f = tid; f < F; f += nthreads) ch |= large_firm_phase_body<G>(lp, f);
+        if (ch) flags[round % 3] = 1;
+        grid.sync();
+        const int again = flags[round % 3];
+        round++;
+        if (!again) break;
+    }
+    if (tid == 0) flags[3] = round;
 }
 
 // produce (profitMaxer.cpp:68-72), sell_goods / search_for_laborers decode (neuralFirmDecisionMaker.cpp:111-180);

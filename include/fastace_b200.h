@@ -242,8 +242,8 @@ typedef struct fastace_step_out {
 /* Take the large-economy path (csrc/large_economy.cuh: request/firm fixed-point iteration over stably sorted
  * per-firm event lists, books in global memory) even when the economy fits the warp-per-economy kernels.  Envs whose
  * dims exceed those kernels (F*G > 254, P > 65535, or books beyond shared memory — BASELINE config D) always take
- * it.  Every fp64 update is made in the reference's order (no rounding-order caveat); the call synchronises the
- * stream once per iteration round. */
+ * it.  Every fp64 update is made in the reference's order (no rounding-order caveat); the iteration runs in
+ * cooperative kernels, so the call stays asynchronous on its stream. */
 #define FASTACE_STEP_LARGE   16u
 
 typedef struct fastace_env fastace_env_t;
