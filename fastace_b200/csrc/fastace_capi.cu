@@ -158,7 +158,6 @@ struct fastace_env {
     int large_coop_blocks_p, large_coop_blocks_f;   // co-resident CTAs of the two cooperative iteration kernels
     void* large_block;
     fastace::LargeScratch large_sc;
-    uint32_t large_rounds_person, large_rounds_firm;   // of the last large step (last economy)
 };
 
 #define FASTACE_CUDA_CHECK(expr)                                                              \

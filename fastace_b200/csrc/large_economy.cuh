@@ -277,7 +277,6 @@ __device__ __forceinline__ bool large_firm_body(const LargeParams& lp, int f, in
     // per-good state, uniform in all lanes (static indices: the loops over g are unrolled)
     double inv[G];
     uint32_t left[G], taken[G], cap[G], made[G];
-    bool anyneg = false;
 #pragma unroll
     for (int g = 0; g < G; g++) {
         inv[g] = p.st.f_inv[(size_t)g * F + f];
@@ -297,9 +296,7 @@ __device__ __forceinline__ bool large_firm_body(const LargeParams& lp, int f, in
 #pragma unroll
         for (int h = 0; h < G; h++) if (h != g) other_neg |= inv[h] < 0.0;
         cap[g] = other_neg ? 0u : min(left[g], unit_sales_possible(inv[g]));
-        anyneg |= other_neg;
     }
-    (void)anyneg;
     double money = p.st.f_money[f], labor = p.st.f_labor[f];
     const int nj = lp.sc.own_job[f];
     uint32_t jleft = 0, jtaken = 0;
