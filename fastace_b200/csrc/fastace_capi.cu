@@ -754,21 +754,33 @@ static int mlp_tiles_for(int hidden) {
 template <int NT>
 static int launch_mlp_stack(const MlpParams& mp, cudaStream_t stream) {
     using T = MlpTile<NT>;
-    static bool configured[64] = {};
+    static size_t configured[64] = {};
     int dev = 0;
     FASTACE_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 64 && !configured[dev]) {
-        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)mlp_residual_stack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
-        configured[dev] = true;
+    size_t smem = T::SMEM + T::LAST_BYTES;
+    if (mp.x0) smem += (size_t)T::NP * mp.K0P * 2 + T::B_BYTES;
+    if (dev < 64 && configured[dev] < smem) {
+        FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)mlp_residual_stack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
     }
     int sms = 0;
     FASTACE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long rows_per_block = (long long)kMlpWarps * 16;
     const long long nblocks = (mp.rows + rows_per_block - 1) / rows_per_block;
     const int grid = (int)std::min<long long>(nblocks, (long long)sms * kMlpBlocksPerSM);   // persistent
-    mlp_residual_stack_kernel<NT><<<grid, kMlpThreads, T::SMEM, stream>>>(mp);
+    mlp_residual_stack_kernel<NT><<<grid, kMlpThreads, smem, stream>>>(mp);
     FASTACE_CUDA_CHECK(cudaGetLastError());
     return FASTACE_OK;
+}
+
+static int dispatch_mlp(const MlpParams& mp, int nt, cudaStream_t stream) {
+    switch (nt) {
+        case 2: return launch_mlp_stack<2>(mp, stream);
+        case 4: return launch_mlp_stack<4>(mp, stream);
+        case 8: return launch_mlp_stack<8>(mp, stream);
+        case 13: return launch_mlp_stack<13>(mp, stream);
+        default: return launch_mlp_stack<16>(mp, stream);
+    }
 }
 
 extern "C" {
@@ -788,15 +800,29 @@ int fastace_mlp_residual_tanh_stack(const float* x, float* y, int64_t rows, int 
     if (hidden < 2 || (hidden & 1) || nt == 0) { set_error("fused stack needs an even hidden size in [2, 128]"); return FASTACE_ERR_INVALID; }
     if (rows == 0) return FASTACE_OK;
     MlpParams mp;
+    std::memset(&mp, 0, sizeof(mp));
     mp.x = x; mp.y = y; mp.rows = rows; mp.H = hidden; mp.L = layers; mp.w = w_bf16; mp.bias = bias;
-    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-    switch (nt) {
-        case 2: return launch_mlp_stack<2>(mp, stream);
-        case 4: return launch_mlp_stack<4>(mp, stream);
-        case 8: return launch_mlp_stack<8>(mp, stream);
-        case 13: return launch_mlp_stack<13>(mp, stream);
-        default: return launch_mlp_stack<16>(mp, stream);
+    return dispatch_mlp(mp, nt, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int fastace_mlp_forward(const fastace_mlp_desc_t* d, void* cuda_stream) {
+    if (!d) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    const int nt = mlp_tiles_for(d->hidden);
+    if (d->hidden < 2 || (d->hidden & 1) || nt == 0) { set_error("fused stack needs an even hidden size in [2, 128]"); return FASTACE_ERR_INVALID; }
+    if (d->rows < 0 || d->layers < 0 || (d->layers > 0 && (!d->w_bf16 || !d->bias))) { set_error("bad stack description"); return FASTACE_ERR_INVALID; }
+    if (!d->x0 && !d->x) { set_error("no input"); return FASTACE_ERR_INVALID; }
+    if (d->x0 && (d->in_features < 1 || d->in_features > 128 || !d->w0_bf16 || !d->b0)) { set_error("first layer: 1..128 inputs"); return FASTACE_ERR_INVALID; }
+    if (d->out && (d->out_features < 1 || d->out_features > 16 || !d->wl_bf16 || !d->bl || d->activation < 0 || d->activation > 2)) {
+        set_error("last layer: 1..16 outputs, activation 0..2"); return FASTACE_ERR_INVALID;
     }
+    if (!d->y && !d->out) { set_error("no output"); return FASTACE_ERR_INVALID; }
+    if (d->rows == 0) return FASTACE_OK;
+    MlpParams mp;
+    std::memset(&mp, 0, sizeof(mp));
+    mp.x = d->x; mp.y = d->y; mp.rows = d->rows; mp.H = d->hidden; mp.L = d->layers; mp.w = d->w_bf16; mp.bias = d->bias;
+    if (d->x0) { mp.x0 = d->x0; mp.K0 = d->in_features; mp.K0P = (d->in_features + 15) / 16 * 16 + 8; mp.w0 = d->w0_bf16; mp.b0 = d->b0; }
+    if (d->out) { mp.out = d->out; mp.NOUT = d->out_features; mp.act = d->activation; mp.wl = d->wl_bf16; mp.bl = d->bl; }
+    return dispatch_mlp(mp, nt, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int fastace_env_large_stats(const fastace_env_t* env, uint32_t* person_rounds, uint32_t* firm_rounds) {

@@ -42,6 +42,21 @@ def _residual_stack(x, layers):
     return x
 
 
+def _body(x, first, layers, last, activation=None):
+    """act(last(residual stack(tanh(first(x)))))  — one net body; the fused path runs it as a single kernel"""
+    if _FUSED and x.is_cuda and not torch.is_grad_enabled():
+        from . import fused_mlp
+        if fused_mlp.supports(first, layers, last, x):
+            return fused_mlp.net_forward(x, first, layers, last, activation)
+    if first is not None:
+        x = torch.tanh(first(x))
+    x = _residual_stack(x, layers)
+    if last is None:
+        return x
+    x = last(x)
+    return torch.sigmoid(x) if activation == "sigmoid" else torch.tanh(x) if activation == "tanh" else x
+
+
 class _Hidden(nn.Module):
     """registers `hidden0..hiddenN-1` (or another prefix) as direct children, like the reference"""
 
@@ -66,9 +81,7 @@ class OfferEncoder(_Hidden):
         self.apply(_xavier)
 
     def forward(self, x):
-        x = torch.tanh(self.dimReduce(x))
-        x = _residual_stack(x, self._hidden)
-        return torch.tanh(self.last(x))
+        return _body(x, self.dimReduce, self._hidden, self.last, "tanh")
 
 
 class IndexedEncodings:
@@ -114,9 +127,7 @@ class PurchaseNet(_Hidden):
 
     def forward(self, offerEncodings, utilParams, budget, labor, inventory):
         x = _head_features(self.flatten, offerEncodings, utilParams, budget, labor, inventory)
-        x = torch.tanh(self._hidden[0](x))
-        x = _residual_stack(x, self._hidden[1:])
-        return torch.sigmoid(self.last(x))
+        return _body(x, self._hidden[0], self._hidden[1:], self.last, "sigmoid")
 
 
 class ConsumptionNet(_Hidden):
@@ -131,9 +142,8 @@ class ConsumptionNet(_Hidden):
         self.apply(_xavier)
 
     def forward(self, utilParams, money, labor, inventory):
-        x = torch.tanh(self.first(torch.cat([utilParams, money, labor, inventory], dim=-1)))
-        x = _residual_stack(x, self._hidden)
-        return self.last(x).reshape(*x.shape[:-1], self.numGoods, 2)
+        x = torch.cat([utilParams, money, labor, inventory], dim=-1)
+        return _body(x, self.first, self._hidden, self.last).reshape(*x.shape[:-1], self.numGoods, 2)
 
 
 class OfferNet(_Hidden):
@@ -164,12 +174,9 @@ class OfferNet(_Hidden):
 
     def forward(self, offerEncodings, utilParams, money, labor, inventory):
         x = _head_features(self.flatten, offerEncodings, utilParams, money, labor, inventory)
-        x = torch.tanh(self._first[0](x))
-        x = _residual_stack(x, self._first[1:])
-        xa = _residual_stack(x, self._a)
-        xb = _residual_stack(x, self._b)
-        xa = self.last_a(xa).reshape(*x.shape[:-1], self.numGoods, 2)
-        xb = self.last_b(xb).reshape(*x.shape[:-1], self.numGoods, 2)
+        x = _body(x, self._first[0], self._first[1:], None)
+        xa = _body(x, None, self._a, self.last_a).reshape(*x.shape[:-1], self.numGoods, 2)
+        xb = _body(x, None, self._b, self.last_b).reshape(*x.shape[:-1], self.numGoods, 2)
         return torch.cat([xa, xb], dim=-1)
 
 
@@ -189,9 +196,7 @@ class JobOfferNet(_Hidden):
 
     def forward(self, offerEncodings, utilParams, money, labor, inventory):
         x = _head_features(self.flatten, offerEncodings, utilParams, money, labor, inventory)
-        x = torch.tanh(self._hidden[0](x))
-        x = _residual_stack(x, self._hidden[1:])
-        return self.last(x)
+        return _body(x, self._hidden[0], self._hidden[1:], self.last)
 
 
 class ValueNet(_Hidden):
@@ -213,9 +218,7 @@ class ValueNet(_Hidden):
         ox = torch.tanh(_flat(self.offerFlatten, offerEncodings))
         jx = torch.tanh(_flat(self.jobOfferFlatten, jobOfferEncodings))
         x = torch.cat([ox, jx, utilParams, money, labor, inventory], dim=-1)
-        x = torch.tanh(self._hidden[0](x))
-        x = _residual_stack(x, self._hidden[1:])
-        return self.last(x)
+        return _body(x, self._hidden[0], self._hidden[1:], self.last)
 
 
 NET_NAMES = ["offerEncoder", "jobOfferEncoder", "purchaseNet", "firmPurchaseNet", "laborSearchNet", "consumptionNet",

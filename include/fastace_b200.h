@@ -315,6 +315,20 @@ int fastace_env_large_stats(const fastace_env_t* env, uint32_t* person_rounds, u
 int fastace_mlp_stack_layout(int hidden, int* padded_out, int* padded_in);
 int fastace_mlp_residual_tanh_stack(const float* x, float* y, int64_t rows, int hidden, int layers,
                                     const uint16_t* w_bf16, const float* bias, void* cuda_stream);
+/* A whole decision-net body in the same kernel: optional first layer  h = tanh(x0 W0^T + b0)  (in_features <= 128),
+ * `layers` residual tanh layers (may be 0), optional last layer  out = act(h Wl^T + bl)  (out_features <= 16,
+ * activation 0 none / 1 sigmoid / 2 tanh).  Give x0 or x (the [rows][hidden] stack input); give y (the [rows][hidden]
+ * stream after the stack) and/or out.  w0_bf16 is [padded_out][16*ceil(in_features/16)+8], wl_bf16 [16][padded_in],
+ * b0 [padded_out], bl [16], all zero-padded. */
+typedef struct fastace_mlp_desc {
+    int64_t rows;
+    int32_t hidden, layers;
+    const float* x;  float* y;
+    const uint16_t* w_bf16;  const float* bias;
+    const float* x0;  int32_t in_features;  const uint16_t* w0_bf16;  const float* b0;
+    float* out;  int32_t out_features, activation;  const uint16_t* wl_bf16;  const float* bl;
+} fastace_mlp_desc_t;
+int fastace_mlp_forward(const fastace_mlp_desc_t* desc, void* cuda_stream);
 
 /* ---- legacy entry points of libpybindings.so (src/pybindings.h:8-28) ------------------ */
 /* Byte-identical layouts of neural::CustomScenarioParams (344 B) and
