@@ -9,9 +9,9 @@ loss is NaN (or stops with "Training failed before first checkpoint"), prints th
 `updateEveryNEpisodes`.  What differs, by construction: every "episode" is `numEconomies` economies stepped at once on
 the GPU (the reference steps one), so an episode loss is the mean over those economies.
 
-Checkpoints: `<saveDir>/<net>.pt` for the reference's eleven names (decisionNetHandler.cpp:726-757).  Files written
-here are torch state_dicts with the reference's parameter names; files written by the reference's torch::save (a
-TorchScript archive) are read through torch.jit.load."""
+Checkpoints: `<saveDir>/<net>.pt` for the reference's eleven names (decisionNetHandler.cpp:726-757).  save_models
+writes torch state_dicts with the reference's parameter names; save_models_reference_format writes the TorchScript
+archives the reference's torch::load reads; load_models reads either (the reference's own torch::save files included)."""
 import math
 import os
 
@@ -30,13 +30,41 @@ def save_models(nets, saveDir=DEFAULT_SAVE_DIR):
         torch.save({k: v.detach().cpu() for k, v in nets.net(name).state_dict().items()}, os.path.join(saveDir, name + ".pt"))
 
 
+class _ParameterTree(torch.nn.Module):
+    """parameter-only mirror of a module tree (same child and parameter names): what torch::load reads by name"""
+
+    def __init__(self):
+        super().__init__()
+
+
+def _mirror(module):
+    tree = _ParameterTree()
+    for n, p in module.named_parameters(recurse=False):
+        tree.register_parameter(n, torch.nn.Parameter(p.detach().cpu().clone(), requires_grad=False))
+    for n, child in module.named_children():
+        tree.add_module(n, _mirror(child))
+    return tree
+
+
+def save_models_reference_format(nets, saveDir=DEFAULT_SAVE_DIR):
+    """The eleven files as the reference's own torch::save writes them (decisionNetHandler.cpp:726-738): a TorchScript
+    archive per net whose attribute tree carries the parameters under the reference's names, so that the reference's
+    DecisionNetHandler::load_models (torch::load, :745-757) reads them."""
+    os.makedirs(saveDir, exist_ok=True)
+    for name in policy.NET_NAMES:
+        torch.jit.save(torch.jit.script(_mirror(nets.net(name))), os.path.join(saveDir, name + ".pt"))
+
+
 def load_models(nets, saveDir=DEFAULT_SAVE_DIR):
     for name in policy.NET_NAMES:
         path = os.path.join(saveDir, name + ".pt")
-        try:
+        import zipfile
+        with zipfile.ZipFile(path) as z:
+            scripted = any(n.endswith("constants.pkl") or "/code/" in n for n in z.namelist())
+        if scripted:      # the reference's torch::save (or save_models_reference_format): a TorchScript archive
+            sd = {k: v.detach() for k, v in torch.jit.load(path, map_location="cpu").named_parameters()}
+        else:
             sd = torch.load(path, map_location="cpu", weights_only=True)
-        except Exception:
-            sd = {k: v.detach() for k, v in torch.jit.load(path, map_location="cpu").named_parameters()}   # reference's torch::save
         own = dict(nets.net(name).named_parameters())
         with torch.no_grad():
             for k, v in sd.items():

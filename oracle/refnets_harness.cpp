@@ -83,6 +83,28 @@ int refnets_param_info(RefNets* r, int i, char* name, int name_cap, int64_t* sha
 }
 void refnets_param_data(RefNets* r, int i, float* dst) { torch::NoGradGuard g; out(r->flat[i].second, dst); }
 
+// checkpoint files as DecisionNetHandler::save_models / load_models write and read them
+// (torch::save / torch::load of one module, decisionNetHandler.cpp:726-757); net = index into `all`
+int refnets_save(RefNets* r, int net, const char* path) {
+    try {
+        auto* m = r->all[net].second;
+        torch::serialize::OutputArchive archive;
+        m->save(archive);
+        archive.save_to(path);
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "refnets_save: %s\n", e.what()); return -1; }
+}
+int refnets_load(RefNets* r, int net, const char* path) {
+    try {
+        auto* m = r->all[net].second;
+        torch::serialize::InputArchive archive;
+        archive.load_from(path);
+        m->load(archive);
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "refnets_load: %s\n", e.what()); return -1; }
+}
+const char* refnets_net_name(RefNets* r, int net) { return r->all[net].first.c_str(); }
+
 // forwards (batch-1, exactly as DecisionNetHandler calls them)
 void refnets_encode(RefNets* r, int job, const float* x, int n, float* y) {
     torch::NoGradGuard g;

@@ -72,3 +72,49 @@ def test_train_and_run_like_py_main(tmp_path, capsys):
     # print_info (src/pybindings.cpp:60-75) after every step: the book posted during that step
     assert len(log) == 5 and log[0].startswith("Time = 1:") and log[4].startswith("Time = 5:")
     assert all(("Avg. price" in e or "[No offers]" in e) and ("Avg. wage" in e or "[No job offers]" in e) for e in log)
+
+
+def test_reads_checkpoints_written_by_the_reference():
+    """tests/golden/ref_checkpoint/*.pt were written by the reference's own torch::save (gen_checkpoint_golden.py)"""
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_checkpoint")
+    z = np.load(os.path.join(d, "params.npz"))
+    cfg = {k.split("/", 1)[1]: int(z[k][0]) for k in z.files if k.startswith("cfg/")}
+    nets = policy.DecisionNets(**cfg)
+    legacy.load_models(nets, d + "/")
+    checked = 0
+    for key in z.files:
+        if key.startswith("cfg/"):
+            continue
+        net, pname = key.split("/", 1)
+        assert np.array_equal(dict(nets.net(net).named_parameters())[pname].detach().numpy(), z[key]), key
+        checked += 1
+    assert checked > 100
+
+
+def test_reference_reads_checkpoints_written_here(tmp_path):
+    """save_models_reference_format -> the reference's torch::load (compiled reference modules, when built here)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    gen = pytest.importorskip("gen_policy_golden")
+    ck = pytest.importorskip("gen_checkpoint_golden")
+    if not os.path.exists(gen.LIB):
+        pytest.skip("oracle/_ref/libfastace_refnets.so not built here")
+    L = ck.bind(gen.load())
+    if not hasattr(L, "refnets_load"):
+        pytest.skip("prebuilt harness without refnets_load")
+    cfg = gen.CFG
+    torch.manual_seed(9)
+    nets = policy.DecisionNets(**cfg)
+    legacy.save_models_reference_format(nets, str(tmp_path) + "/")
+    h = L.refnets_create(cfg["stackSize"], cfg["encodingSize"], cfg["hiddenSize"], cfg["nHidden"], cfg["nHiddenSmall"], cfg["numGoods"], 1)
+    for i in range(11):
+        name = L.refnets_net_name(h, i).decode()
+        assert L.refnets_load(h, i, os.path.join(str(tmp_path), name + ".pt").encode()) == 0, name
+    for key, value in gen.export_params(L, h).items():
+        net, pname = key.split("/", 1)
+        assert np.array_equal(dict(nets.net(net).named_parameters())[pname].detach().numpy(), value), key
+    # and the round trip through our own reader
+    other = policy.DecisionNets(**cfg)
+    legacy.load_models(other, str(tmp_path) + "/")
+    for (k, a), (_, b) in zip(nets.named_parameters(), other.named_parameters()):
+        assert torch.equal(a, b), k
