@@ -307,3 +307,36 @@ def test_non_finite_economies_are_dropped(gold):
     n2, a2 = build(case, cfg)
     a2.nan_policy = "propagate"
     assert np.isnan(a2.train_on_episode(both))
+
+
+@pytest.mark.gpu
+def test_value_nets_learn_on_env_episodes():
+    """beyond gradient parity: a few updates on fresh episodes of the CUDA env reduce the critics' error
+    (mean squared advantage of persons and firms) — the trainer, the recorded episodes and the env fit together"""
+    from fastace_b200 import _abi, scenario
+    from fastace_b200.env import BatchedEconomy
+    dims = (128, 40, 6, 2, 8)
+    env = BatchedEconomy(dims)
+    state = scenario.custom_initial_state(dims, 3)[0]
+    torch.manual_seed(0)
+    nets = policy.DecisionNets(numGoods=2, stackSize=8, hiddenSize=32, nHidden=3, nHiddenSmall=2).cuda()
+    with torch.no_grad():                      # finite log-normal heads at random init (see bench.py --train)
+        for name, prm in nets.named_parameters():
+            if ".last" in name and "offerEncoder" not in name and "jobOfferEncoder" not in name:
+                prm.mul_(0.05)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0)
+    pol = policy.BatchedPolicy(env, nets, generator=gen)
+    # critics only (the policy heads keep lr 0, so the returns they are regressed on stay comparable between episodes)
+    a2c = trainer.AdvantageActorCritic(nets, lr=0.0, lrs={"valueNet": 1e-2, "firmValueNet": 1e-2}, wiring="intended")
+    out = env.alloc_outputs()
+    errs = []
+    for k in range(10):
+        env.set_state(state, time=0)
+        ep = trainer.run_episode(pol, scenario.OrderStream(dims, 4), out, 6, flags=_abi.IDX_ABSOLUTE)
+        _, adv_p, _, adv_f = a2c.returns_and_advantages(ep)
+        keep = ep.finite
+        err = torch.stack([a[keep] for a in adv_p]).pow(2).mean().item() + torch.stack([a[keep] for a in adv_f[:-1]]).pow(2).mean().item()
+        errs.append(err)
+        assert np.isfinite(a2c.train_on_episode(ep))
+    assert errs[-1] < 0.9 * errs[0] and min(errs[5:]) < min(errs[:3]), errs
+    env.close()
