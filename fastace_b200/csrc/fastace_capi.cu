@@ -154,6 +154,7 @@ struct fastace_env {
     uint64_t prof_steps;
     // large-economy path (large_economy.cuh)
     bool large_only;          // dims beyond the warp-per-economy kernels: every step takes the large path
+    bool mid_step;            // FASTACE_STEP_PERSONS has run, FASTACE_STEP_FIRMS has not yet
     bool have_large;
     int large_coop_blocks_p, large_coop_blocks_f;   // co-resident CTAs of the two cooperative iteration kernels
     void* large_block;
@@ -337,6 +338,7 @@ int fastace_env_set_state(fastace_env_t* env, const fastace_state_t* host_state,
         FASTACE_CUDA_CHECK(cudaMemcpy(member(&env->dstate, f.offset), src, f.elem * f.count, cudaMemcpyHostToDevice));
     }
     env->time = time;
+    env->mid_step = false;
     return FASTACE_OK;
 }
 
@@ -536,16 +538,32 @@ extern "C" {
 
 static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const fastace_actions_compact_t* dcz,
                        const fastace_step_out_t* dout, uint32_t flags, cudaStream_t stream) {
+    const bool only_p = (flags & FASTACE_STEP_PERSONS) != 0, only_f = (flags & FASTACE_STEP_FIRMS) != 0;
+    if (only_p && only_f) { set_error("FASTACE_STEP_PERSONS and FASTACE_STEP_FIRMS are two separate calls"); return FASTACE_ERR_INVALID; }
+    if ((only_p || only_f) && (dcz || (flags & (FASTACE_STEP_SERIAL | FASTACE_STEP_LARGE)) || env->large_only)) {
+        set_error("two-call stepping is implemented by the warp-per-economy kernels with the int32 action encoding");
+        return FASTACE_ERR_INVALID;
+    }
+    if (only_f != env->mid_step) {
+        set_error(env->mid_step ? "the person phase has run: the next call must be FASTACE_STEP_FIRMS"
+                                : "FASTACE_STEP_FIRMS must follow a FASTACE_STEP_PERSONS call");
+        return FASTACE_ERR_INVALID;
+    }
     if (dcz) {
         for (auto& f : compact_fields(env->dims))
             if (f.count && !member(dcz, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
         if (flags & FASTACE_STEP_SERIAL) { set_error("the serial kernel takes the int32 action encoding"); return FASTACE_ERR_INVALID; }
     } else {
-        for (auto& f : action_fields(env->dims))
-            if (f.count && !member(dact, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
+        for (auto& f : action_fields(env->dims)) {
+            const bool person_field = f.offset == offsetof(fastace_actions_t, perm_person) || f.offset == offsetof(fastace_actions_t, p_job_idx) ||
+                                      f.offset == offsetof(fastace_actions_t, p_job_take) || f.offset == offsetof(fastace_actions_t, p_good_idx) ||
+                                      f.offset == offsetof(fastace_actions_t, p_good_take) || f.offset == offsetof(fastace_actions_t, p_consume);
+            if ((only_p && !person_field) || (only_f && person_field)) continue;   // the other phase's arrays are not read
+            if (f.count && !member(dact, f.offset)) { set_error("actions: every array of the phase is mandatory"); return FASTACE_ERR_INVALID; }
+        }
     }
-    if ((env->dims.num_persons > 0 && !dout->p_reward) || !dout->f_profit) {
-        set_error("out: p_reward and f_profit are mandatory");
+    if ((!only_f && env->dims.num_persons > 0 && !dout->p_reward) || (!only_p && !dout->f_profit)) {
+        set_error("out: p_reward (person phase) and f_profit (firm phase) are mandatory");
         return FASTACE_ERR_INVALID;
     }
     if (env->large_only || (flags & FASTACE_STEP_LARGE)) {
@@ -589,9 +607,10 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         UpdateParams up;
         up.sp = sp; up.scr_pnh = env->scr_pnh; up.scr_pnb = env->scr_pnb;
         const size_t persons = (size_t)sp.E * sp.P;
-        const int person_blocks = (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
-        up.firm_blocks = (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
-        ks.update<<<person_blocks + up.firm_blocks, kUpdateThreads, 0, stream>>>(up);
+        // update_kernel: blocks [0, firm_blocks) do the firms, the rest the persons; a phase call launches only its part
+        const int person_blocks = only_f ? 0 : (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
+        up.firm_blocks = only_p ? 0 : (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
+        if (person_blocks + up.firm_blocks > 0) ks.update<<<person_blocks + up.firm_blocks, kUpdateThreads, 0, stream>>>(up);
         FASTACE_CUDA_CHECK(cudaGetLastError());
         env->launches += 2;
         if (prof) {
@@ -603,7 +622,8 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
             env->prof_match_ms += a; env->prof_update_ms += b; env->prof_steps += 1;
         }
     }
-    env->time += 1;
+    if (only_p) env->mid_step = true;          // the step completes with the FASTACE_STEP_FIRMS call
+    else { env->mid_step = false; env->time += 1; }
     return FASTACE_OK;
 }
 
@@ -656,7 +676,8 @@ static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::ve
     if (env->buf_used[b]) FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->copy_in, env->kern_done[b], 0));
     {
         // Host arrays that sit in one block with the staging buffer's own layout (fields in struct order, each
-        // padded to 256 B — what fastace_b200._abi.alloc_host_block hands out) travel as ONE copy instead of 14.
+        // padded to 256 B — what fastace_b200._abi.alloc_host_block hands out) travel as ONE copy instead of 14
+        // wherever consecutive arrays touch.
         const char* run_h = nullptr; char* run_d = nullptr; size_t run_n = 0;
         auto flush = [&]() -> cudaError_t {
             cudaError_t e = run_n ? cudaMemcpyAsync(run_d, run_h, run_n, cudaMemcpyHostToDevice, env->copy_in) : cudaSuccess;
@@ -668,8 +689,10 @@ static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::ve
             const char* h = static_cast<const char*>(member(actions, f.offset));
             char* d = static_cast<char*>(member(&dacts[b], f.offset));
             const size_t bytes = f.elem * f.count;
-            if (run_n && h == run_h + align_up(run_n, 256) && d == run_d + align_up(run_n, 256)) {
-                run_n = align_up(run_n, 256) + bytes;
+            // merged only when the arrays touch with no gap (sizes that are multiples of 256 B, e.g. any E multiple of
+            // 256): bytes between two host arrays may belong to somebody else
+            if (run_n && (run_n % 256) == 0 && h == run_h + run_n && d == run_d + run_n) {
+                run_n += bytes;
             } else {
                 FASTACE_CUDA_CHECK(flush());
                 run_h = h; run_d = d; run_n = bytes;
@@ -701,8 +724,8 @@ static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::ve
             if (!h || !f.count) continue;
             const char* d = static_cast<const char*>(member(&env->dout[b], f.offset));
             const size_t bytes = f.elem * f.count;
-            if (run_n && h == run_h + align_up(run_n, 256) && d == run_d + align_up(run_n, 256)) {
-                run_n = align_up(run_n, 256) + bytes;
+            if (run_n && (run_n % 256) == 0 && h == run_h + run_n && d == run_d + run_n) {
+                run_n += bytes;
             } else {
                 FASTACE_CUDA_CHECK(flush());
                 run_h = h; run_d = d; run_n = bytes;

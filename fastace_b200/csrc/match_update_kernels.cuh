@@ -149,6 +149,9 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     auto rec_good = [&](int n) { return (int)((s_mrec[n].z >> 8) & 0xFFu); };
 
     const size_t eP = (size_t)e * P, eF = (size_t)e * F, eCap = (size_t)e * cap;
+    // a step may be taken in two calls (FASTACE_STEP_PERSONS, then FASTACE_STEP_FIRMS): the state in HBM between
+    // them is the economy as it stands when the last person has acted and no firm has (economy.cpp:118-123)
+    const bool do_persons = !(p.flags & FASTACE_STEP_FIRMS), do_firms = !(p.flags & FASTACE_STEP_PERSONS);
     const int NM = p.st.m_count[e];
     const int NJ = p.st.j_count[e];
     const int NR = NJ + NM;
@@ -157,13 +160,15 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     {
         const IndexMap mapJ(NJ, p.flags), mapM(NM, p.flags);
         const bool hasJ = NJ > 0, hasM = NM > 0;   // empty book: no requests at all (decisionNetHandler.cpp:398-403, 476-480)
-        for (int pid = lane; pid < P; pid += 32) {
+        for (int pid = lane; do_persons && pid < P; pid += 32) {
             s_pmoney[pid] = p.st.p_money[eP + pid];
             s_permp[pid] = p.compact ? p.cz.perm_person[eP + pid] : (uint16_t)p.ac.perm_person[eP + pid];
         }
         // request lists -> person-major rows; 4 consecutive persons per lane when rows are 16B-aligned
         const size_t row0 = (size_t)e * S * P;
-        if (p.compact) {
+        if (!do_persons) {
+            // firms-only call: no person requests are read
+        } else if (p.compact) {
             for (int pid = lane; pid < P; pid += 32) {
                 const uint32_t tj = hasJ ? p.cz.p_job_take[eP + pid] : 0u, tg = hasM ? p.cz.p_good_take[eP + pid] : 0u;
                 uint8_t* row = s_att + pid * AS;
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
         }
         for (int f = lane; f < F; f += 32) {
             s_fmoney[f] = p.st.f_money[eF + f];
-            s_permf[f] = (uint16_t)perm_firm_at(p, eF + f);
+            s_permf[f] = do_firms ? (uint16_t)perm_firm_at(p, eF + f) : (uint16_t)f;
             s_fnh[f] = 0;
             s_fok[f] = 0;
             s_fcnt[f] = 0;
@@ -222,8 +227,10 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
 #pragma unroll
             for (int g = 0; g < G; g++) s_finv[g * F + f] = p.st.f_inv[((size_t)e * G + g) * F + f];
             const size_t k0 = (size_t)e * S * F + f;
-            for (int i = S; i < 16; i++) s_fatt[f * 16 + i] = (uint8_t)kNone;
-            if (p.compact) {
+            for (int i = do_firms ? S : 0; i < 16; i++) s_fatt[f * 16 + i] = (uint8_t)kNone;
+            if (!do_firms) {
+                // persons-only call: the firms' requests are not read
+            } else if (p.compact) {
                 const uint32_t tg = hasM ? p.cz.f_good_take[eF + f] : 0u;
                 for (int i = 0; i < S; i++)
                     s_fatt[f * 16 + i] = (uint8_t)(((tg >> i) & 1u) ? mapM((int)p.cz.f_good_idx[k0 + (size_t)i * F]) : kNone);
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     __syncwarp();
 
     // ------------------------------ persons: windows of 32 visiting ranks -------------------
-    for (int base = 0; base < P; base += 32) {
+    for (int base = 0; do_persons && base < P; base += 32) {
         const int r = base + lane;
         const bool active = r < P;
         const int pid = active ? (int)s_permp[r] : 0;
@@ -486,20 +493,26 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     }
 
     // ------------------------------ persons: results to HBM ---------------------------------
-    for (int pid = lane; pid < P; pid += 32) {
+    for (int pid = lane; do_persons && pid < P; pid += 32) {
         p.st.p_money[eP + pid] = s_pmoney[pid];
         mp.scr_pnh[eP + pid] = s_pnh[pid];
 #pragma unroll
         for (int g = 0; g < G; g++) mp.scr_pnb[((size_t)e * G + g) * P + pid] = s_pnb[g * Pp + pid];
     }
     // job counters are final after the person phase
-    if (p.out.old_j_left) for (int n = lane; n < NJ; n += 32) p.out.old_j_left[eF + n] = s_jleft[n];
-    if (p.out.old_j_taken) for (int n = lane; n < NJ; n += 32) p.out.old_j_taken[eF + n] = s_jtaken[n];
+    if (do_persons && p.out.old_j_left) for (int n = lane; n < NJ; n += 32) p.out.old_j_left[eF + n] = s_jleft[n];
+    if (do_persons && p.out.old_j_taken) for (int n = lane; n < NJ; n += 32) p.out.old_j_taken[eF + n] = s_jtaken[n];
+    if (!do_firms) {
+        // persons-only call: the books' counters go back to HBM for the firms call (a full step never needs them
+        // there: update_kernel replaces the books)
+        for (int n = lane; n < NM; n += 32) { p.st.m_left[eCap + n] = s_mleft[n]; p.st.m_taken[eCap + n] = s_mtaken[n]; }
+        for (int n = lane; n < NJ; n += 32) { p.st.j_left[eF + n] = s_jleft[n]; p.st.j_taken[eF + n] = s_jtaken[n]; }
+    }
 
     // ------------------------------ firms: serial walk in visiting order ---------------------
-    for (int f = lane; f < F; f += 32) s_flast[f] = p.st.f_last_money[eF + f];
+    for (int f = lane; do_firms && f < F; f += 32) s_flast[f] = p.st.f_last_money[eF + f];
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0 && do_firms) {
         for (int r = 0; r < F; r++) {
             const int f = s_permf[r];
             const int first = s_ffirst[f], cnt = s_fcnt[f];
@@ -583,18 +596,18 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     }
     __syncwarp();
     // ------------------------------ firms: results to HBM -----------------------------------
-    if (p.out.old_m_left) for (int n = lane; n < NM; n += 32) p.out.old_m_left[eCap + n] = (uint32_t)s_dord[n];
-    if (p.out.old_m_taken) for (int n = lane; n < NM; n += 32) p.out.old_m_taken[eCap + n] = s_mtaken[n];
+    if (do_firms && p.out.old_m_left) for (int n = lane; n < NM; n += 32) p.out.old_m_left[eCap + n] = (uint32_t)s_dord[n];
+    if (do_firms && p.out.old_m_taken) for (int n = lane; n < NM; n += 32) p.out.old_m_taken[eCap + n] = s_mtaken[n];
     for (int f = lane; f < F; f += 32) {
         p.st.f_money[eF + f] = s_fmoney[f];
-        p.out.f_profit[eF + f] = s_flast[f];
+        if (do_firms) p.out.f_profit[eF + f] = s_flast[f];
 #pragma unroll
         for (int g = 0; g < G; g++) p.st.f_inv[((size_t)e * G + g) * F + f] = s_finv[g * F + f];
         double labor = p.st.f_labor[eF + f];
         const uint32_t nhf = s_fnh[f];
         for (uint32_t k = 0; k < nhf; k++) labor += kLaborPerOffer;  // firm.cpp:109, one add per hire
         p.st.f_labor[eF + f] = labor;
-        if (p.out.f_good_ok) {
+        if (do_firms && p.out.f_good_ok) {
             const uint32_t ok = s_fok[f];
             for (int i = 0; i < S; i++) p.out.f_good_ok[((size_t)e * S + i) * F + f] = (ok >> i) & 1u;
         }

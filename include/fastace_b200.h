@@ -246,6 +246,17 @@ typedef struct fastace_step_out {
  * cooperative kernels, so the call stays asynchronous on its stream. */
 #define FASTACE_STEP_LARGE   16u
 
+/* One step in two calls, so that a caller can compute the firms' decisions from the state the firms actually see
+ * (after every person has acted: money after sales and hires, inventories after sales, laborHired; the reference's
+ * firms decide inside their own turn, economy.cpp:121-123).  FASTACE_STEP_PERSONS runs the person phase only (reads
+ * the person members of `actions`, writes p_reward, p_*_ok, old_j_*); FASTACE_STEP_FIRMS, which must follow it, runs
+ * the firm phase (reads perm_firm and the f_* members, writes f_profit, f_good_ok, old_m_*) and completes the step
+ * (time advances here); give each call only its own output arrays (the others NULL).  The two calls together give
+ * bit-identical results to one full call.  Warp-per-economy
+ * kernels only (not with FASTACE_STEP_SERIAL / FASTACE_STEP_LARGE / the compact encoding). */
+#define FASTACE_STEP_PERSONS 32u
+#define FASTACE_STEP_FIRMS   64u
+
 typedef struct fastace_env fastace_env_t;
 
 /* ---- library ---------------------------------------------------------------------- */

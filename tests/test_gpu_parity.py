@@ -223,3 +223,49 @@ def test_host_block_single_copy_path(oracle, kind):
         H.compare_outputs(gout, oout, dims, before)
         H.compare_states(env.get_state(), ost, dims)
     env.close()
+
+
+def test_two_call_step_equals_one_call(oracle):
+    """FASTACE_STEP_PERSONS + FASTACE_STEP_FIRMS == one full step, bit for bit (state, outputs), and the oracle"""
+    from fastace_b200 import lib
+    from fastace_b200.env import BatchedEconomy
+    dims = (12, 100, 10, 2, 10)
+    state = scenario.custom_initial_state(dims, 51)[0]
+    one, two = BatchedEconomy(dims), BatchedEconomy(dims)
+    one.set_state(state); two.set_state(state)
+    ost = H.copy_state(state)
+    orders = scenario.OrderStream(dims, 52)
+    for t in range(10):
+        act = scenario.synthetic_actions(dims, seed=53, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
+        before = H.copy_state(ost)
+        oout = _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=_abi.IDX_MODULO, time_before=t)
+        out1, out2 = _abi.alloc_host("out", dims), _abi.alloc_host("out", dims)
+        one.time_step_host(act, out1, flags=_abi.IDX_MODULO)
+        person_out = {k: out2[k] for k in ("p_reward", "p_job_ok", "p_good_ok", "old_j_left", "old_j_taken")}
+        firm_out = {k: out2[k] for k in ("f_profit", "f_good_ok", "old_m_left", "old_m_taken")}
+        two.time_step_host(act, person_out, flags=_abi.IDX_MODULO | _abi.STEP_PERSONS)
+        assert two.get_time() == t                                  # the step is not complete yet
+        mid = two.get_state()
+        assert np.array_equal(mid["p_money"], one.get_state()["p_money"])        # persons are done ...
+        assert np.array_equal(mid["m_count"], before["m_count"])                 # ... the books are still last step's
+        with pytest.raises(lib.FastaceError):
+            two.time_step_host(act, out2, flags=_abi.IDX_MODULO)                 # a full step cannot start mid-step
+        two.time_step_host(act, firm_out, flags=_abi.IDX_MODULO | _abi.STEP_FIRMS)
+        assert two.get_time() == t + 1
+        s1, s2 = one.get_state(), two.get_state()
+        for k in s1:
+            if k.startswith("m_") and k != "m_count" or k.startswith("j_") and k != "j_count":
+                cnt = s1["m_count"] if k.startswith("m_") else s1["j_count"]     # books: live prefix (the rest is not market)
+                for e in range(dims[0]):
+                    assert np.array_equal(s1[k][e, :cnt[e]], s2[k][e, :cnt[e]], equal_nan=s1[k].dtype.kind == "f"), (k, e)
+            else:
+                assert np.array_equal(s1[k], s2[k], equal_nan=s1[k].dtype.kind == "f"), k
+        for k in ("p_reward", "f_profit", "p_job_ok", "p_good_ok", "f_good_ok"):
+            assert np.array_equal(out1[k], out2[k], equal_nan=out1[k].dtype.kind == "f"), k
+        H.compare_outputs(out2, out1, dims, before)      # old_* counters: live prefix of the previous books
+        H.compare_outputs(out2, oout, dims, before)
+        H.compare_states(s2, ost, dims)
+    with pytest.raises(lib.FastaceError):
+        two.time_step_host(act, out2, flags=_abi.IDX_MODULO | _abi.STEP_FIRMS)   # firms need the person phase first
+    one.close(); two.close()
