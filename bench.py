@@ -393,8 +393,9 @@ def run_ours(args):
         gen = torch.Generator(device=dev)
         gen.manual_seed(1234 + rank)
         results = {}
-        for label, dt, fused in (("tf32", None, False), ("bf16", torch.bfloat16, False), ("fused_stack", None, True)):
-            pol = policy.BatchedPolicy(env, nets, generator=gen, autocast_dtype=dt, fused=fused)
+        for label, dt, fused, two in (("tf32", None, False, False), ("bf16", torch.bfloat16, False, False),
+                                      ("fused_stack", None, True, False), ("fused_two_phase", None, True, True)):
+            pol = policy.BatchedPolicy(env, nets, generator=gen, autocast_dtype=dt, fused=fused, two_phase=two)
             reset_state(0)
             rsteps = 8
             perm_dev = [(torch.from_numpy(a["perm_person"]).to(dev), torch.from_numpy(a["perm_firm"]).to(dev)) for a in acts[:rsteps + 2]]
@@ -413,8 +414,9 @@ def run_ours(args):
                 dist.all_reduce(t_r, op=dist.ReduceOp.MAX)
             results[label] = {"ms_per_step": float(t_r.item()), "value": world * E * (P + F) / (float(t_r.item()) * 1e-3)}
         rollout = {"unit": METRIC, "policy": "11 decision nets (hidden 100 x 12 layers), random init, batched over all agents; tf32 / bf16 = eager torch, "
-                             "fused_stack = hidden stacks through csrc/mlp_stack.cuh (bf16 mma operands, fp32 accumulate + residual)",
-                   "semantics": "decisions taken from the state at the start of the step (DESIGN.md §7)", **results}
+                             "fused_* = net bodies through csrc/mlp_stack.cuh (bf16 mma operands, fp32 accumulate + residual)",
+                   "semantics": "decisions taken from the state at the start of the step; fused_two_phase: firms decide after the "
+                                "person phase, on the state they see in the reference (DESIGN.md §7)", **results}
 
     # ---- training (row f-2): T-step rollout with recording + one advantage actor-critic update -----------
     training = None

@@ -129,7 +129,7 @@ def run(scenarioParams, trainingParams, numEconomies=1, device=0, saveDir=DEFAUL
     dims, env, nets = _build(scenarioParams, trainingParams, numEconomies, device)
     load_models(nets, saveDir)
     env.set_state(scenario.custom_initial_state(dims, seed, scenarioParams)[0])
-    pol = policy.BatchedPolicy(env, nets.eval(), fused=fused)
+    pol = policy.BatchedPolicy(env, nets.eval(), fused=fused, two_phase=True)
     orders = scenario.OrderStream(dims, seed + 1)
     out = env.alloc_outputs()
     log = []
@@ -155,7 +155,7 @@ def train(scenarioParams, trainingParams, fromPretrained=False, perturbationSize
     a2c = trainer.AdvantageActorCritic(
         nets, lrs=lrs, episodeBatchSizeForLRDecay=int(tp.episodeBatchSizeForLRDecay), patienceForLRDecay=int(tp.patienceForLRDecay),
         multiplierForLRDecay=float(tp.multiplierForLRDecay), cosinePeriod=int(tp.reverseAnnealingPeriod), **(trainer_kwargs or {}))
-    pol = policy.BatchedPolicy(env, nets)
+    pol = policy.BatchedPolicy(env, nets, two_phase=True)    # firms decide after the person phase, as in the reference
     out = env.alloc_outputs()
     say = (lambda *a: None) if quiet else print
     losses = [0.0] * int(tp.numEpisodes)

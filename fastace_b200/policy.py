@@ -329,13 +329,22 @@ def draw(snap, stackSize, generator=None):
     }
 
 
-def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference"):
+PERSON_OUT = ("p_reward", "p_job_ok", "p_good_ok", "old_j_left", "old_j_taken")
+FIRM_OUT = ("f_profit", "f_good_ok", "old_m_left", "old_m_taken")
+FIRM_SNAPSHOT_KEYS = ("f_money", "f_labor", "f_inv")      # what the person phase changes of the firms' inputs
+
+
+def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", sides=("persons", "firms")):
     """Forward of the 11 nets for every agent of every economy + sampling with the given draws.
     Differentiable when autograd is enabled (the trainer re-evaluates recorded steps with it).
 
     sample_grad: "reference" keeps the reparameterised sample attached to the graph exactly as the
     reference does (decisionNetHandler.cpp:31-32: the quadratic term of the log-density then has zero
     gradient, only -log sigma trains); "score_function" detaches the sample (the textbook estimator).
+
+    sides: evaluate only the persons' or only the firms' nets (two-phase stepping decides the firms after the
+    person phase has run; a recorded two-phase step holds the firms' post-person-phase state in its f_* fields,
+    so re-evaluating it with both sides reproduces both).
 
     Returns (decoded, info): decoded = agent-major action tensors, info = log-probabilities [E,agents]
     and state values."""
@@ -362,64 +371,72 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference"):
         # agents as rows of 2-D matrices: nn.Linear then runs as ONE addmm with the bias in the GEMM epilogue
         rows = lambda x: x.reshape(-1, x.shape[-1])
 
-        # --- persons
-        pidxM, pidxJ = draws["pidxM"], draws["pidxJ"]
-        util = torch.cat([st["p_util_tfp"].unsqueeze(1), st["p_util_share"], st["p_util_rho"].unsqueeze(1)], dim=1)
-        util = util.permute(0, 2, 1).to(f32)                                     # [E,P,G+3]: tfp, shares, rho (:30-38)
-        money = st["p_money"].to(f32).unsqueeze(-1)
-        if "p_labor_input" in st:                                                 # tests inject it; the env path uses 0
-            labor0 = st["p_labor_input"].to(f32).unsqueeze(-1)
-        else:
-            labor0 = torch.zeros_like(money)                                      # laborSupplied was just reset (person.cpp:24)
-        inv = st["p_inv"].permute(0, 2, 1).to(f32)
-        eM, eJ = gather(encM, pidxM, validM), gather(encJ, pidxJ, validJ)
-        util, money, labor0, inv = rows(util), rows(money), rows(labor0), rows(inv)
-        p_value = nets.valueNet(eM, eJ, util, money, labor0, inv).reshape(E, P)
-        p_job_p = nets.laborSearchNet(eJ, util, money, labor0, inv).reshape(E, P, S)
-        p_good_p = nets.purchaseNet(eM, util, money, labor0, inv).reshape(E, P, S)
-        cons = nets.consumptionNet(util, money, labor0, inv).reshape(E, P, G, 2)
-        # --- firms
-        fidxM, fidxJ = draws["fidxM"], draws["fidxJ"]
-        pf = torch.cat([st["f_prod_tfp"].unsqueeze(2), st["f_prod_share"], st["f_prod_rho"].unsqueeze(2)], dim=2)
-        pf = pf.permute(0, 3, 1, 2).reshape(E, F, G * (G + 3)).to(f32)           # per good: tfp, shares, rho (:36-48)
-        fmoney = st["f_money"].to(f32).unsqueeze(-1)
-        flabor = st["f_labor"].to(f32).unsqueeze(-1)
-        finv = st["f_inv"].permute(0, 2, 1).to(f32)
-        feM, feJ = gather(encM, fidxM, validM), gather(encJ, fidxJ, validJ)
-        pf, fmoney, flabor, finv = rows(pf), rows(fmoney), rows(flabor), rows(finv)
-        f_value = nets.firmValueNet(feM, feJ, pf, fmoney, flabor, finv).reshape(E, F)
-        f_good_p = nets.firmPurchaseNet(feM, pf, fmoney, flabor, finv).reshape(E, F, S)
-        prod = nets.productionNet(pf, fmoney, flabor, finv).reshape(E, F, G, 2)
-        offer = nets.offerNet(feM, pf, fmoney, flabor, finv).reshape(E, F, G, 4)
-        job = nets.jobOfferNet(feJ, pf, fmoney, flabor, finv).reshape(E, F, 4)
-    # --- sampling (fp32)
+        do_p, do_f = "persons" in sides, "firms" in sides
+        decoded, info, heads = {}, {}, {}
+        if do_p:
+            # --- persons
+            pidxM, pidxJ = draws["pidxM"], draws["pidxJ"]
+            util = torch.cat([st["p_util_tfp"].unsqueeze(1), st["p_util_share"], st["p_util_rho"].unsqueeze(1)], dim=1)
+            util = util.permute(0, 2, 1).to(f32)                                 # [E,P,G+3]: tfp, shares, rho (:30-38)
+            money = st["p_money"].to(f32).unsqueeze(-1)
+            if "p_labor_input" in st:                                             # tests inject it; the env path uses 0
+                labor0 = st["p_labor_input"].to(f32).unsqueeze(-1)
+            else:
+                labor0 = torch.zeros_like(money)                                  # laborSupplied was just reset (person.cpp:24)
+            inv = st["p_inv"].permute(0, 2, 1).to(f32)
+            eM, eJ = gather(encM, pidxM, validM), gather(encJ, pidxJ, validJ)
+            util, money, labor0, inv = rows(util), rows(money), rows(labor0), rows(inv)
+            heads["p_value"] = nets.valueNet(eM, eJ, util, money, labor0, inv).reshape(E, P)
+            heads["p_job_p"] = nets.laborSearchNet(eJ, util, money, labor0, inv).reshape(E, P, S)
+            heads["p_good_p"] = nets.purchaseNet(eM, util, money, labor0, inv).reshape(E, P, S)
+            heads["cons"] = nets.consumptionNet(util, money, labor0, inv).reshape(E, P, G, 2)
+        if do_f:
+            # --- firms
+            fidxM, fidxJ = draws["fidxM"], draws["fidxJ"]
+            pf = torch.cat([st["f_prod_tfp"].unsqueeze(2), st["f_prod_share"], st["f_prod_rho"].unsqueeze(2)], dim=2)
+            pf = pf.permute(0, 3, 1, 2).reshape(E, F, G * (G + 3)).to(f32)       # per good: tfp, shares, rho (:36-48)
+            fmoney = st["f_money"].to(f32).unsqueeze(-1)
+            flabor = st["f_labor"].to(f32).unsqueeze(-1)
+            finv = st["f_inv"].permute(0, 2, 1).to(f32)
+            feM, feJ = gather(encM, fidxM, validM), gather(encJ, fidxJ, validJ)
+            pf, fmoney, flabor, finv = rows(pf), rows(fmoney), rows(flabor), rows(finv)
+            heads["f_value"] = nets.firmValueNet(feM, feJ, pf, fmoney, flabor, finv).reshape(E, F)
+            heads["f_good_p"] = nets.firmPurchaseNet(feM, pf, fmoney, flabor, finv).reshape(E, F, S)
+            heads["prod"] = nets.productionNet(pf, fmoney, flabor, finv).reshape(E, F, G, 2)
+            heads["offer"] = nets.offerNet(feM, pf, fmoney, flabor, finv).reshape(E, F, G, 4)
+            heads["job"] = nets.jobOfferNet(feJ, pf, fmoney, flabor, finv).reshape(E, F, 4)
+    # --- sampling (fp32) and the empty-market conventions: purchase log-prob NaN = "no decision", job search 0.0
+    #     (decisionNetHandler.cpp:398-403, 476-480)
     detach = sample_grad != "reference"
-    p_job_take, lp_job = sample_bernoulli(p_job_p.float(), draws["u_job"])
-    p_good_take, lp_good = sample_bernoulli(p_good_p.float(), draws["u_good"])
-    f_good_take, lp_fgood = sample_bernoulli(f_good_p.float(), draws["u_fgood"])
-    cons_x, lp_cons = sample_logit_normal(cons.float(), draws["n_cons"], detach)
-    prod_x, lp_prod = sample_logit_normal(prod.float(), draws["n_prod"], detach)
-    amt_x, lp_amt = sample_logit_normal(offer.float()[..., 0:2], draws["n_amt"], detach)
-    price_x, lp_price = sample_log_normal(offer.float()[..., 2:4], draws["n_price"], detach)
-    lab_x, lp_lab = sample_log_normal(job.float()[..., 0:2], draws["n_lab"], detach)
-    wage_x, lp_wage = sample_log_normal(job.float()[..., 2:4], draws["n_wage"], detach)
-    decoded = {
-        "p_job_idx": pidxJ, "p_job_take": p_job_take & validJ, "p_good_idx": pidxM, "p_good_take": p_good_take & validM,
-        "p_consume": cons_x, "f_good_idx": fidxM, "f_good_take": f_good_take & validM, "f_prod": prod_x,
-        "f_offer_amt": amt_x, "f_offer_price": price_x, "f_job_labor": lab_x, "f_job_wage": wage_x,
-    }
-    nan = torch.full_like(lp_good, float("nan"))
-    info = {
-        "value_person": p_value.float(), "value_firm": f_value.float(),
-        # empty market: purchase log-prob NaN = "no decision", job search 0.0 (decisionNetHandler.cpp:398-403, 476-480)
-        "logp_purchase": torch.where(validM.view(E, 1), lp_good, nan),
-        "logp_laborSearch": torch.where(validJ.view(E, 1), lp_job, torch.zeros_like(lp_job)),
-        "logp_consumption": lp_cons.sum(-1),
-        "logp_firmPurchase": torch.where(validM.view(E, 1), lp_fgood, torch.full_like(lp_fgood, float("nan"))),
-        "logp_production": lp_prod.sum(-1),
-        "logp_offer": lp_amt.sum(-1) + lp_price.sum(-1),
-        "logp_jobOffer": lp_lab + lp_wage,
-    }
+    if do_p:
+        p_job_take, lp_job = sample_bernoulli(heads["p_job_p"].float(), draws["u_job"])
+        p_good_take, lp_good = sample_bernoulli(heads["p_good_p"].float(), draws["u_good"])
+        cons_x, lp_cons = sample_logit_normal(heads["cons"].float(), draws["n_cons"], detach)
+        decoded.update({"p_job_idx": draws["pidxJ"], "p_job_take": p_job_take & validJ, "p_good_idx": draws["pidxM"],
+                        "p_good_take": p_good_take & validM, "p_consume": cons_x})
+        info.update({
+            "value_person": heads["p_value"].float(),
+            "logp_purchase": torch.where(validM.view(E, 1), lp_good, torch.full_like(lp_good, float("nan"))),
+            "logp_laborSearch": torch.where(validJ.view(E, 1), lp_job, torch.zeros_like(lp_job)),
+            "logp_consumption": lp_cons.sum(-1),
+        })
+    if do_f:
+        f_good_take, lp_fgood = sample_bernoulli(heads["f_good_p"].float(), draws["u_fgood"])
+        prod_x, lp_prod = sample_logit_normal(heads["prod"].float(), draws["n_prod"], detach)
+        offer, job = heads["offer"].float(), heads["job"].float()
+        amt_x, lp_amt = sample_logit_normal(offer[..., 0:2], draws["n_amt"], detach)
+        price_x, lp_price = sample_log_normal(offer[..., 2:4], draws["n_price"], detach)
+        lab_x, lp_lab = sample_log_normal(job[..., 0:2], draws["n_lab"], detach)
+        wage_x, lp_wage = sample_log_normal(job[..., 2:4], draws["n_wage"], detach)
+        decoded.update({"f_good_idx": draws["fidxM"], "f_good_take": f_good_take & validM, "f_prod": prod_x,
+                        "f_offer_amt": amt_x, "f_offer_price": price_x, "f_job_labor": lab_x, "f_job_wage": wage_x})
+        info.update({
+            "value_firm": heads["f_value"].float(),
+            "logp_firmPurchase": torch.where(validM.view(E, 1), lp_fgood, torch.full_like(lp_fgood, float("nan"))),
+            "logp_production": lp_prod.sum(-1),
+            "logp_offer": lp_amt.sum(-1) + lp_price.sum(-1),
+            "logp_jobOffer": lp_lab + lp_wage,
+        })
     return decoded, info
 
 
@@ -434,10 +451,14 @@ class BatchedPolicy:
     persons, as in the reference's first decision of a turn).  The networks, the index draws, the
     sampling rules and the action decode are the reference's."""
 
-    def __init__(self, env, nets, generator=None, autocast_dtype=None, fused=False):
+    def __init__(self, env, nets, generator=None, autocast_dtype=None, fused=False, two_phase=False):
         """fused=True: the residual hidden stacks run through the hand-written kernel (csrc/mlp_stack.cuh, bf16
-        tensor-core operands, fp32 accumulate/residual) instead of eager torch — a rollout-only fast mode."""
+        tensor-core operands, fp32 accumulate/residual) instead of eager torch — a rollout-only fast mode.
+        two_phase=True: step() runs the person phase first (FASTACE_STEP_PERSONS) and takes the firms' decisions
+        from the state the firms actually see in the reference — after every person has acted: money after sales and
+        hires, inventories after sales, laborHired of this step — then completes the step (FASTACE_STEP_FIRMS)."""
         self.env, self.nets, self.gen, self.autocast_dtype, self.fused = env, nets, generator, autocast_dtype, fused
+        self.two_phase = two_phase
         self.E, self.P, self.F, self.G, self.S = env.dims.tuple
         self.state = env.device_state_tensors()
         self.dev = self.state["p_money"].device
@@ -466,10 +487,42 @@ class BatchedPolicy:
             a[key].copy_(value if value.dim() == 2 else value.permute(0, 2, 1))   # agent-major -> [E][slot|good][agent]
         return info
 
+    def _write(self, decoded):
+        for key, value in decoded.items():
+            self.actions[key].copy_(value if value.dim() == 2 else value.permute(0, 2, 1))   # agent-major -> [E][slot|good][agent]
+
+    def _evaluate(self, snap, draws, sides):
+        global _FUSED
+        _FUSED = self.fused
+        try:
+            return evaluate(self.nets, snap, draws, self.autocast_dtype, sides=sides)
+        finally:
+            _FUSED = False
+
+    @torch.no_grad()
     def step(self, perms, out, flags=0, record=None):
         """decide + one env step (device path, current stream)."""
-        info = self.decide(perms, record)
-        self.env.time_step(self.packed, out, flags=flags)
+        if not self.two_phase:
+            info = self.decide(perms, record)
+            self.env.time_step(self.packed, out, flags=flags)
+            return info
+        from . import _abi
+        a = self.actions
+        a["perm_person"].copy_(torch.as_tensor(perms[0]))
+        a["perm_firm"].copy_(torch.as_tensor(perms[1]))
+        snap = snapshot(self.state) if record is not None else self.state
+        draws = draw(snap, self.S, self.gen)          # the books (and so the index ranges) do not change before the firms post
+        decoded, info = self._evaluate(snap, draws, ("persons",))
+        self._write(decoded)
+        self.env.time_step(self.packed, {k: v for k, v in out.items() if k in PERSON_OUT}, flags=flags | _abi.STEP_PERSONS)
+        if record is not None:
+            for k in FIRM_SNAPSHOT_KEYS:              # the firms' inputs as they stand after the person phase
+                snap[k] = self.state[k].clone()
+            record.append((snap, draws))
+        decoded_f, info_f = self._evaluate(snap, draws, ("firms",))
+        self._write(decoded_f)
+        self.env.time_step(self.packed, {k: v for k, v in out.items() if k in FIRM_OUT}, flags=flags | _abi.STEP_FIRMS)
+        info.update(info_f)
         return info
 
 
