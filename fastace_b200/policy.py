@@ -507,6 +507,16 @@ class BatchedPolicy:
             self.env.time_step(self.packed, out, flags=flags)
             return info
         from . import _abi
+
+        def phase_out(names):                         # each call gets only its own output arrays
+            if isinstance(out, _abi.StepOut):
+                sub = _abi.StepOut()
+                for n in names:
+                    setattr(sub, n, getattr(out, n))
+                sub._keepalive = out
+                return sub
+            return {k: v for k, v in out.items() if k in names}
+
         a = self.actions
         a["perm_person"].copy_(torch.as_tensor(perms[0]))
         a["perm_firm"].copy_(torch.as_tensor(perms[1]))
@@ -514,14 +524,14 @@ class BatchedPolicy:
         draws = draw(snap, self.S, self.gen)          # the books (and so the index ranges) do not change before the firms post
         decoded, info = self._evaluate(snap, draws, ("persons",))
         self._write(decoded)
-        self.env.time_step(self.packed, {k: v for k, v in out.items() if k in PERSON_OUT}, flags=flags | _abi.STEP_PERSONS)
+        self.env.time_step(self.packed, phase_out(PERSON_OUT), flags=flags | _abi.STEP_PERSONS)
         if record is not None:
             for k in FIRM_SNAPSHOT_KEYS:              # the firms' inputs as they stand after the person phase
                 snap[k] = self.state[k].clone()
             record.append((snap, draws))
         decoded_f, info_f = self._evaluate(snap, draws, ("firms",))
         self._write(decoded_f)
-        self.env.time_step(self.packed, {k: v for k, v in out.items() if k in FIRM_OUT}, flags=flags | _abi.STEP_FIRMS)
+        self.env.time_step(self.packed, phase_out(FIRM_OUT), flags=flags | _abi.STEP_FIRMS)
         info.update(info_f)
         return info
 
