@@ -18,6 +18,8 @@ STEP_ASYNC = 8
 STEP_LARGE = 16
 STEP_PERSONS = 32     # person phase only; STEP_FIRMS must follow and completes the step
 STEP_FIRMS = 64
+STEP_PERSONS_TRADE = 128      # job search + purchases; STEP_PERSONS_CONSUME must follow
+STEP_PERSONS_CONSUME = 256
 MAX_GOODS = 8
 FN_CES, FN_COBB_DOUGLAS, FN_STONE_GEARY, FN_LEONTIEF, FN_LINEAR = range(5)
 MAX_STACK = 16

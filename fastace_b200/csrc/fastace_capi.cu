@@ -154,7 +154,7 @@ struct fastace_env {
     uint64_t prof_steps;
     // large-economy path (large_economy.cuh)
     bool large_only;          // dims beyond the warp-per-economy kernels: every step takes the large path
-    bool mid_step;            // FASTACE_STEP_PERSONS has run, FASTACE_STEP_FIRMS has not yet
+    int mid_step;             // 0 between steps; 1 after PERSONS_TRADE (CONSUME is due); 2 after the person phase (FIRMS is due)
     bool have_large;
     int large_coop_blocks_p, large_coop_blocks_f;   // co-resident CTAs of the two cooperative iteration kernels
     void* large_block;
@@ -338,7 +338,7 @@ int fastace_env_set_state(fastace_env_t* env, const fastace_state_t* host_state,
         FASTACE_CUDA_CHECK(cudaMemcpy(member(&env->dstate, f.offset), src, f.elem * f.count, cudaMemcpyHostToDevice));
     }
     env->time = time;
-    env->mid_step = false;
+    env->mid_step = 0;
     return FASTACE_OK;
 }
 
@@ -538,16 +538,22 @@ extern "C" {
 
 static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const fastace_actions_compact_t* dcz,
                        const fastace_step_out_t* dout, uint32_t flags, cudaStream_t stream) {
-    const bool only_p = (flags & FASTACE_STEP_PERSONS) != 0, only_f = (flags & FASTACE_STEP_FIRMS) != 0;
-    if (only_p && only_f) { set_error("FASTACE_STEP_PERSONS and FASTACE_STEP_FIRMS are two separate calls"); return FASTACE_ERR_INVALID; }
+    const bool ph_p = (flags & FASTACE_STEP_PERSONS) != 0, only_f = (flags & FASTACE_STEP_FIRMS) != 0;
+    const bool ph_t = (flags & FASTACE_STEP_PERSONS_TRADE) != 0, ph_c = (flags & FASTACE_STEP_PERSONS_CONSUME) != 0;
+    const bool only_p = ph_p || ph_t || ph_c;          // some part of the person phase, no firm phase
+    if ((int)ph_p + (int)ph_t + (int)ph_c + (int)only_f > 1) { set_error("the phase flags are separate calls"); return FASTACE_ERR_INVALID; }
     if ((only_p || only_f) && (dcz || (flags & (FASTACE_STEP_SERIAL | FASTACE_STEP_LARGE)) || env->large_only)) {
-        set_error("two-call stepping is implemented by the warp-per-economy kernels with the int32 action encoding");
+        set_error("phase-wise stepping is implemented by the warp-per-economy kernels with the int32 action encoding");
         return FASTACE_ERR_INVALID;
     }
-    if (only_f != env->mid_step) {
-        set_error(env->mid_step ? "the person phase has run: the next call must be FASTACE_STEP_FIRMS"
-                                : "FASTACE_STEP_FIRMS must follow a FASTACE_STEP_PERSONS call");
-        return FASTACE_ERR_INVALID;
+    {
+        const int need = only_f ? 2 : ph_c ? 1 : 0;    // what must have run before this call
+        if (env->mid_step != need) {
+            set_error(env->mid_step == 1 ? "FASTACE_STEP_PERSONS_TRADE has run: the next call must be FASTACE_STEP_PERSONS_CONSUME"
+                      : env->mid_step == 2 ? "the person phase has run: the next call must be FASTACE_STEP_FIRMS"
+                      : only_f ? "FASTACE_STEP_FIRMS must follow the person phase" : "FASTACE_STEP_PERSONS_CONSUME must follow FASTACE_STEP_PERSONS_TRADE");
+            return FASTACE_ERR_INVALID;
+        }
     }
     if (dcz) {
         for (auto& f : compact_fields(env->dims))
@@ -555,15 +561,19 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         if (flags & FASTACE_STEP_SERIAL) { set_error("the serial kernel takes the int32 action encoding"); return FASTACE_ERR_INVALID; }
     } else {
         for (auto& f : action_fields(env->dims)) {
-            const bool person_field = f.offset == offsetof(fastace_actions_t, perm_person) || f.offset == offsetof(fastace_actions_t, p_job_idx) ||
-                                      f.offset == offsetof(fastace_actions_t, p_job_take) || f.offset == offsetof(fastace_actions_t, p_good_idx) ||
-                                      f.offset == offsetof(fastace_actions_t, p_good_take) || f.offset == offsetof(fastace_actions_t, p_consume);
-            if ((only_p && !person_field) || (only_f && person_field)) continue;   // the other phase's arrays are not read
-            if (f.count && !member(dact, f.offset)) { set_error("actions: every array of the phase is mandatory"); return FASTACE_ERR_INVALID; }
+            const bool consume_field = f.offset == offsetof(fastace_actions_t, p_consume);
+            const bool trade_field = f.offset == offsetof(fastace_actions_t, perm_person) || f.offset == offsetof(fastace_actions_t, p_job_idx) ||
+                                     f.offset == offsetof(fastace_actions_t, p_job_take) || f.offset == offsetof(fastace_actions_t, p_good_idx) ||
+                                     f.offset == offsetof(fastace_actions_t, p_good_take);
+            const bool firm_field = !consume_field && !trade_field;
+            // only the arrays the call reads are mandatory
+            const bool read = (!only_p && !only_f) || (ph_p && !firm_field) || (ph_t && trade_field) || (ph_c && consume_field) || (only_f && firm_field);
+            if (read && f.count && !member(dact, f.offset)) { set_error("actions: every array the call reads is mandatory"); return FASTACE_ERR_INVALID; }
         }
     }
-    if ((!only_f && env->dims.num_persons > 0 && !dout->p_reward) || (!only_p && !dout->f_profit)) {
-        set_error("out: p_reward (person phase) and f_profit (firm phase) are mandatory");
+    const bool needs_reward = !only_f && !ph_t, needs_profit = !only_p;
+    if ((needs_reward && env->dims.num_persons > 0 && !dout->p_reward) || (needs_profit && !dout->f_profit)) {
+        set_error("out: p_reward (consumption) and f_profit (firm phase) are mandatory");
         return FASTACE_ERR_INVALID;
     }
     if (env->large_only || (flags & FASTACE_STEP_LARGE)) {
@@ -601,8 +611,11 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         mp.sp = sp; mp.scr_pnh = env->scr_pnh; mp.scr_pnb = env->scr_pnb;
         mp.lay = make_match_layout(sp.P, sp.F, env->dims.num_goods, sp.S);
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[0], stream));
-        (sp.S <= 12 ? ks.match12 : ks.match16)<<<sp.E, 32, env->match_smem_bytes, stream>>>(mp);
-        FASTACE_CUDA_CHECK(cudaGetLastError());
+        if (!ph_c) {   // a consume-only call has no matching to do
+            (sp.S <= 12 ? ks.match12 : ks.match16)<<<sp.E, 32, env->match_smem_bytes, stream>>>(mp);
+            FASTACE_CUDA_CHECK(cudaGetLastError());
+            env->launches += 1;
+        }
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[1], stream));
         UpdateParams up;
         up.sp = sp; up.scr_pnh = env->scr_pnh; up.scr_pnb = env->scr_pnb;
@@ -610,9 +623,11 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         // update_kernel: blocks [0, firm_blocks) do the firms, the rest the persons; a phase call launches only its part
         const int person_blocks = only_f ? 0 : (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
         up.firm_blocks = only_p ? 0 : (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
-        if (person_blocks + up.firm_blocks > 0) ks.update<<<person_blocks + up.firm_blocks, kUpdateThreads, 0, stream>>>(up);
+        if (person_blocks + up.firm_blocks > 0) {
+            ks.update<<<person_blocks + up.firm_blocks, kUpdateThreads, 0, stream>>>(up);
+            env->launches += 1;
+        }
         FASTACE_CUDA_CHECK(cudaGetLastError());
-        env->launches += 2;
         if (prof) {
             FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[2], stream));
             FASTACE_CUDA_CHECK(cudaEventSynchronize(env->ev[2]));
@@ -622,8 +637,9 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
             env->prof_match_ms += a; env->prof_update_ms += b; env->prof_steps += 1;
         }
     }
-    if (only_p) env->mid_step = true;          // the step completes with the FASTACE_STEP_FIRMS call
-    else { env->mid_step = false; env->time += 1; }
+    if (ph_t) env->mid_step = 1;               // consumption is due
+    else if (only_p) env->mid_step = 2;        // the step completes with the FASTACE_STEP_FIRMS call
+    else { env->mid_step = 0; env->time += 1; }
     return FASTACE_OK;
 }
 

@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
     const size_t eP = (size_t)e * P, eF = (size_t)e * F, eCap = (size_t)e * cap;
     // a step may be taken in two calls (FASTACE_STEP_PERSONS, then FASTACE_STEP_FIRMS): the state in HBM between
     // them is the economy as it stands when the last person has acted and no firm has (economy.cpp:118-123)
-    const bool do_persons = !(p.flags & FASTACE_STEP_FIRMS), do_firms = !(p.flags & FASTACE_STEP_PERSONS);
+    const bool do_persons = !(p.flags & FASTACE_STEP_FIRMS);
+    const bool do_firms = !(p.flags & (FASTACE_STEP_PERSONS | FASTACE_STEP_PERSONS_TRADE));
     const int NM = p.st.m_count[e];
     const int NJ = p.st.j_count[e];
     const int NR = NJ + NM;
@@ -638,13 +639,28 @@ __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateP
         if (t >= (size_t)p.E * P) return;
         const int e = (int)(t / P), pid = (int)(t % P);
         const double labor = kLaborPerOffer * (double)up.scr_pnh[t];       // exact: 0, 0.5 or 1.0
+        if (p.flags & FASTACE_STEP_PERSONS_TRADE) {
+            // trade-only call: purchases and labour go into the state, consumption follows in its own call
+            // (it touches nobody but the person, so deferring it changes nothing: utilMaxer.cpp:88-92)
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const size_t k = ((size_t)e * G + g) * P + pid;
+                double v = p.st.p_inv[k];
+                const int nb = up.scr_pnb[k];
+                for (int q = 0; q < nb; q++) v += kAmountPerOffer;         // agent.cpp:109, one add per purchase
+                p.st.p_inv[k] = v;
+            }
+            p.st.p_labor[t] = labor;
+            return;
+        }
+        const bool applied = (p.flags & FASTACE_STEP_PERSONS_CONSUME) != 0;   // purchases are already in p_inv
         double x[G + 1], inv[G];
         x[0] = 1 - labor;
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const size_t k = ((size_t)e * G + g) * P + pid;
             double v = p.st.p_inv[k];
-            const int nb = up.scr_pnb[k];
+            const int nb = applied ? 0 : up.scr_pnb[k];
             for (int q = 0; q < nb; q++) v += kAmountPerOffer;             // agent.cpp:109, one add per purchase
             const double c = v * (double)p.ac.p_consume[k];                 // neuralPersonDecisionMaker.cpp:99
             x[g + 1] = c;

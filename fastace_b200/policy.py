@@ -334,7 +334,10 @@ FIRM_OUT = ("f_profit", "f_good_ok", "old_m_left", "old_m_taken")
 FIRM_SNAPSHOT_KEYS = ("f_money", "f_labor", "f_inv")      # what the person phase changes of the firms' inputs
 
 
-def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", sides=("persons", "firms")):
+CONSUME_SNAPSHOT = {"c_money": "p_money", "c_labor": "p_labor", "c_inv": "p_inv"}   # the consumption decision's inputs
+
+
+def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", sides=("persons", "consume", "firms")):
     """Forward of the 11 nets for every agent of every economy + sampling with the given draws.
     Differentiable when autograd is enabled (the trainer re-evaluates recorded steps with it).
 
@@ -342,9 +345,10 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
     reference does (decisionNetHandler.cpp:31-32: the quadratic term of the log-density then has zero
     gradient, only -log sigma trains); "score_function" detaches the sample (the textbook estimator).
 
-    sides: evaluate only the persons' or only the firms' nets (two-phase stepping decides the firms after the
-    person phase has run; a recorded two-phase step holds the firms' post-person-phase state in its f_* fields,
-    so re-evaluating it with both sides reproduces both).
+    sides: which decisions to evaluate — "persons" (value, job search, purchases), "consume", "firms".  Phase-wise
+    stepping takes the consumption decision after the trades and the firms' decisions after the person phase; a
+    recorded phase-wise step holds those later inputs (c_money / c_labor / c_inv, and the f_* fields), so
+    re-evaluating it with all sides reproduces every decision.
 
     Returns (decoded, info): decoded = agent-major action tensors, info = log-probabilities [E,agents]
     and state values."""
@@ -371,9 +375,9 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
         # agents as rows of 2-D matrices: nn.Linear then runs as ONE addmm with the bias in the GEMM epilogue
         rows = lambda x: x.reshape(-1, x.shape[-1])
 
-        do_p, do_f = "persons" in sides, "firms" in sides
+        do_p, do_c, do_f = "persons" in sides, "consume" in sides, "firms" in sides
         decoded, info, heads = {}, {}, {}
-        if do_p:
+        if do_p or do_c:
             # --- persons
             pidxM, pidxJ = draws["pidxM"], draws["pidxJ"]
             util = torch.cat([st["p_util_tfp"].unsqueeze(1), st["p_util_share"], st["p_util_rho"].unsqueeze(1)], dim=1)
@@ -386,10 +390,16 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
             inv = st["p_inv"].permute(0, 2, 1).to(f32)
             eM, eJ = gather(encM, pidxM, validM), gather(encJ, pidxJ, validJ)
             util, money, labor0, inv = rows(util), rows(money), rows(labor0), rows(inv)
-            heads["p_value"] = nets.valueNet(eM, eJ, util, money, labor0, inv).reshape(E, P)
-            heads["p_job_p"] = nets.laborSearchNet(eJ, util, money, labor0, inv).reshape(E, P, S)
-            heads["p_good_p"] = nets.purchaseNet(eM, util, money, labor0, inv).reshape(E, P, S)
-            heads["cons"] = nets.consumptionNet(util, money, labor0, inv).reshape(E, P, G, 2)
+            if do_p:
+                heads["p_value"] = nets.valueNet(eM, eJ, util, money, labor0, inv).reshape(E, P)
+                heads["p_job_p"] = nets.laborSearchNet(eJ, util, money, labor0, inv).reshape(E, P, S)
+                heads["p_good_p"] = nets.purchaseNet(eM, util, money, labor0, inv).reshape(E, P, S)
+            if do_c:
+                if "c_money" in st:      # phase-wise step: the person's state when it chooses what to consume
+                    money = rows(st["c_money"].to(f32).unsqueeze(-1))
+                    labor0 = rows(st["c_labor"].to(f32).unsqueeze(-1))
+                    inv = rows(st["c_inv"].permute(0, 2, 1).to(f32))
+                heads["cons"] = nets.consumptionNet(util, money, labor0, inv).reshape(E, P, G, 2)
         if do_f:
             # --- firms
             fidxM, fidxJ = draws["fidxM"], draws["fidxJ"]
@@ -411,15 +421,17 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
     if do_p:
         p_job_take, lp_job = sample_bernoulli(heads["p_job_p"].float(), draws["u_job"])
         p_good_take, lp_good = sample_bernoulli(heads["p_good_p"].float(), draws["u_good"])
-        cons_x, lp_cons = sample_logit_normal(heads["cons"].float(), draws["n_cons"], detach)
         decoded.update({"p_job_idx": draws["pidxJ"], "p_job_take": p_job_take & validJ, "p_good_idx": draws["pidxM"],
-                        "p_good_take": p_good_take & validM, "p_consume": cons_x})
+                        "p_good_take": p_good_take & validM})
         info.update({
             "value_person": heads["p_value"].float(),
             "logp_purchase": torch.where(validM.view(E, 1), lp_good, torch.full_like(lp_good, float("nan"))),
             "logp_laborSearch": torch.where(validJ.view(E, 1), lp_job, torch.zeros_like(lp_job)),
-            "logp_consumption": lp_cons.sum(-1),
         })
+    if do_c:
+        cons_x, lp_cons = sample_logit_normal(heads["cons"].float(), draws["n_cons"], detach)
+        decoded["p_consume"] = cons_x
+        info["logp_consumption"] = lp_cons.sum(-1)
     if do_f:
         f_good_take, lp_fgood = sample_bernoulli(heads["f_good_p"].float(), draws["u_fgood"])
         prod_x, lp_prod = sample_logit_normal(heads["prod"].float(), draws["n_prod"], detach)
@@ -454,9 +466,11 @@ class BatchedPolicy:
     def __init__(self, env, nets, generator=None, autocast_dtype=None, fused=False, two_phase=False):
         """fused=True: the residual hidden stacks run through the hand-written kernel (csrc/mlp_stack.cuh, bf16
         tensor-core operands, fp32 accumulate/residual) instead of eager torch — a rollout-only fast mode.
-        two_phase=True: step() runs the person phase first (FASTACE_STEP_PERSONS) and takes the firms' decisions
-        from the state the firms actually see in the reference — after every person has acted: money after sales and
-        hires, inventories after sales, laborHired of this step — then completes the step (FASTACE_STEP_FIRMS)."""
+        two_phase=True (phase-wise stepping): step() runs the persons' trades (FASTACE_STEP_PERSONS_TRADE), takes the
+        consumption decision from each person's money / laborSupplied / inventory after its trades
+        (FASTACE_STEP_PERSONS_CONSUME), then takes the firms' decisions from the state the firms actually see in the
+        reference — after every person has acted: money after sales and hires, inventories after sales, laborHired of
+        this step — and completes the step (FASTACE_STEP_FIRMS)."""
         self.env, self.nets, self.gen, self.autocast_dtype, self.fused = env, nets, generator, autocast_dtype, fused
         self.two_phase = two_phase
         self.E, self.P, self.F, self.G, self.S = env.dims.tuple
@@ -524,7 +538,18 @@ class BatchedPolicy:
         draws = draw(snap, self.S, self.gen)          # the books (and so the index ranges) do not change before the firms post
         decoded, info = self._evaluate(snap, draws, ("persons",))
         self._write(decoded)
-        self.env.time_step(self.packed, phase_out(PERSON_OUT), flags=flags | _abi.STEP_PERSONS)
+        self.env.time_step(self.packed, phase_out(("p_job_ok", "p_good_ok", "old_j_left", "old_j_taken")),
+                           flags=flags | _abi.STEP_PERSONS_TRADE)
+        # consumption: decided from the person's money, laborSupplied and inventory after its trades
+        # (neuralPersonDecisionMaker.cpp:93-111)
+        live = {k: self.state[v] for k, v in CONSUME_SNAPSHOT.items()}
+        if record is not None:
+            live = {k: v.clone() for k, v in live.items()}
+        snap = dict(snap, **live)
+        decoded_c, info_c = self._evaluate(snap, draws, ("consume",))
+        self._write(decoded_c)
+        info.update(info_c)
+        self.env.time_step(self.packed, phase_out(("p_reward",)), flags=flags | _abi.STEP_PERSONS_CONSUME)
         if record is not None:
             for k in FIRM_SNAPSHOT_KEYS:              # the firms' inputs as they stand after the person phase
                 snap[k] = self.state[k].clone()

@@ -256,6 +256,13 @@ typedef struct fastace_step_out {
  * kernels only (not with FASTACE_STEP_SERIAL / FASTACE_STEP_LARGE / the compact encoding). */
 #define FASTACE_STEP_PERSONS 32u
 #define FASTACE_STEP_FIRMS   64u
+/* The person phase itself in two calls: FASTACE_STEP_PERSONS_TRADE runs job search and purchases (reads perm_person,
+ * p_job_*, p_good_*; writes p_*_ok, old_j_*; afterwards p_money / p_inv / p_labor are the persons' money, inventory
+ * and laborSupplied as they stand when they choose what to consume), FASTACE_STEP_PERSONS_CONSUME consumes (reads
+ * p_consume, writes p_reward).  Consumption touches nobody but the person (utilMaxer.cpp:88-92), so deferring it past
+ * the other persons' trades changes nothing: TRADE + CONSUME + FIRMS is bit-identical to one full call. */
+#define FASTACE_STEP_PERSONS_TRADE   128u
+#define FASTACE_STEP_PERSONS_CONSUME 256u
 
 typedef struct fastace_env fastace_env_t;
 

@@ -268,4 +268,28 @@ def test_two_call_step_equals_one_call(oracle):
         H.compare_states(s2, ost, dims)
     with pytest.raises(lib.FastaceError):
         two.time_step_host(act, out2, flags=_abi.IDX_MODULO | _abi.STEP_FIRMS)   # firms need the person phase first
+    # the person phase itself in two calls: trades, then consumption (which touches nobody but the person)
+    for t in range(10, 14):
+        act = scenario.synthetic_actions(dims, seed=53, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
+        out1, out2 = _abi.alloc_host("out", dims), _abi.alloc_host("out", dims)
+        before = one.get_state()
+        one.time_step_host(act, out1, flags=_abi.IDX_MODULO)
+        two.time_step_host(act, {k: out2[k] for k in ("p_job_ok", "p_good_ok", "old_j_left", "old_j_taken")},
+                           flags=_abi.IDX_MODULO | _abi.STEP_PERSONS_TRADE)
+        mid = two.get_state()
+        bought = out2["p_good_ok"].sum()
+        assert np.isclose((mid["p_inv"] - before["p_inv"]).sum(), bought)       # purchases are in, nothing consumed yet
+        assert np.array_equal(mid["p_labor"], 0.5 * out2["p_job_ok"].sum(axis=1))
+        with pytest.raises(lib.FastaceError):
+            two.time_step_host(act, {"f_profit": out2["f_profit"]}, flags=_abi.IDX_MODULO | _abi.STEP_FIRMS)   # consumption is due
+        two.time_step_host(act, {"p_reward": out2["p_reward"]}, flags=_abi.IDX_MODULO | _abi.STEP_PERSONS_CONSUME)
+        two.time_step_host(act, {k: out2[k] for k in ("f_profit", "f_good_ok", "old_m_left", "old_m_taken")},
+                           flags=_abi.IDX_MODULO | _abi.STEP_FIRMS)
+        s1, s2 = one.get_state(), two.get_state()
+        for k in ("p_money", "p_inv", "p_labor", "f_money", "f_inv", "f_labor", "f_last_money", "m_count", "j_count"):
+            assert np.array_equal(s1[k], s2[k], equal_nan=s1[k].dtype.kind == "f"), k
+        for k in ("p_reward", "f_profit", "p_job_ok", "p_good_ok", "f_good_ok"):
+            assert np.array_equal(out1[k], out2[k], equal_nan=out1[k].dtype.kind == "f"), k
+        H.compare_states(s2, s1, dims)
+    assert one.get_time() == two.get_time() == 14
     one.close(); two.close()
