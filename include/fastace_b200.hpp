@@ -183,6 +183,37 @@ public:
         firm_dm_->choose_job_offers(actions_);
         return step_with(actions_, flags);
     }
+    // The same step taken phase by phase, so that every decision maker is asked when the reference would ask it and
+    // sees the state the reference's plugin sees at that point through the read API: persons choose jobs and goods
+    // (state at the start of the step), trade; choose_goods_to_consume sees money / laborSupplied / inventory after
+    // the trades (neuralPersonDecisionMaker.cpp:93-111); the firm plugins see the economy after the person phase
+    // (economy.cpp:118-123).  Bit-identical to time_step() for the same decisions.
+    bool time_step_phased(uint32_t flags = FASTACE_IDX_ABSOLUTE) {
+        if (!person_dm_ || !firm_dm_) { last_error_() = "no decision makers"; return false; }
+        if (!ok(fastace_shuffle_orders(&dims_, seed_, rng_state_.data(), actions_.perm_person.data(),
+                                       actions_.perm_firm.data(), first_step_ ? 1 : 0))) return false;
+        first_step_ = false;
+        const fastace_actions_t av = actions_.view();     // the vectors are sized once: pointers stay valid
+        fastace_step_out_t none{};
+        person_dm_->choose_jobs(actions_);
+        person_dm_->choose_goods(actions_);
+        if (!ok(fastace_env_step_host(env_, &av, &none, flags | FASTACE_STEP_PERSONS_TRADE))) return false;
+        fresh_ = false;
+        person_dm_->choose_goods_to_consume(actions_);
+        fastace_step_out_t pout{};
+        pout.p_reward = p_reward_.data();
+        if (!ok(fastace_env_step_host(env_, &av, &pout, flags | FASTACE_STEP_PERSONS_CONSUME))) return false;
+        fresh_ = false;
+        firm_dm_->choose_goods(actions_);
+        firm_dm_->choose_production_inputs(actions_);
+        firm_dm_->choose_good_offers(actions_);
+        firm_dm_->choose_job_offers(actions_);
+        fastace_step_out_t fout{};
+        fout.f_profit = f_profit_.data();
+        if (!ok(fastace_env_step_host(env_, &av, &fout, flags | FASTACE_STEP_FIRMS))) return false;
+        fresh_ = false;
+        return true;
+    }
     // the same step with caller-provided decisions and visiting orders
     bool step_with(const StepActions& a, uint32_t flags = FASTACE_IDX_ABSOLUTE) {
         fastace_actions_t av = a.view();

@@ -28,7 +28,16 @@ public:
     explicit RandomPerson(uint64_t seed) : rng(seed) {}
     void choose_jobs(StepActions& a) override { draw(a.p_job_idx, a.p_job_take, /*jobs=*/true); }
     void choose_goods(StepActions& a) override { draw(a.p_good_idx, a.p_good_take, false); }
-    void choose_goods_to_consume(StepActions& a) override { for (auto& x : a.p_consume) x = rng.uniform(); }
+    void choose_goods_to_consume(StepActions& a) override {
+        auto econ = parent.lock();
+        const auto& d = econ->dims();
+        for (auto& x : a.p_consume) x = rng.uniform();
+        // in phased mode this is called after the trades: what the plugin reads is the post-trade inventory
+        seen_inventory = econ->person_inventory(0, 0, 0) + econ->person_inventory(d.num_econ - 1, d.num_persons - 1, 1);
+        seen_labor = 0.0;
+        for (int p = 0; p < d.num_persons; p++) seen_labor += econ->person_laborSupplied(0, p);
+    }
+    double seen_inventory = 0.0, seen_labor = 0.0;
 private:
     void draw(std::vector<int32_t>& idx, std::vector<uint8_t>& take, bool jobs) {
         auto econ = parent.lock();
@@ -105,7 +114,8 @@ int main(int argc, char** argv) {
     fastace_custom_scenario_params_t params = create_scenario_params(P, F);
     std::vector<double> discount;
     expect(economy->setup(params, &discount), "setup", 0);
-    economy->set_decision_makers(std::make_shared<RandomPerson>(1), std::make_shared<RandomFirm>(2));
+    auto persons = std::make_shared<RandomPerson>(1);
+    economy->set_decision_makers(persons, std::make_shared<RandomFirm>(2));
 
     // the checker's copy of the world
     HostState ref = economy->state();
@@ -116,8 +126,11 @@ int main(int argc, char** argv) {
     for (double m : ref.f_money) money0 += m;
 
     unsigned long trades = 0;
+    double labour_seen_by_consumption = 0.0;
     for (unsigned t = 0; t < steps; t++) {
-        expect(economy->time_step(), "time_step", (int)t);
+        // odd steps phase by phase (plugins asked when the reference would ask them), even steps in one call
+        expect((t & 1) ? economy->time_step_phased() : economy->time_step(), "time_step", (int)t);
+        if (t & 1) labour_seen_by_consumption += persons->seen_labor;
         expect(economy->get_time() == t + 1, "get_time", (int)t);
         // oracle on the same decisions and visiting orders
         fastace_actions_t av = economy->last_actions().view();
@@ -166,6 +179,7 @@ int main(int argc, char** argv) {
     for (double m : economy->state().f_money) money1 += m;
     expect(std::fabs(money1 - money0) <= 1e-9 * money0, "money is conserved", (int)steps);
     expect(economy->get_jobMarket(0).size() > 0 || economy->get_market(0).size() > 0, "markets populated", (int)steps);
+    expect(labour_seen_by_consumption > 0.0, "phased mode: choose_goods_to_consume saw this step's laborSupplied", (int)steps);
 
     if (failures) { std::printf("%d failure(s)\n", failures); return 1; }
     std::printf("OK: %u economies x %u steps through fastace::BatchedEconomy matched the oracle\n", E, steps);
