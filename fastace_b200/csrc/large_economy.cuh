@@ -35,6 +35,9 @@ namespace fastace {
 constexpr uint32_t kNoEntry = 0xFFFFFFFFu;
 constexpr uint32_t kReqMask = (1u << 27) - 1u;   // request id in the sort value; bits 27.. = 0 job, 1+g goods of good g
 constexpr int kLargeThreads = 256;
+// first guess of the iteration: false = every request is granted; true = every taken request is made and the firms
+// answer that (capacity-limited availability), which the requesters then refine
+constexpr bool kPessimisticStart = false;   // measured at config D: 9 rounds + the extra pass vs 8 rounds
 
 struct LargeScratch {
     int32_t* rank_f;       // [F]   visiting rank of firm f this step
@@ -130,8 +133,8 @@ __global__ void large_prep_persons(const LargeParams lp) {
     if (phase == 0) { if (p.ac.p_job_take[a]) n = large_map_index(p.ac.p_job_idx[a], p.st.j_count[0], p.flags); }
     else            { if (p.ac.p_good_take[a]) n = large_map_index(p.ac.p_good_idx[a], p.st.m_count[0], p.flags); }
     lp.sc.req_n[req] = n;
-    lp.sc.want[req] = 0;
-    lp.sc.ok[req] = (n != kNoEntry);     // optimistic start
+    lp.sc.want[req] = (n != kNoEntry) && kPessimisticStart;
+    lp.sc.ok[req] = (n != kNoEntry);     // optimistic start (replaced by a firm pass when kPessimisticStart)
     if (n == kNoEntry) { lp.sc.key_in[t] = 0xFFFFu; lp.sc.val_in[t] = req; return; }
     const int firm = phase == 0 ? p.st.j_owner[n] : p.st.m_owner[n];
     const uint32_t type = phase == 0 ? 0u : 1u + (uint32_t)p.st.m_good[n];
@@ -169,7 +172,7 @@ __global__ void large_index_events(const LargeParams lp) {
     const size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n) return;
     const bool valid = lp.sc.key_out[pos] != 0xFFFFu;
-    lp.sc.want_sorted[pos] = 0;
+    lp.sc.want_sorted[pos] = valid && kPessimisticStart;
     lp.sc.ok_sorted[pos] = valid;
     if (valid) lp.sc.req_pos[lp.sc.val_out[pos] & kReqMask] = (uint32_t)pos;
 }
@@ -383,6 +386,10 @@ __global__ void __launch_bounds__(kLargeThreads, 3) large_iterate_persons(const 
     const int P = lp.sp.P, F = lp.sp.F;
     volatile int* flags = lp.sc.changed;
     int round = 0;
+    if (kPessimisticStart) {
+        for (int f = warp; f < F; f += nwarps) { lp.sc.dirty_firm[f] = 1; large_firm_body<G>(lp, f, lane); }
+        grid.sync();
+    }
     while (round < max_rounds) {
         if (tid == 0) flags[(round + 1) % 3] = 0;
         for (int pid = tid; pid < P; pid += nthreads) large_person_body<G>(lp, pid);
