@@ -154,6 +154,7 @@ struct fastace_env {
     uint64_t prof_steps;
     // large-economy path (large_economy.cuh)
     bool large_only;          // dims beyond the warp-per-economy kernels: every step takes the large path
+    bool mid_large;           // the phase-wise step in progress runs on the large-economy path
     int mid_step;             // 0 between steps; 1 after PERSONS_TRADE (CONSUME is due); 2 after the person phase (FIRMS is due)
     bool have_large;
     int large_coop_blocks_p, large_coop_blocks_f;   // co-resident CTAs of the two cooperative iteration kernels
@@ -466,71 +467,85 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
         lp.sc = env->large_sc;
         lp.G = G;
         const LargeScratch& sc = lp.sc;
-        const size_t n_index = std::max((size_t)(cap > F ? cap : F), (size_t)P);
-        large_index_books<<<blocks(n_index), T, 0, stream>>>(lp);
-        large_index_books2<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
-        env->launches += 2;
-        // ---- person phase
+        const bool ph_p = (flags & FASTACE_STEP_PERSONS) != 0, ph_t = (flags & FASTACE_STEP_PERSONS_TRADE) != 0;
+        const bool ph_c = (flags & FASTACE_STEP_PERSONS_CONSUME) != 0, ph_f = (flags & FASTACE_STEP_FIRMS) != 0;
+        const bool run_trades = !ph_c && !ph_f;           // job search + purchases
+        const bool run_consume = !ph_t && !ph_f;          // consumption (with the trades, or on its own after TRADE)
+        const bool run_firms = !ph_p && !ph_t && !ph_c;
         const size_t R = (size_t)2 * S * P;
-        FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed, 0, 32, stream));
-        if (R > 0) {
-            large_prep_persons<<<blocks(R), T, 0, stream>>>(lp);
-            size_t bytes = sc.cub_bytes;
-            FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sc.cub_temp, bytes, sc.key_in, sc.key_out, sc.val_in, sc.val_out,
-                                                               (int)R, 0, 16, stream));
+        if (run_trades) {
+            const size_t n_index = std::max((size_t)(cap > F ? cap : F), (size_t)P);
+            large_index_books<<<blocks(n_index), T, 0, stream>>>(lp);
+            large_index_books2<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
             env->launches += 2;
+            // ---- person phase
+            FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed, 0, 32, stream));
+            if (R > 0) {
+                large_prep_persons<<<blocks(R), T, 0, stream>>>(lp);
+                size_t bytes = sc.cub_bytes;
+                FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sc.cub_temp, bytes, sc.key_in, sc.key_out, sc.val_in, sc.val_out,
+                                                                   (int)R, 0, 16, stream));
+                env->launches += 2;
+            }
+            large_scan<<<1, 1024, 0, stream>>>(sc.hist, sc.seg, F);
+            env->launches += 1;
+            if (R > 0) {
+                large_index_events<<<blocks(R), T, 0, stream>>>(lp);
+                env->launches += 1;
+            }
+            {
+                // requester pass / firm pass rounds until nothing changes: ONE cooperative launch, no host round trip
+                int max_rounds = kMaxRounds;
+                void* args[] = {(void*)&lp, (void*)&max_rounds};
+                const size_t want_blocks = std::max<size_t>(blocks(P), blocks((size_t)F * 32));
+                const int grid = (int)std::min<size_t>(std::max<size_t>(want_blocks, 1), (size_t)env->large_coop_blocks_p);
+                FASTACE_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lk.iterate_persons, dim3(grid), dim3(T), args, 0, stream));
+                env->launches += 1;
+            }
+            large_old_jobs<<<blocks(F), T, 0, stream>>>(lp);
+            env->launches += 1;
+            if (S > 0 && P > 0 && (lp.sp.out.p_job_ok || lp.sp.out.p_good_ok)) {
+                large_person_flags<<<blocks((size_t)S * P), T, 0, stream>>>(lp);
+                env->launches += 1;
+            }
+            if (!run_firms) {   // phase-wise: the firms as they stand after the person phase become visible
+                large_publish_firms<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
+                env->launches += 1;
+            }
         }
-        large_scan<<<1, 1024, 0, stream>>>(sc.hist, sc.seg, F);
-        env->launches += 1;
-        if (R > 0) {
-            large_index_events<<<blocks(R), T, 0, stream>>>(lp);
+        if ((run_trades || run_consume) && P > 0) {
+            lk.finalize_persons<<<blocks(P), T, 0, stream>>>(lp);   // trades and/or consumption, by the call's flags
             env->launches += 1;
         }
-        {
-            // requester pass / firm pass rounds until nothing changes: ONE cooperative launch, no host round trip
-            int max_rounds = kMaxRounds;
-            void* args[] = {(void*)&lp, (void*)&max_rounds};
-            const size_t want_blocks = std::max<size_t>(blocks(P), blocks((size_t)F * 32));
-            const int grid = (int)std::min<size_t>(std::max<size_t>(want_blocks, 1), (size_t)env->large_coop_blocks_p);
-            FASTACE_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lk.iterate_persons, dim3(grid), dim3(T), args, 0, stream));
-            env->launches += 1;
+        if (run_firms) {
+            // ---- firm phase
+            const size_t RF = (size_t)S * F;
+            large_index_firms<<<blocks(F), T, 0, stream>>>(lp);
+            FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed + 4, 0, 16, stream));
+            if (RF > 0) {
+                large_prep_firms<<<blocks(RF), T, 0, stream>>>(lp);
+                size_t bytes = sc.cub_bytes;
+                FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sc.cub_temp, bytes, sc.fkey_in, sc.fkey_out, sc.fval_in, sc.fval_out,
+                                                                   (int)RF, 0, 16, stream));
+                env->launches += 2;
+            }
+            large_scan<<<1, 1024, 0, stream>>>(sc.fhist, sc.fseg, F);
+            {
+                int max_rounds = kMaxRounds;
+                void* args[] = {(void*)&lp, (void*)&max_rounds};
+                const int grid = (int)std::min<size_t>(std::max<size_t>(blocks(F), 1), (size_t)env->large_coop_blocks_f);
+                FASTACE_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lk.iterate_firms, dim3(grid), dim3(T), args, 0, stream));
+            }
+            env->launches += 3;
+            if (RF > 0 && lp.sp.out.f_good_ok)
+                FASTACE_CUDA_CHECK(cudaMemcpyAsync(lp.sp.out.f_good_ok, sc.fok, RF, cudaMemcpyDeviceToDevice, stream));
+            lk.finalize_firms<<<blocks(cap), T, 0, stream>>>(lp);
+            large_post_scan<<<1, 1024, 0, stream>>>(lp);
+            large_post_write<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
+            env->launches += 3;
         }
-        if (P > 0) {
-            lk.finalize_persons<<<blocks(P), T, 0, stream>>>(lp);
-            env->launches += 1;
-        }
-        large_old_jobs<<<blocks(F), T, 0, stream>>>(lp);
-        env->launches += 1;
-        if (S > 0 && P > 0 && (lp.sp.out.p_job_ok || lp.sp.out.p_good_ok)) {
-            large_person_flags<<<blocks((size_t)S * P), T, 0, stream>>>(lp);
-            env->launches += 1;
-        }
-        // ---- firm phase
-        const size_t RF = (size_t)S * F;
-        if (RF > 0) {
-            large_prep_firms<<<blocks(RF), T, 0, stream>>>(lp);
-            size_t bytes = sc.cub_bytes;
-            FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sc.cub_temp, bytes, sc.fkey_in, sc.fkey_out, sc.fval_in, sc.fval_out,
-                                                               (int)RF, 0, 16, stream));
-            env->launches += 2;
-        }
-        large_scan<<<1, 1024, 0, stream>>>(sc.fhist, sc.fseg, F);
-        {
-            int max_rounds = kMaxRounds;
-            void* args[] = {(void*)&lp, (void*)&max_rounds};
-            const int grid = (int)std::min<size_t>(std::max<size_t>(blocks(F), 1), (size_t)env->large_coop_blocks_f);
-            FASTACE_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lk.iterate_firms, dim3(grid), dim3(T), args, 0, stream));
-        }
-        env->launches += 2;
-        if (RF > 0 && lp.sp.out.f_good_ok)
-            FASTACE_CUDA_CHECK(cudaMemcpyAsync(lp.sp.out.f_good_ok, sc.fok, RF, cudaMemcpyDeviceToDevice, stream));
-        lk.finalize_firms<<<blocks(cap), T, 0, stream>>>(lp);
-        large_post_scan<<<1, 1024, 0, stream>>>(lp);
-        large_post_write<<<blocks(cap > F ? cap : F), T, 0, stream>>>(lp);
-        env->launches += 3;
         FASTACE_CUDA_CHECK(cudaGetLastError());
     }
-    env->time += 1;
     return FASTACE_OK;
 }
 
@@ -542,8 +557,8 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
     const bool ph_t = (flags & FASTACE_STEP_PERSONS_TRADE) != 0, ph_c = (flags & FASTACE_STEP_PERSONS_CONSUME) != 0;
     const bool only_p = ph_p || ph_t || ph_c;          // some part of the person phase, no firm phase
     if ((int)ph_p + (int)ph_t + (int)ph_c + (int)only_f > 1) { set_error("the phase flags are separate calls"); return FASTACE_ERR_INVALID; }
-    if ((only_p || only_f) && (dcz || (flags & (FASTACE_STEP_SERIAL | FASTACE_STEP_LARGE)) || env->large_only)) {
-        set_error("phase-wise stepping is implemented by the warp-per-economy kernels with the int32 action encoding");
+    if ((only_p || only_f) && (dcz || (flags & FASTACE_STEP_SERIAL))) {
+        set_error("phase-wise stepping takes the int32 action encoding and is not implemented by the serial kernel");
         return FASTACE_ERR_INVALID;
     }
     {
@@ -578,8 +593,20 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
     }
     if (env->large_only || (flags & FASTACE_STEP_LARGE)) {
         if (dcz) { set_error("the large-economy path takes the int32 action encoding"); return FASTACE_ERR_INVALID; }
-        return launch_step_large(env, dact, dout, flags, stream);
+        if (env->mid_step != 0 && !env->mid_large) { set_error("a phase-wise step must be finished on the path it was started on"); return FASTACE_ERR_INVALID; }
+        if ((only_p || only_f) && env->dims.num_econ != 1) {
+            set_error("phase-wise stepping on the large-economy path needs num_econ == 1 (its scratch holds one economy between calls)");
+            return FASTACE_ERR_INVALID;
+        }
+        const int rc = launch_step_large(env, dact, dout, flags, stream);
+        if (rc != FASTACE_OK) return rc;
+        if (ph_t) env->mid_step = 1;
+        else if (only_p) env->mid_step = 2;
+        else { env->mid_step = 0; env->time += 1; }
+        env->mid_large = env->mid_step != 0;
+        return FASTACE_OK;
     }
+    if (env->mid_step != 0 && env->mid_large) { set_error("a phase-wise step must be finished on the path it was started on"); return FASTACE_ERR_INVALID; }
     StepParams sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.E = env->dims.num_econ; sp.P = env->dims.num_persons; sp.F = env->dims.num_firms; sp.S = env->dims.stack_size;

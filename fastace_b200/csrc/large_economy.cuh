@@ -104,10 +104,7 @@ __global__ void large_index_books(const LargeParams lp) {
     const int F = p.F, G = lp.G, cap = F * G;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < cap) lp.sc.own_offer[t] = -1;
-    if (t < F) {
-        lp.sc.own_job[t] = -1; lp.sc.hist[t] = 0; lp.sc.fhist[t] = 0; lp.sc.rank_f[p.ac.perm_firm[t]] = t;
-        lp.sc.dirty_firm[t] = 1;
-    }
+    if (t < F) { lp.sc.own_job[t] = -1; lp.sc.hist[t] = 0; lp.sc.dirty_firm[t] = 1; }
     if (t < p.P) lp.sc.dirty_person[t] = 1;
 }
 __global__ void large_index_books2(const LargeParams lp) {
@@ -117,6 +114,21 @@ __global__ void large_index_books2(const LargeParams lp) {
     if (t < p.st.m_count[0]) lp.sc.own_offer[p.st.m_owner[t] * G + p.st.m_good[t]] = t;
     if (t < p.st.j_count[0]) lp.sc.own_job[p.st.j_owner[t]] = t;
     (void)F;
+}
+
+// firm-phase prologue: visiting ranks of the firms, cleared histogram
+__global__ void large_index_firms(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < p.F) { lp.sc.fhist[t] = 0; lp.sc.rank_f[p.ac.perm_firm[t]] = t; }
+}
+// after the person phase of a phase-wise step: the firms as they stand now, visible in the state arrays
+__global__ void large_publish_firms(const LargeParams lp) {
+    const StepParams& p = lp.sp;
+    const int F = p.F, G = lp.G;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < F) { p.st.f_money[t] = lp.sc.fm_money[t]; p.st.f_labor[t] = lp.sc.fm_labor[t]; }
+    if (t < F * G) p.st.f_inv[t] = lp.sc.fm_inv[t];
 }
 
 // ---- person phase: requests enumerated in the reference's order (rank, jobs before goods, slot) --------------
@@ -413,13 +425,27 @@ __global__ void large_finalize_persons(const LargeParams lp) {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= P) return;
     const double labor = kLaborPerOffer * (double)lp.sc.pm_hires[pid];
+    if (p.flags & FASTACE_STEP_PERSONS_TRADE) {      // trades into the state; consumption follows in its own call
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const size_t k = (size_t)g * P + pid;
+            double v = p.st.p_inv[k];
+            const int nb = lp.sc.pm_bought[k];
+            for (int q = 0; q < nb; q++) v += kAmountPerOffer;
+            p.st.p_inv[k] = v;
+        }
+        p.st.p_money[pid] = lp.sc.pm_money[pid];
+        p.st.p_labor[pid] = labor;
+        return;
+    }
+    const bool applied = (p.flags & FASTACE_STEP_PERSONS_CONSUME) != 0;   // purchases are already in p_inv
     double x[G + 1], inv[G];
     x[0] = 1 - labor;
 #pragma unroll
     for (int g = 0; g < G; g++) {
         const size_t k = (size_t)g * P + pid;
         double v = p.st.p_inv[k];
-        const int nb = lp.sc.pm_bought[k];
+        const int nb = applied ? 0 : lp.sc.pm_bought[k];
         for (int q = 0; q < nb; q++) v += kAmountPerOffer;
         const double c = v * (double)p.ac.p_consume[k];
         x[g + 1] = c;

@@ -252,8 +252,8 @@ typedef struct fastace_step_out {
  * the person members of `actions`, writes p_reward, p_*_ok, old_j_*); FASTACE_STEP_FIRMS, which must follow it, runs
  * the firm phase (reads perm_firm and the f_* members, writes f_profit, f_good_ok, old_m_*) and completes the step
  * (time advances here); give each call only its own output arrays (the others NULL).  The two calls together give
- * bit-identical results to one full call.  Warp-per-economy
- * kernels only (not with FASTACE_STEP_SERIAL / FASTACE_STEP_LARGE / the compact encoding). */
+ * bit-identical results to one full call.  Not with FASTACE_STEP_SERIAL or the compact encoding; on the large-economy
+ * path for single-economy envs (num_econ == 1). */
 #define FASTACE_STEP_PERSONS 32u
 #define FASTACE_STEP_FIRMS   64u
 /* The person phase itself in two calls: FASTACE_STEP_PERSONS_TRADE runs job search and purchases (reads perm_person,

@@ -99,3 +99,35 @@ def test_large_path_extreme_actions(oracle):
         H.compare_outputs(gout, oout, dims, before)
         H.compare_states(env.get_state(), ost, dims)
     env.close()
+
+
+@pytest.mark.parametrize("dims", [(1, 100, 10, 2, 10), (1, 3000, 100, 4, 10)])
+def test_large_path_phase_wise_equals_one_call(oracle, dims):
+    """TRADE + CONSUME + FIRMS (and PERSONS + FIRMS) on the large-economy path == one call, bit for bit"""
+    from fastace_b200.env import BatchedEconomy
+    state = scenario.generic_initial_state(dims, 7) if dims[3] != 2 else scenario.custom_initial_state(dims, 7)[0]
+    one, two = BatchedEconomy(dims), BatchedEconomy(dims)
+    one.set_state(state); two.set_state(state)
+    orders = scenario.OrderStream(dims, 8)
+    base = _abi.IDX_MODULO | LARGE
+    for t in range(8):
+        act = scenario.synthetic_actions(dims, seed=9, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
+        out1, out2 = _abi.alloc_host("out", dims), _abi.alloc_host("out", dims)
+        one.time_step_host(act, out1, flags=base)
+        person_flags = ("p_job_ok", "p_good_ok", "old_j_left", "old_j_taken")
+        if t % 2 == 0:
+            two.time_step_host(act, {k: out2[k] for k in person_flags}, flags=base | _abi.STEP_PERSONS_TRADE)
+            mid = two.get_state()
+            assert np.array_equal(mid["p_labor"], 0.5 * out2["p_job_ok"].sum(axis=1))
+            two.time_step_host(act, {"p_reward": out2["p_reward"]}, flags=base | _abi.STEP_PERSONS_CONSUME)
+        else:
+            two.time_step_host(act, {k: out2[k] for k in person_flags + ("p_reward",)}, flags=base | _abi.STEP_PERSONS)
+        mid = two.get_state()
+        assert np.array_equal(mid["p_money"], one.get_state()["p_money"]) and two.get_time() == t
+        two.time_step_host(act, {k: out2[k] for k in ("f_profit", "f_good_ok", "old_m_left", "old_m_taken")}, flags=base | _abi.STEP_FIRMS)
+        s1, s2 = one.get_state(), two.get_state()
+        for k in s1:
+            assert np.array_equal(s1[k], s2[k], equal_nan=s1[k].dtype.kind == "f"), (k, t)
+        for k in ("p_reward", "f_profit", "p_job_ok", "p_good_ok", "f_good_ok"):
+            assert np.array_equal(out1[k], out2[k], equal_nan=out1[k].dtype.kind == "f"), (k, t)
+    one.close(); two.close()
