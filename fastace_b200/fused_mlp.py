@@ -1,6 +1,7 @@
 """Host side of the fused residual tanh stack (csrc/mlp_stack.cuh) — rollout-only fast path of the decision nets.
 Library boundary: fastace_mlp_residual_tanh_stack in include/fastace_b200.h; torch is only the tensor container."""
 import ctypes as C
+import weakref
 
 import torch
 
@@ -22,7 +23,8 @@ def pack_layers(layers):
     key = tuple(id(l) for l in layers)
     ver = tuple((l.weight._version, l.bias._version, l.weight.data_ptr()) for l in layers)
     hit = _cache.get(key)
-    if hit is not None and hit[0] == ver:
+    # ids (and device addresses) are reused once a module is freed: an entry counts only for the very same live objects
+    if hit is not None and hit[0] == ver and all(r() is l for r, l in zip(hit[3], layers)):
         return hit[1], hit[2]
     H = layers[0].in_features
     assert all(l.in_features == H and l.out_features == H for l in layers), "residual stack needs square layers"
@@ -33,7 +35,7 @@ def pack_layers(layers):
         w[:, :H, :H] = torch.stack([l.weight for l in layers]).to(torch.bfloat16)
         b = torch.zeros(len(layers), np_, dtype=torch.float32, device=dev)
         b[:, :H] = torch.stack([l.bias for l in layers]).float()
-    _cache[key] = (ver, w, b)
+    _cache[key] = (ver, w, b, [weakref.ref(l) for l in layers])
     return w, b
 
 
@@ -52,7 +54,7 @@ def _pack_edge(layer, rows_pad, cols_pad, key):
     """one Linear as zero-padded bf16 [rows_pad][cols_pad] + fp32 bias [rows_pad]; cached like pack_layers"""
     ver = (layer.weight._version, layer.bias._version, layer.weight.data_ptr())
     hit = _cache.get((key, id(layer)))
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and hit[3]() is layer:
         return hit[1], hit[2]
     o, i = layer.weight.shape
     with torch.no_grad():
@@ -60,7 +62,7 @@ def _pack_edge(layer, rows_pad, cols_pad, key):
         w[:o, :i] = layer.weight.to(torch.bfloat16)
         b = torch.zeros(rows_pad, dtype=torch.float32, device=layer.weight.device)
         b[:o] = layer.bias.float()
-    _cache[(key, id(layer))] = (ver, w, b)
+    _cache[(key, id(layer))] = (ver, w, b, weakref.ref(layer))
     return w, b
 
 
