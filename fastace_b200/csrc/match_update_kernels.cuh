@@ -108,7 +108,7 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
 // SMAX: compile-time bound of the stack size S (12 or 16): request lists live in SMAX/4 registers
 // per list and the evaluation is fully unrolled over SMAX slots.
 template <int G, int SMAX>
-__global__ void __launch_bounds__(32, 32) match_kernel(const MatchParams mp) {
+__global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     extern __shared__ __align__(16) unsigned char smem[];
     const StepParams& p = mp.sp;
     const int e = blockIdx.x;
