@@ -340,3 +340,33 @@ def test_value_nets_learn_on_env_episodes():
         assert np.isfinite(a2c.train_on_episode(ep))
     assert errs[-1] < 0.9 * errs[0] and min(errs[5:]) < min(errs[:3]), errs
     env.close()
+
+
+@pytest.mark.gpu
+def test_cuda_training_gradients_match_the_reference(gold):
+    """the reference-pinned episode trained on the GPU: loss and every gradient against the reference's own
+    (the CPU tests pin the same numbers; this covers the CUDA autograd path the trainer really runs on)"""
+    z, cfg = gold
+    case = _sub(z, "market/")
+    nets, _ = build(case, cfg)
+    epi, _ = episode_for(case, cfg, nets, 0)
+    nets.cuda()
+    a2c = trainer.AdvantageActorCritic(nets, lr=1e-4, discount=float(case["discount"]))
+    dev = lambda d: {k: v.cuda() for k, v in d.items()}
+    epi.steps = [(dev(a), dev(b)) for a, b in epi.steps]
+    for name in ("value_person", "value_firm", "p_reward", "f_profit"):
+        setattr(epi, name, [x.cuda() for x in getattr(epi, name)])
+    epi.finite = epi.finite.cuda()
+    loss = a2c.train_on_episode(epi)
+    assert abs(loss - float(case["ep0/loss"])) <= 2e-4 * abs(float(case["ep0/loss"])) + 1e-4
+    grads = _sub(case, "ep0/grad/")
+    checked = 0
+    for net in policy.NET_NAMES:
+        for pname, p in nets.net(net).named_parameters():
+            if p.grad is None:
+                continue
+            key = f"{net}/{pname}"
+            scale = max(np.abs(grads[key]).max(), 1e-6)
+            assert np.abs(p.grad.cpu().numpy() - grads[key]).max() <= 2e-4 * scale, key
+            checked += 1
+    assert checked > 100
