@@ -16,6 +16,7 @@
 #include "match_update_kernels.cuh"
 #include "large_economy.cuh"
 #include "mlp_stack.cuh"
+#include "layer_kernels.cuh"
 
 namespace fastace {
 
@@ -889,6 +890,26 @@ int fastace_mlp_forward(const fastace_mlp_desc_t* d, void* cuda_stream) {
     if (d->x0) { mp.x0 = d->x0; mp.K0 = d->in_features; mp.K0P = (d->in_features + 15) / 16 * 16 + 8; mp.w0 = d->w0_bf16; mp.b0 = d->b0; }
     if (d->out) { mp.out = d->out; mp.NOUT = d->out_features; mp.act = d->activation; mp.wl = d->wl_bf16; mp.bl = d->bl; }
     return dispatch_mlp(mp, nt, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int fastace_layer_forward(const float* z, const float* bias, const float* x, float* y, float* t, int64_t rows, int hidden,
+                          void* cuda_stream) {
+    if (!z || !bias || !y || !t || rows < 0 || hidden < 1) { set_error("bad argument"); return FASTACE_ERR_INVALID; }
+    const long long n = (long long)rows * hidden;
+    if (n == 0) return FASTACE_OK;
+    const unsigned blocks = (unsigned)((n / 4 + 1 + 255) / 256);
+    layer_forward_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(z, bias, x, y, t, n, hidden);
+    FASTACE_CUDA_CHECK(cudaGetLastError());
+    return FASTACE_OK;
+}
+
+int fastace_layer_backward(const float* dy, const float* t, float* dz, int64_t n, void* cuda_stream) {
+    if (!dy || !t || !dz || n < 0) { set_error("bad argument"); return FASTACE_ERR_INVALID; }
+    if (n == 0) return FASTACE_OK;
+    const unsigned blocks = (unsigned)((n / 4 + 1 + 255) / 256);
+    layer_backward_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(dy, t, dz, (long long)n);
+    FASTACE_CUDA_CHECK(cudaGetLastError());
+    return FASTACE_OK;
 }
 
 int fastace_env_large_stats(const fastace_env_t* env, uint32_t* person_rounds, uint32_t* firm_rounds) {

@@ -29,6 +29,7 @@ def _xavier(module):
 
 
 _FUSED = False    # set by BatchedPolicy(fused=True) around its no-grad forward: residual stacks run as one CUDA kernel
+_TRAIN_LAYERS = False   # set by the trainer: autograd layers with hand-written element-wise halves (train_layers.py)
 
 
 def _residual_stack(x, layers):
@@ -37,6 +38,12 @@ def _residual_stack(x, layers):
             and x.shape[-1] <= 128 and all(h.in_features == h.out_features == x.shape[-1] for h in layers)):
         from . import fused_mlp
         return fused_mlp.residual_tanh_stack(x, layers)
+    if _TRAIN_LAYERS and len(layers) > 0:
+        from . import train_layers
+        if train_layers.usable(x):
+            for h in layers:
+                x = train_layers.tanh_layer(x, h, True)
+            return x
     for h in layers:
         x = x + torch.tanh(h(x))
     return x
@@ -49,7 +56,11 @@ def _body(x, first, layers, last, activation=None):
         if fused_mlp.supports(first, layers, last, x):
             return fused_mlp.net_forward(x, first, layers, last, activation)
     if first is not None:
-        x = torch.tanh(first(x))
+        if _TRAIN_LAYERS:
+            from . import train_layers
+            x = train_layers.tanh_layer(x, first, False) if train_layers.usable(x) else torch.tanh(first(x))
+        else:
+            x = torch.tanh(first(x))
     x = _residual_stack(x, layers)
     if last is None:
         return x

@@ -135,7 +135,8 @@ class AdvantageActorCritic:
                  multiplierForLRDecay=DEFAULT_MULTIPLIER_FOR_LR_DECAY,
                  cosinePeriod=DEFAULT_REVERSE_ANNEALING_PERIOD,
                  discount=0.9, wiring="reference", sign="reference", sample_grad="reference",
-                 autocast_dtype=None, process_group=None, adam_kwargs=None, nan_policy="drop_economy"):
+                 autocast_dtype=None, process_group=None, adam_kwargs=None, nan_policy="drop_economy",
+                 fused_layers=True):
         """lrs: optional {net name: lr} (TrainingParams.purchaseNetLR ..., neuralScenarios.h:173-181).
         nan_policy: the reference abandons an episode whose loss is NaN and reloads its last checkpoint
         (neuralScenarios.cpp:229-243).  With E episodes per update the equivalent is "drop_economy": economies
@@ -143,6 +144,8 @@ class AdvantageActorCritic:
         runs over the kept ones; `last_dropped` counts them); "propagate" keeps them and returns NaN like the
         reference."""
         self.nan_policy, self.last_dropped = nan_policy, 0
+        # CUDA re-evaluation through train_layers.py (fused element-wise halves, split-K weight gradients); CPU / autocast: eager
+        self.fused_layers = fused_layers
         self.nets, self.discount = nets, discount
         self.sign = 1.0 if sign == "reference" else -1.0
         self.sample_grad, self.autocast_dtype, self.group = sample_grad, autocast_dtype, process_group
@@ -226,7 +229,11 @@ class AdvantageActorCritic:
         for t in range(T):
             snap, draws = ep.steps[t]
             with torch.enable_grad():
-                _, info = policy.evaluate(self.nets, snap, draws, self.autocast_dtype, self.sample_grad)
+                policy._TRAIN_LAYERS = self.fused_layers
+                try:
+                    _, info = policy.evaluate(self.nets, snap, draws, self.autocast_dtype, self.sample_grad)
+                finally:
+                    policy._TRAIN_LAYERS = False
                 err = q_p[t] - info["value_person"].double()
                 terms = [self.sign * (_masked(info["logp_purchase"]) * adv_p[t]).sum(),
                          self.sign * (_masked(info["logp_laborSearch"]) * adv_p[t]).sum(),

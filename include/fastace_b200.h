@@ -348,6 +348,13 @@ typedef struct fastace_mlp_desc {
 } fastace_mlp_desc_t;
 int fastace_mlp_forward(const fastace_mlp_desc_t* desc, void* cuda_stream);
 
+/* Training-time layer halves (fp32, DEVICE pointers): forward  y = [x +] tanh(z + bias), t = tanh(z + bias)  for the
+ * [rows][hidden] GEMM output z (x NULL: no residual); backward  dz = dy * (1 - t^2)  over n elements.  One
+ * element-wise pass each instead of eager autograd's three per layer and direction (src/neural/decisionNets.cpp). */
+int fastace_layer_forward(const float* z, const float* bias, const float* x, float* y, float* t, int64_t rows, int hidden,
+                          void* cuda_stream);
+int fastace_layer_backward(const float* dy, const float* t, float* dz, int64_t n, void* cuda_stream);
+
 /* ---- legacy entry points of libpybindings.so (src/pybindings.h:8-28) ------------------ */
 /* Byte-identical layouts of neural::CustomScenarioParams (344 B) and
  * neural::TrainingParams (136 B), src/neural/neuralScenarios.h:49-186, py/main.py:12-85. */

@@ -370,3 +370,23 @@ def test_cuda_training_gradients_match_the_reference(gold):
             assert np.abs(p.grad.cpu().numpy() - grads[key]).max() <= 2e-4 * scale, key
             checked += 1
     assert checked > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,K,H,residual", [(20000, 100, 100, True), (20000, 19, 100, False), (8192, 32, 32, True), (37, 9, 16, False)])
+def test_training_layer_matches_eager_autograd(rows, K, H, residual):
+    """train_layers.TanhLayer (csrc/layer_kernels.cuh + split-K weight gradient) against eager autograd, fp32"""
+    from fastace_b200 import train_layers
+    torch.manual_seed(rows + K)
+    lin = torch.nn.Linear(K, H).cuda()
+    x = torch.randn(rows, K, device="cuda", requires_grad=True)
+    gy = torch.randn(rows, H, device="cuda")
+    y0 = (x + torch.tanh(lin(x))) if residual else torch.tanh(lin(x))
+    y0.backward(gy)
+    ref = (x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    x.grad = None; lin.weight.grad = None; lin.bias.grad = None
+    y1 = train_layers.tanh_layer(x, lin, residual)
+    y1.backward(gy)
+    torch.testing.assert_close(y1.detach(), y0.detach(), rtol=1e-6, atol=1e-6)
+    for got, want in zip((x.grad, lin.weight.grad, lin.bias.grad), ref):
+        assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item()
