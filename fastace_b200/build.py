@@ -12,13 +12,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfastace_b200.so")
 SOURCES = [os.path.join(CSRC, "fastace_capi.cu"), os.path.join(CSRC, "fastace_host.cpp")]
-DEPS = SOURCES + [
-    os.path.join(CSRC, "step_kernel.cuh"),
-    os.path.join(CSRC, "match_update_kernels.cuh"),
-    os.path.join(CSRC, "common.cuh"),
-    os.path.join(CSRC, "fastace_internal.h"),
-    os.path.join(HERE, "..", "include", "fastace_b200.h"),
-]
+def _deps():
+    """Every file the library is compiled from: all of csrc/ and the public headers (a stale
+    .so must never travel to the GPU box, so nothing is listed by hand)."""
+    import glob
+    inc = os.path.join(HERE, "..", "include")
+    return sorted(set(SOURCES + glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                      glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cpp")) +
+                      glob.glob(os.path.join(inc, "*.h")) + glob.glob(os.path.join(inc, "*.hpp")) +
+                      [os.path.abspath(__file__)]))
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -41,7 +44,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force=False, verbose=False, extra_flags=()):

@@ -5,7 +5,21 @@
 
 #include "../../include/fastace_b200.h"
 
+// dynamic shared memory of a kernel (tests/emu/warp_emu.h, which runs this source on the CPU for the
+// parity tests of the GPU-less container, substitutes its own block buffer)
+#ifndef FASTACE_DYN_SMEM
+#define FASTACE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+// event counters of the CPU emulation build (how many rounds / re-scans / slow paths a workload takes); nothing
+// on the device
+#ifndef FASTACE_STAT
+#define FASTACE_STAT(which, n)
+#endif
+
 namespace fastace {
+
+enum { kStatWindows, kStatRounds, kStatRescans, kStatRiskyWalks, kStatSalesWindows, kStatDeadExits, kStatFirmSerial, kStatRoundsW0, kStatRoundsW1, kStatRoundsW2, kStatRoundsW3, kStatRescansW0, kStatCount };
 
 struct StepParams {
     int E, P, F, S;
@@ -28,6 +42,7 @@ constexpr double kLargeNumber = 1e8;     // constants::largeNumber (base/constan
 constexpr double kAmountPerOffer = 1.0;  // neural/neuralFirmDecisionMaker.cpp:6
 constexpr double kLaborPerOffer = 0.5;   // neural/neuralFirmDecisionMaker.cpp:7
 constexpr int kNone = 0xFF;
+constexpr int kMaxStack = FASTACE_MAX_STACK;
 
 // (int)double as the x86-64 reference binary does it (cvttsd2si): out-of-range and NaN
 // give INT_MIN, which fails the `numOffers > 0` tests.

@@ -14,6 +14,7 @@
 #include "fastace_internal.h"
 #include "step_kernel.cuh"
 #include "match_update_kernels.cuh"
+#include "shuffle_kernel.cuh"
 #include "large_economy.cuh"
 #include "mlp_stack.cuh"
 #include "layer_kernels.cuh"
@@ -149,6 +150,13 @@ struct fastace_env {
     size_t match_smem_bytes;  // match_kernel
     uint8_t* scr_pnh;         // [E][P]    match_kernel -> update_kernel
     uint8_t* scr_pnb;         // [E][G][P]
+    // visiting orders generated on the device (fastace_env_shuffle_orders)
+    uint64_t* ord_rng;        // [E]    one minstd_rand0 per economy
+    int32_t* ord_person;      // [E][P] cumulative order of the persons
+    int32_t* ord_firm;        // [E][F]
+    bool ord_started;
+    uint32_t* err_host;       // host-mapped error words the kernels raise (match_kernel.cuh: kDevErr*)
+    uint32_t* err_dev;        // the same words as the device sees them
     cudaEvent_t ev[3];        // FASTACE_STEP_PROFILE
     bool have_ev;
     double prof_match_ms, prof_update_ms;
@@ -173,6 +181,19 @@ struct fastace_env {
     } while (0)
 
 using namespace fastace;
+
+// A kernel that could not finish its fixed-point iteration within the round cap leaves a word in host-mapped
+// memory: such a step is an error, never a result.
+static int check_device_errors(const fastace_env_t* env) {
+    if (!env->err_host) return FASTACE_OK;
+    volatile const uint32_t* w = env->err_host;
+    if (w[kDevErrRounds] | w[kDevErrLargeRounds]) {
+        set_error(w[kDevErrRounds] ? "match_kernel: a window's fixed-point iteration hit the round cap (state is not a valid step result)"
+                                   : "large-economy path: the iteration hit the round cap (state is not a valid step result)");
+        return FASTACE_ERR_NOT_CONVERGED;
+    }
+    return FASTACE_OK;
+}
 
 template <typename StructT>
 static int carve(const std::vector<FieldDesc>& fields, StructT* s, void** block, bool zero) {
@@ -278,11 +299,22 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
         cudaError_t e2 = cudaMalloc((void**)&env->scr_pnb, np ? np * d.num_goods : 1);
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
             set_error("cudaMalloc of matching scratch failed");
-            cudaFree(env->state_block); delete env; return FASTACE_ERR_ALLOC;
+            cudaGetLastError();
+            fastace_env_destroy(env); return FASTACE_ERR_ALLOC;
         }
     }
+    {
+        cudaError_t e1 = cudaHostAlloc((void**)&env->err_host, 4 * sizeof(uint32_t), cudaHostAllocMapped);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaHostGetDevicePointer((void**)&env->err_dev, env->err_host, 0) : e1;
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_error("allocation of the device error words failed");
+            cudaGetLastError();
+            fastace_env_destroy(env); return FASTACE_ERR_ALLOC;
+        }
+        std::memset(env->err_host, 0, 4 * sizeof(uint32_t));
+    }
     cudaError_t err = cudaStreamCreateWithFlags(&env->stream, cudaStreamNonBlocking);
-    if (err != cudaSuccess) { set_error(cudaGetErrorString(err)); cudaFree(env->state_block); delete env; return FASTACE_ERR_CUDA; }
+    if (err != cudaSuccess) { set_error(cudaGetErrorString(err)); fastace_env_destroy(env); return FASTACE_ERR_CUDA; }
     *out_env = env;
     return FASTACE_OK;
 }
@@ -304,6 +336,10 @@ int fastace_env_destroy(fastace_env_t* env) {
     if (env->have_ev) for (int i = 0; i < 3; i++) cudaEventDestroy(env->ev[i]);
     if (env->scr_pnh) cudaFree(env->scr_pnh);
     if (env->scr_pnb) cudaFree(env->scr_pnb);
+    if (env->err_host) cudaFreeHost(env->err_host);
+    if (env->ord_rng) cudaFree(env->ord_rng);
+    if (env->ord_person) cudaFree(env->ord_person);
+    if (env->ord_firm) cudaFree(env->ord_firm);
     if (env->large_block) cudaFree(env->large_block);
     if (env->large_sc.cub_temp) cudaFree(env->large_sc.cub_temp);
     delete env;
@@ -334,6 +370,9 @@ int fastace_env_time(const fastace_env_t* env, uint32_t* out_time) {
 int fastace_env_set_state(fastace_env_t* env, const fastace_state_t* host_state, uint32_t time) {
     if (!env || !host_state) { set_error("null argument"); return FASTACE_ERR_INVALID; }
     FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+    // steps may still be running on non-blocking streams (the env's own, or the caller's): the state they read
+    // must not be overwritten under them
+    FASTACE_CUDA_CHECK(cudaDeviceSynchronize());
     for (auto& f : state_fields(env->dims)) {
         const void* src = member(host_state, f.offset);
         if (!src || f.count == 0) continue;
@@ -341,6 +380,7 @@ int fastace_env_set_state(fastace_env_t* env, const fastace_state_t* host_state,
     }
     env->time = time;
     env->mid_step = 0;
+    if (env->err_host) std::memset(env->err_host, 0, 4 * sizeof(uint32_t));   // a fresh state: earlier errors are void
     return FASTACE_OK;
 }
 
@@ -353,7 +393,7 @@ int fastace_env_get_state(const fastace_env_t* env, fastace_state_t* host_state)
         if (!dst || f.count == 0) continue;
         FASTACE_CUDA_CHECK(cudaMemcpy(dst, member(&env->dstate, f.offset), f.elem * f.count, cudaMemcpyDeviceToHost));
     }
-    return FASTACE_OK;
+    return check_device_errors(env);
 }
 
 int fastace_env_device_state(const fastace_env_t* env, fastace_state_t* out_device_state) {
@@ -467,6 +507,7 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
         offset_to_economy(out_fields(d), &lp.sp.out, e, d.num_econ);
         lp.sc = env->large_sc;
         lp.G = G;
+        lp.dev_err = env->err_dev;
         const LargeScratch& sc = lp.sc;
         const bool ph_p = (flags & FASTACE_STEP_PERSONS) != 0, ph_t = (flags & FASTACE_STEP_PERSONS_TRADE) != 0;
         const bool ph_c = (flags & FASTACE_STEP_PERSONS_CONSUME) != 0, ph_f = (flags & FASTACE_STEP_FIRMS) != 0;
@@ -558,6 +599,7 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
     const bool ph_t = (flags & FASTACE_STEP_PERSONS_TRADE) != 0, ph_c = (flags & FASTACE_STEP_PERSONS_CONSUME) != 0;
     const bool only_p = ph_p || ph_t || ph_c;          // some part of the person phase, no firm phase
     if ((int)ph_p + (int)ph_t + (int)ph_c + (int)only_f > 1) { set_error("the phase flags are separate calls"); return FASTACE_ERR_INVALID; }
+    if (int erc = check_device_errors(env)) return erc;   // an earlier step did not converge
     if ((only_p || only_f) && (dcz || (flags & FASTACE_STEP_SERIAL))) {
         set_error("phase-wise stepping takes the int32 action encoding and is not implemented by the serial kernel");
         return FASTACE_ERR_INVALID;
@@ -636,7 +678,7 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
             env->have_ev = true;
         }
         MatchParams mp;
-        mp.sp = sp; mp.scr_pnh = env->scr_pnh; mp.scr_pnb = env->scr_pnb;
+        mp.sp = sp; mp.scr_pnh = env->scr_pnh; mp.scr_pnb = env->scr_pnb; mp.dev_err = env->err_dev;
         mp.lay = make_match_layout(sp.P, sp.F, env->dims.num_goods, sp.S);
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[0], stream));
         if (!ph_c) {   // a consume-only call has no matching to do
@@ -798,6 +840,52 @@ int fastace_env_step_host_compact(fastace_env_t* env, const fastace_actions_comp
     return step_host_impl(env, actions, compact_fields(env->dims), env->dcact, env->cact_block, true, out, flags);
 }
 
+int fastace_env_shuffle_orders(fastace_env_t* env, uint32_t seed, int restart, int steps,
+                               int32_t* perm_person, int32_t* perm_firm, uint16_t* perm_person16, uint16_t* perm_firm16,
+                               void* cuda_stream) {
+    if (!env || steps < 1) { set_error("bad argument"); return FASTACE_ERR_INVALID; }
+    FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+    const int E = env->dims.num_econ, P = env->dims.num_persons, F = env->dims.num_firms;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (!env->ord_rng) {
+        FASTACE_CUDA_CHECK(cudaMalloc((void**)&env->ord_rng, sizeof(uint64_t) * (size_t)E));
+        FASTACE_CUDA_CHECK(cudaMalloc((void**)&env->ord_person, sizeof(int32_t) * ((size_t)E * P + 1)));
+        FASTACE_CUDA_CHECK(cudaMalloc((void**)&env->ord_firm, sizeof(int32_t) * ((size_t)E * F + 1)));
+    }
+    if (!restart && !env->ord_started) { set_error("the first call must (re)start the orders"); return FASTACE_ERR_INVALID; }
+    ShuffleParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.E = E; sp.P = P; sp.F = F; sp.seed = seed;
+    sp.rng_state = env->ord_rng; sp.state_person = env->ord_person; sp.state_firm = env->ord_firm;
+    const size_t smem = (size_t)(P + F) * kShuffleThreads * sizeof(uint16_t);
+    int max_optin = 0;
+    FASTACE_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, env->device));
+    const bool use_smem = P <= 65535 && F <= 65535 && smem <= (size_t)max_optin;
+    const unsigned blocks = (unsigned)((E + kShuffleThreads - 1) / kShuffleThreads);
+    if (use_smem) {
+        if (smem > 48 * 1024)
+            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)shuffle_orders_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sp.use_smem = 1; sp.restart = restart ? 1 : 0; sp.steps = steps;
+        sp.out_person = perm_person; sp.out_firm = perm_firm; sp.out_person16 = perm_person16; sp.out_firm16 = perm_firm16;
+        shuffle_orders_kernel<<<blocks, kShuffleThreads, smem, stream>>>(sp);
+        FASTACE_CUDA_CHECK(cudaGetLastError());
+        env->launches += 1;
+    } else {
+        // economies too large for shared memory: one launch per step, in place in the env's own arrays (32-bit ids only)
+        if (perm_person16 || perm_firm16) { set_error("16-bit orders need P, F <= 65535"); return FASTACE_ERR_INVALID; }
+        for (int t = 0; t < steps; t++) {
+            sp.use_smem = 0; sp.restart = (restart && t == 0) ? 1 : 0; sp.steps = 1;
+            shuffle_orders_kernel<<<blocks, kShuffleThreads, 0, stream>>>(sp);
+            FASTACE_CUDA_CHECK(cudaGetLastError());
+            env->launches += 1;
+            if (perm_person) FASTACE_CUDA_CHECK(cudaMemcpyAsync(perm_person + (size_t)t * E * P, env->ord_person, sizeof(int32_t) * (size_t)E * P, cudaMemcpyDeviceToDevice, stream));
+            if (perm_firm) FASTACE_CUDA_CHECK(cudaMemcpyAsync(perm_firm + (size_t)t * E * F, env->ord_firm, sizeof(int32_t) * (size_t)E * F, cudaMemcpyDeviceToDevice, stream));
+        }
+    }
+    env->ord_started = true;
+    return FASTACE_OK;
+}
+
 int fastace_env_sync(fastace_env_t* env) {
     if (!env) { set_error("null argument"); return FASTACE_ERR_INVALID; }
     FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
@@ -806,7 +894,7 @@ int fastace_env_sync(fastace_env_t* env) {
         FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->stream));
         FASTACE_CUDA_CHECK(cudaStreamSynchronize(env->copy_out));
     }
-    return FASTACE_OK;
+    return check_device_errors(env);
 }
 
 }  // extern "C"

@@ -89,6 +89,7 @@ struct LargeParams {
     StepParams sp;     // state / action / out pointers already offset to the economy being stepped (E = 1 view)
     LargeScratch sc;
     int G;
+    volatile uint32_t* dev_err;   // device error words of the env (match_kernel.cuh)
 };
 
 __device__ __forceinline__ uint32_t large_map_index(int32_t raw, int count, uint32_t flags) {
@@ -413,6 +414,7 @@ __global__ void __launch_bounds__(kLargeThreads, 3) large_iterate_persons(const 
         const int again = flags[round % 3];
         round++;
         if (!again) break;
+        if (round >= max_rounds && tid == 0) lp.dev_err[kDevErrLargeRounds] = 1u;   // not converged: an error, not a result
     }
     if (tid == 0) flags[3] = round;
 }
@@ -617,6 +619,7 @@ __global__ void __launch_bounds__(kLargeThreads) large_iterate_firms(const Large
         const int again = flags[round % 3];
         round++;
         if (!again) break;
+        if (round >= max_rounds && tid == 0) lp.dev_err[kDevErrLargeRounds] = 1u;
     }
     if (tid == 0) flags[3] = round;
 }

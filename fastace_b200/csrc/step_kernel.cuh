@@ -103,7 +103,7 @@ __device__ __forceinline__ bool request_good(int n, double& money, double* s_fmo
 // reference's order.  The default path is match_kernel + update_kernel (match_update_kernels.cuh).
 template <int G>
 __global__ void __launch_bounds__(32, 32) step_kernel(const StepParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    FASTACE_DYN_SMEM(smem);
     const int e = blockIdx.x;
     const int lane = threadIdx.x;
     const int P = p.P, F = p.F, S = p.S;

@@ -45,7 +45,11 @@ typedef enum fastace_status {
     FASTACE_ERR_INVALID = -1,   /* bad argument / unsupported dimension */
     FASTACE_ERR_CUDA = -2,      /* CUDA runtime error (message in fastace_last_error) */
     FASTACE_ERR_NO_DEVICE = -3, /* no CUDA device: there is NO CPU fallback */
-    FASTACE_ERR_ALLOC = -4
+    FASTACE_ERR_ALLOC = -4,
+    FASTACE_ERR_NOT_CONVERGED = -5 /* a matching kernel hit its iteration cap: the env's state is not a valid step
+                                      result (cannot happen per the convergence proof; never silently committed).
+                                      Returned by fastace_env_sync, fastace_env_get_state and the next step call;
+                                      cleared by fastace_env_set_state */
 } fastace_status_t;
 
 /* Limits of every path; the warp-per-economy kernels (one economy = one warp, books in shared memory) additionally
@@ -405,6 +409,16 @@ int fastace_scenario_custom_init(const fastace_dims_t* dims,
  * step 0) and the perm arrays carry the stream and the cumulative order between calls. */
 int fastace_shuffle_orders(const fastace_dims_t* dims, uint32_t seed, uint64_t* rng_state,
                            int32_t* perm_person, int32_t* perm_firm, int first_call);
+
+/* The same on the DEVICE, for a rollout that never leaves it: advances the env's own engines and cumulative orders by
+ * `steps` Economy::time_step shuffles (economy.cpp:110-111, bit-identical to libstdc++'s std::shuffle with
+ * std::minstd_rand0 — one thread per economy replays the generator and the pairwise-swap algorithm) and writes step
+ * t's orders to slice t of the DEVICE arrays perm_person [steps][E][P] / perm_firm [steps][E][F], in int32 and / or
+ * 16-bit form (NULL = not wanted).  restart != 0: economy e seeds minstd_rand0(seed + e) and starts from the identity
+ * order, exactly like first_call of fastace_shuffle_orders.  Enqueued on `cuda_stream`; does not synchronise. */
+int fastace_env_shuffle_orders(fastace_env_t* env, uint32_t seed, int restart, int steps,
+                               int32_t* perm_person, int32_t* perm_firm, uint16_t* perm_person16, uint16_t* perm_firm16,
+                               void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,105 @@
+// TEST INFRASTRUCTURE ONLY — the step kernels' CUDA source (fastace_b200/csrc/match_kernel.cuh, update_kernel of
+// match_update_kernels.cuh) compiled for the CPU under tests/emu/warp_emu.h and driven exactly as
+// launch_step (fastace_capi.cu) drives them on the device.  Lets `pytest -m "not gpu"` check the kernel logic
+// against the oracle in a container without a GPU.  Built by tests/emu/build_emu.py with -ffp-contract=off
+// (the device build uses --fmad=false).
+#include "warp_emu.h"
+
+#include "../../fastace_b200/csrc/match_update_kernels.cuh"
+#include "../../fastace_b200/csrc/shuffle_kernel.cuh"
+
+#include <vector>
+
+using namespace fastace;
+
+template <int G>
+static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vector<uint8_t>& pnb, uint32_t* err) {
+    const uint32_t flags = sp.flags;
+    const bool ph_p = (flags & FASTACE_STEP_PERSONS) != 0, only_f = (flags & FASTACE_STEP_FIRMS) != 0;
+    const bool ph_t = (flags & FASTACE_STEP_PERSONS_TRADE) != 0, ph_c = (flags & FASTACE_STEP_PERSONS_CONSUME) != 0;
+    const bool only_p = ph_p || ph_t || ph_c;
+    MatchParams mp;
+    mp.sp = sp; mp.scr_pnh = pnh.data(); mp.scr_pnb = pnb.data(); mp.dev_err = err;
+    mp.lay = make_match_layout(sp.P, sp.F, G, sp.S);
+    if (!ph_c) {
+        if (sp.S <= 12) emu::launch(match_kernel<G, 12>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+        else emu::launch(match_kernel<G, 16>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+    }
+    UpdateParams up;
+    up.sp = sp; up.scr_pnh = pnh.data(); up.scr_pnb = pnb.data();
+    const size_t persons = (size_t)sp.E * sp.P;
+    const int person_blocks = only_f ? 0 : (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
+    up.firm_blocks = only_p ? 0 : (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
+    if (person_blocks + up.firm_blocks > 0)
+        emu::launch(update_kernel<G>, (unsigned)(person_blocks + up.firm_blocks), (unsigned)kUpdateThreads, 0, up);
+}
+
+struct EmuEnv {
+    std::vector<uint8_t> pnh, pnb;
+    uint32_t err[4] = {0, 0, 0, 0};
+};
+
+extern "C" {
+
+void* fastace_emu_create(const fastace_dims_t* d) {
+    EmuEnv* e = new EmuEnv();
+    e->pnh.assign((size_t)d->num_econ * d->num_persons + 1, 0xEE);
+    e->pnb.assign((size_t)d->num_econ * d->num_persons * d->num_goods + 1, 0xEE);
+    return e;
+}
+void fastace_emu_destroy(void* h) { delete static_cast<EmuEnv*>(h); }
+
+// One call of launch_step's default path on HOST arrays.  Exactly one of actions / compact is non-null.
+// Returns the error words the kernels raised (0 = converged).
+int fastace_emu_step(void* h, const fastace_dims_t* d, fastace_state_t* state, const fastace_actions_t* actions,
+                     const fastace_actions_compact_t* compact, const fastace_step_out_t* out, uint32_t flags,
+                     uint32_t time_before, int util_kind, int prod_kind) {
+    EmuEnv* env = static_cast<EmuEnv*>(h);
+    StepParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.E = d->num_econ; sp.P = d->num_persons; sp.F = d->num_firms; sp.S = d->stack_size;
+    sp.flags = flags; sp.time_before = time_before;
+    sp.util_kind = util_kind; sp.prod_kind = prod_kind;
+    sp.st = *state;
+    if (compact) {
+        sp.compact = 1;
+        sp.cz = *compact;
+        sp.ac.p_consume = compact->p_consume; sp.ac.f_prod = compact->f_prod; sp.ac.f_offer_amt = compact->f_offer_amt;
+        sp.ac.f_offer_price = compact->f_offer_price; sp.ac.f_job_labor = compact->f_job_labor; sp.ac.f_job_wage = compact->f_job_wage;
+    } else {
+        sp.ac = *actions;
+    }
+    sp.out = *out;
+    switch (d->num_goods) {
+        case 1: run_step<1>(sp, env->pnh, env->pnb, env->err); break;
+        case 2: run_step<2>(sp, env->pnh, env->pnb, env->err); break;
+        case 3: run_step<3>(sp, env->pnh, env->pnb, env->err); break;
+        case 4: run_step<4>(sp, env->pnh, env->pnb, env->err); break;
+        case 5: run_step<5>(sp, env->pnh, env->pnb, env->err); break;
+        case 8: run_step<8>(sp, env->pnh, env->pnb, env->err); break;
+        default: return -1;
+    }
+    return (int)(env->err[0] | (env->err[1] << 1));
+}
+
+// shuffle_orders_kernel on HOST arrays (the shared-memory variant when use_smem != 0)
+void fastace_emu_shuffle(int E, int P, int F, uint32_t seed, int restart, int steps, uint64_t* rng, int32_t* state_person,
+                         int32_t* state_firm, int32_t* out_person, int32_t* out_firm, uint16_t* out_person16, uint16_t* out_firm16,
+                         int use_smem) {
+    ShuffleParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.E = E; sp.P = P; sp.F = F; sp.seed = seed; sp.restart = restart; sp.steps = steps;
+    sp.rng_state = rng; sp.state_person = state_person; sp.state_firm = state_firm;
+    sp.out_person = out_person; sp.out_firm = out_firm; sp.out_person16 = out_person16; sp.out_firm16 = out_firm16;
+    sp.use_smem = use_smem;
+    const unsigned blocks = (unsigned)((E + kShuffleThreads - 1) / kShuffleThreads);
+    emu::launch(shuffle_orders_kernel, blocks, (unsigned)kShuffleThreads,
+                use_smem ? (size_t)(P + F) * kShuffleThreads * sizeof(uint16_t) : 0, sp);
+}
+
+// event counters of the kernels since the last call (common.cuh: kStat*); resets them
+void fastace_emu_stats(unsigned long long* out) {
+    for (int i = 0; i < kStatCount; i++) { out[i] = emu::stats()[i]; emu::stats()[i] = 0; }
+}
+
+}  // extern "C"
