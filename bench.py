@@ -263,44 +263,71 @@ def run_ours(args):
             reset_state(t)
         env.time_step(dacts[k], dout, flags=_abi.IDX_MODULO)
 
+    # The device-resident inputs of the timed region are in the library's COMPACT action encoding
+    # (fastace_actions_compact_t: 8-bit offer indices, take bit masks, 16-bit orders — the format the e2e leg ships
+    # over PCIe as well); the int32 encoding (fastace_actions_t) is timed next to it ("value_int32").  A compact index
+    # byte is `draw % book size`, so the book sizes of every step are replayed once with the int32 path first.
+    counts = []
+    reset_state(0)
+    for k in range(EPISODE):
+        cnt = env.get_state(names=("j_count", "m_count"))
+        counts.append((cnt["j_count"].copy(), cnt["m_count"].copy()))
+        env.time_step(dacts[k], dout, flags=_abi.IDX_MODULO)
+    torch.cuda.synchronize()
+    host_cz = [_abi.compact_actions_for_counts(acts[k], counts[k][0], counts[k][1], True) for k in range(EPISODE)]
+    dcz = [env.pack_device("compact", env.alloc_compact_actions(cz)) for cz in host_cz]
+    reset_state(0)
+
+    def timed_run(step_structs, n_warm, n_steps):
+        """W untimed + K timed steps, every step bracketed by CUDA events on the launching stream, L2 flushed between
+        steps; returns (per-step ms of this rank, launches, wall seconds)."""
+        for t in range(n_warm):
+            if t % EPISODE == 0:
+                reset_state(t)
+            if not args.no_flush:
+                flush.zero_()
+            env.time_step(step_structs[t % EPISODE], dout, flags=_abi.IDX_MODULO)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = env.launch_count()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for i in range(n_steps):
+            t = n_warm + i
+            if t % EPISODE == 0:
+                reset_state(t)
+            if not args.no_flush:
+                flush.zero_()
+            starts[i].record()
+            env.time_step(step_structs[t % EPISODE], dout, flags=_abi.IDX_MODULO)
+            stops[i].record()
+        torch.cuda.synchronize()
+        w = time.perf_counter() - w0
+        if world > 1:
+            dist.barrier()
+        return np.array([s.elapsed_time(e) for s, e in zip(starts, stops)]), env.launch_count() - l0, w
+
+    def whole_job(ms):
+        t_ms = torch.tensor([float(ms.sum())], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        return float(t_ms.item())
+
     sampler = ClockSampler(local)   # samples through warm-up and the timed region (same load)
     sampler.start()
-    for t in range(args.warmup):
-        if not args.no_flush:
-            flush.zero_()
-        one_step(t)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches0 = env.launch_count()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        t = args.warmup + i
-        if t % EPISODE == 0:
-            reset_state(t)
-        if not args.no_flush:
-            flush.zero_()
-        starts[i].record()
-        env.time_step(dacts[t % EPISODE], dout, flags=_abi.IDX_MODULO)
-        stops[i].record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - wall0
-    if world > 1:
-        dist.barrier()
+    step_ms, launches, wall = timed_run(dcz, args.warmup, args.steps)
     sampler.stop_flag = True
     sampler.join()
-    launches = env.launch_count() - launches0
-    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
     total_ms = float(step_ms.sum())
-    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t_ms.item())
+    total_ms_max = whole_job(step_ms)
     agent_steps = world * E * (P + F) * args.steps
     value = agent_steps / (total_ms_max * 1e-3)
+    n32 = max(10, args.steps // 4)
+    ms32, _, _ = timed_run(dacts, 3, n32)
+    value_int32 = world * E * (P + F) * n32 / (whole_job(ms32) * 1e-3)
 
     # ---- per-kernel device time (CUDA events inside the library, FASTACE_STEP_PROFILE) ------
     env.kernel_times()
@@ -309,7 +336,7 @@ def run_ours(args):
             reset_state(i)
         if not args.no_flush:
             flush.zero_()
-        env.time_step(dacts[i % EPISODE], dout, flags=_abi.IDX_MODULO | _abi.STEP_PROFILE)
+        env.time_step(dcz[i % EPISODE], dout, flags=_abi.IDX_MODULO | _abi.STEP_PROFILE)
     match_ms, update_ms, prof_steps = env.kernel_times()
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers) -------------------
@@ -319,15 +346,6 @@ def run_ours(args):
     # region.  The plain int32 encoding, synchronous, is timed as well ("e2e_int32_sync").
     e2e_steps = min(args.steps, EPISODE)
     st_host = {k: v.copy() for k, v in state.items()}
-    # compact encoding needs the book sizes of each step: replay them once with the device path
-    reset_state(0)
-    counts = []
-    for k in range(e2e_steps):
-        cnt = env.get_state(names=("j_count", "m_count"))
-        counts.append((cnt["j_count"].copy(), cnt["m_count"].copy()))
-        env.time_step(dacts[k], dout, flags=_abi.IDX_MODULO)
-    torch.cuda.synchronize()
-
     def pin_block(kind, d):
         """one pinned block per struct, in the library's staging layout: one host<->device copy per step"""
         blk, holder = _abi.alloc_host_block(kind, env.dims, names=tuple(d.keys()), pinned=True)
@@ -338,7 +356,7 @@ def run_ours(args):
 
     pinned_c, pinned_i = [], []
     for k in range(e2e_steps):
-        cz = pin_block("compact", _abi.compact_actions_for_counts(acts[k], counts[k][0], counts[k][1], True))
+        cz = pin_block("compact", host_cz[k])
         holder = cz.pop("_holder")
         st_c = _abi.struct_from_numpy("compact", cz, env.dims)
         st_c._holder = holder
@@ -485,11 +503,14 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"config B: {E} economies/GPU x (100 persons + 10 firms), 2 goods, stack 10, 40-step episodes, "
-                            "fixed injected actions (scenario.BENCH_PRESET), std::shuffle visiting orders, IDX_MODULO",
+                            "fixed injected actions (scenario.BENCH_PRESET), std::shuffle visiting orders, IDX_MODULO; device-resident "
+                            "inputs in the compact action encoding (fastace_actions_compact_t)",
                 "economies_per_gpu": E, "l2": "flushed between timed steps (512 MiB write)" if not args.no_flush else "not flushed",
                 "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
                 "wall_s_including_flushes": wall,
             },
+            "value_int32": {"value": value_int32, "unit": METRIC, "steps": n32,
+                            "what": "the same steps with device-resident inputs in the int32 encoding (fastace_actions_t)"},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "fastace_env_step_host_compact + FASTACE_STEP_ASYNC, fastace_env_sync at the end (one pinned block per step: "

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FASTACE_OK = 0
 IDX_ABSOLUTE = 0
 IDX_MODULO = 1
@@ -101,12 +101,12 @@ ACTION_FIELDS = [
 COMPACT_FIELDS = [
     ("perm_person", _hp, np.uint16, lambda E, P, F, G, S: (E, P)),
     ("perm_firm", _hp, np.uint16, lambda E, P, F, G, S: (E, F)),
-    ("p_job_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, S, P)),
+    ("p_job_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, P, S)),      # agent-major: one agent's S bytes are contiguous
     ("p_job_take", _hp, np.uint16, lambda E, P, F, G, S: (E, P)),
-    ("p_good_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, S, P)),
+    ("p_good_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, P, S)),
     ("p_good_take", _hp, np.uint16, lambda E, P, F, G, S: (E, P)),
     ("p_consume", _fp, np.float32, lambda E, P, F, G, S: (E, G, P)),
-    ("f_good_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, S, F)),
+    ("f_good_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, F, S)),
     ("f_good_take", _hp, np.uint16, lambda E, P, F, G, S: (E, F)),
     ("f_prod", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
     ("f_offer_amt", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
@@ -261,13 +261,15 @@ def compact_actions_for_counts(actions, j_count, m_count, modulo):
     jc = np.asarray(j_count, dtype=np.int64).reshape(E, 1, 1)
     mc = np.asarray(m_count, dtype=np.int64).reshape(E, 1, 1)
 
-    def idx8(raw, cnt):
+    def idx8(raw, cnt):   # [E][S][N] int32 -> [E][N][S] u8 (agent-major)
         raw = raw.astype(np.int64)
         if modulo:
             u = raw & 0xFFFFFFFF
-            return np.where(cnt > 0, u % np.maximum(cnt, 1), 0).astype(np.uint8)
-        ok = (raw >= 0) & (raw < cnt)
-        return np.where(ok, raw, 255).astype(np.uint8)
+            b = np.where(cnt > 0, u % np.maximum(cnt, 1), 0).astype(np.uint8)
+        else:
+            ok = (raw >= 0) & (raw < cnt)
+            b = np.where(ok, raw, 255).astype(np.uint8)
+        return b.transpose(0, 2, 1)
 
     def mask16(take):  # [E][S][N] u8 -> [E][N] u16
         S = take.shape[1]

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfastace_b200.so")
-SOURCES = [os.path.join(CSRC, "fastace_capi.cu"), os.path.join(CSRC, "fastace_host.cpp")]
+SOURCES = [os.path.join(CSRC, "fastace_capi.cu"), os.path.join(CSRC, "fastace_host.cpp"), os.path.join(CSRC, "legacy_capi.cpp")]
 def _deps():
     """Every file the library is compiled from: all of csrc/ and the public headers (a stale
     .so must never travel to the GPU box, so nothing is listed by hand)."""
@@ -50,7 +50,7 @@ def needs_build():
 def build(force=False, verbose=False, extra_flags=()):
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB] + SOURCES
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB] + SOURCES + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
     out = subprocess.run(cmd, capture_output=True, text=True)

@@ -19,6 +19,39 @@
 
 namespace fastace {
 
+// Shared-memory accesses of the hot loops by explicit 32-bit shared address + immediate offset: one LDS / STS each,
+// no generic-pointer arithmetic for the compiler to re-derive under the register cap.  (The CPU emulation build
+// supplies the same functions over its own block buffer.)
+#ifndef FASTACE_HAVE_SMEM_OPS
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// a value the compiler must keep in a register instead of re-deriving it from its operands at every use
+__device__ __forceinline__ uint32_t keep_u32(uint32_t x) { uint32_t y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+#define FASTACE_SMEM_LD(NAME, T, PTX, C)                                                                   \
+    template <int OFF = 0> __device__ __forceinline__ T NAME(uint32_t a) {                                 \
+        T v; asm volatile("ld.shared." PTX " %0, [%1+%2];" : "=" C(v) : "r"(a), "n"(OFF)); return v;       \
+    }
+#define FASTACE_SMEM_ST(NAME, T, PTX, C)                                                                   \
+    template <int OFF = 0> __device__ __forceinline__ void NAME(uint32_t a, T v) {                         \
+        asm volatile("st.shared." PTX " [%0+%1], %2;" :: "r"(a), "n"(OFF), C(v));                          \
+    }
+FASTACE_SMEM_LD(lds_u8, uint32_t, "u8", "r")
+FASTACE_SMEM_LD(lds_u16, uint32_t, "u16", "r")
+FASTACE_SMEM_LD(lds_u32, uint32_t, "u32", "r")
+FASTACE_SMEM_LD(lds_f64, double, "f64", "d")
+FASTACE_SMEM_ST(sts_u8, uint32_t, "u8", "r")
+FASTACE_SMEM_ST(sts_u16, uint32_t, "u16", "r")
+FASTACE_SMEM_ST(sts_u32, uint32_t, "u32", "r")
+FASTACE_SMEM_ST(sts_f64, double, "f64", "d")
+#undef FASTACE_SMEM_LD
+#undef FASTACE_SMEM_ST
+template <int OFF = 0> __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(OFF)); return v;
+}
+template <int OFF = 0> __device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0+%1], {%2,%3,%4,%5};" :: "r"(a), "n"(OFF), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+#endif
+
 enum { kStatWindows, kStatRounds, kStatRescans, kStatRiskyWalks, kStatSalesWindows, kStatDeadExits, kStatFirmSerial, kStatRoundsW0, kStatRoundsW1, kStatRoundsW2, kStatRoundsW3, kStatRescansW0, kStatCount };
 
 struct StepParams {

@@ -212,9 +212,9 @@ static int carve(const std::vector<FieldDesc>& fields, StructT* s, void** block,
 typedef void (*serial_fn)(const StepParams);
 typedef void (*match_fn)(const MatchParams);
 typedef void (*update_fn)(const UpdateParams);
-struct KernelSet { serial_fn serial; match_fn match12; match_fn match16; update_fn update; };
+struct KernelSet { serial_fn serial; match_fn match; update_fn update; };
 template <int G>
-static KernelSet kernels_of() { return {step_kernel<G>, match_kernel<G, 12>, match_kernel<G, 16>, update_kernel<G>}; }
+static KernelSet kernels_of() { return {step_kernel<G>, match_kernel<G>, update_kernel<G>}; }
 static KernelSet kernels_for_goods(int G) {
     switch (G) {
         case 1: return kernels_of<1>();
@@ -225,7 +225,7 @@ static KernelSet kernels_for_goods(int G) {
         case 6: return kernels_of<6>();
         case 7: return kernels_of<7>();
         case 8: return kernels_of<8>();
-        default: return {nullptr, nullptr, nullptr, nullptr};
+        default: return {nullptr, nullptr, nullptr};
     }
 }
 
@@ -278,8 +278,7 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
         if (L.total > 48 * 1024)
             FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.serial, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         if (ML.total > 48 * 1024) {
-            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match12, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
-            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match16, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
+            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
         }
     }
 
@@ -682,7 +681,7 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         mp.lay = make_match_layout(sp.P, sp.F, env->dims.num_goods, sp.S);
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[0], stream));
         if (!ph_c) {   // a consume-only call has no matching to do
-            (sp.S <= 12 ? ks.match12 : ks.match16)<<<sp.E, 32, env->match_smem_bytes, stream>>>(mp);
+            ks.match<<<sp.E, 32, env->match_smem_bytes, stream>>>(mp);
             FASTACE_CUDA_CHECK(cudaGetLastError());
             env->launches += 1;
         }

@@ -1,4 +1,4 @@
-// match_kernel<G,SMAX> — all matching of one Economy::time_step, one warp per economy (kernel v4).
+// match_kernel<G> — all matching of one Economy::time_step, one warp per economy (kernel v4).
 //
 // What it computes (reference, paths under /root/reference/src): the person phase and the firm phase of
 // Economy::time_step (base/economy.cpp:113-123) as far as they touch OTHER agents — labour acceptance
@@ -8,10 +8,11 @@
 // (profitMaxer.cpp:79-81, 93-95).  Everything that touches only the agent itself (consumption, utility,
 // production, the new offers) is update_kernel's.
 //
-// Shared memory holds the economy's two books (a 32-byte record and three 32-byte lane vectors per offer) and the
-// firms' money / inventories.  Person
-// state and requests are never staged: a person's money and its 2S request slots are gathered straight from HBM
-// (L1/L2-resident after the first window) into the registers of the lane that owns it.
+// Shared memory holds the economy's two books (a 32-byte record and three 32-byte lane vectors per offer), the
+// firms' money / inventories and, per window, the 32 persons' request lists as offer numbers (36 bytes per lane).
+// Person state is never staged: a person's money and request slots go straight from HBM (prefetched into L2 by one
+// bulk prefetch per array at kernel start) to the lane that owns it — three 32-bit loads per list in the compact
+// encoding, whose index bytes are agent-major.
 //
 // Persons, lane-parallel and exact.  A window = 32 persons with consecutive visiting ranks, lane = rank in the
 // window.  For offer row R the ordinal number of an ELIGIBLE request (the person-side test passed:
@@ -47,8 +48,9 @@
 namespace fastace {
 
 // ---- offer rows ------------------------------------------------------------------------------------
-// Every offer has a MATRIX row (three 32-byte lane vectors) and a RECORD row.  Job offers are rows 0..F
-// (row NJ = "no request"), goods offers rows F+1.. (row F+1+NM likewise).
+// Every offer has a MATRIX row (three 32-byte lane vectors) and a RECORD row.  Rows are numbered
+//   job offer n -> n,   "no job request" -> NJ,   goods offer n -> NJ + 1 + n,   "no goods request" -> NJ + NM + 1,
+// the two "no request" rows being ordinary rows with no lots: a request on them is eligible and never succeeds.
 constexpr int kMatBytes = 96;
 constexpr int kMatCnt = 0;      // u8[32]  eligible requests per lane, current evaluation
 constexpr int kMatRoom = 32;    // u8[32]  how many of a lane's eligible requests can succeed
@@ -59,10 +61,14 @@ constexpr int kRecLeft = 8;     // u32     BaseOffer::amountLeft
 constexpr int kRecTaken = 12;   // u32     BaseOffer::amountTaken
 constexpr int kRecD = 16;       // i32     death ordinal of the window; firm phase: amountLeft at withdrawal
 constexpr int kRecTot = 20;     // i32     eligible requests of the window; after the commit: successes
-constexpr int kRecMeta = 24;    // u32     owner | good << 8 | rescanned << 16
+constexpr int kRecMeta = 24;    // u32     owner | good << 8
+constexpr int kRecScanned = 28; // u8      the rooms of this window have been re-scanned (they follow `prev`)
 constexpr int kRoomMax = 127;   // rooms are clamped here (a lane has at most FASTACE_MAX_STACK requests)
 constexpr int kRoundCap = 200;  // > 2 * 32 + 2, the proven bound: reaching it raises kDevErrRounds
-constexpr int kEvPerLane = 2 + FASTACE_MAX_STACK;   // successes of one person: <= 2 hires + S purchases
+constexpr int kEvPerLane = 2 + FASTACE_MAX_STACK;   // list of one lane's purchases: count byte + <= S rows
+constexpr int kMaxHiresPerWindow = 64;              // 32 persons, at most two jobs each (person.cpp:39)
+constexpr int kReqStride = 2 * FASTACE_MAX_STACK + 4;   // a lane's request lists: jobs at +0, goods at +16 (9 words: conflict-free)
+constexpr int kReqGoods = FASTACE_MAX_STACK;
 
 // device error words (fastace_env_t::dev_err, host-mapped memory), surfaced as FASTACE_ERR_NOT_CONVERGED by
 // fastace_env_sync, fastace_env_get_state and the next step call
@@ -70,22 +76,21 @@ constexpr int kDevErrRounds = 0;        // the window iteration hit kRoundCap (w
 constexpr int kDevErrLargeRounds = 1;   // the large-economy iteration hit its round cap
 
 struct MatchLayout {
-    int off_mat;                        // matrix rows; between windows' evaluations the first 96*F bytes double as the
-                                        // counting-sort scratch of the firm-money fold (evcnt u8 [F][32], evpos u16 [F][32])
-    int off_rec;                        // record rows
+    int off_mat, off_rec;                                 // matrix rows, record rows (F + F*G + 2 each)
     int off_fmoney, off_finv, off_flast;                  // double
     int off_fnh, off_fok, off_flive;                      // u32
-    int off_evbase, off_evtot, off_permf;                 // u16
+    int off_permf;                                        // u16
     int off_fatt;                                         // u8 [F][16]
     int off_fjob, off_ffirst, off_fcnt, off_frisk;        // u8 [F]
     int off_evlist;                                       // u8 [32][kEvPerLane]
+    int off_req;                                          // u8 [32][kReqStride]
     int total;
 };
 
 __host__ __device__ inline MatchLayout make_match_layout(int P, int F, int G, int S) {
     (void)P; (void)S;
     MatchLayout L;
-    const int rows = F + 1 + F * G + 1;
+    const int rows = F + F * G + 2;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     L.off_mat = take(kMatBytes * rows);
@@ -96,8 +101,6 @@ __host__ __device__ inline MatchLayout make_match_layout(int P, int F, int G, in
     L.off_fnh = take(4 * F);
     L.off_fok = take(4 * F);
     L.off_flive = take(4 * F);
-    L.off_evbase = take(2 * F);
-    L.off_evtot = take(2 * F);
     L.off_permf = take(2 * F);
     L.off_fatt = take(16 * F);
     L.off_fjob = take(F);
@@ -105,6 +108,7 @@ __host__ __device__ inline MatchLayout make_match_layout(int P, int F, int G, in
     L.off_fcnt = take(F);
     L.off_frisk = take(F);
     L.off_evlist = take(32 * kEvPerLane);
+    L.off_req = take(32 * kReqStride);
     L.total = o;
     return L;
 }
@@ -117,39 +121,55 @@ struct MatchParams {
     volatile uint32_t* dev_err;   // device error words of the env
 };
 
-__device__ __forceinline__ uint32_t& rec_u32(unsigned char* rec, int off) { return *reinterpret_cast<uint32_t*>(rec + off); }
-__device__ __forceinline__ int32_t& rec_i32(unsigned char* rec, int off) { return *reinterpret_cast<int32_t*>(rec + off); }
-__device__ __forceinline__ double& rec_value(unsigned char* rec) { return *reinterpret_cast<double*>(rec + kRecValue); }
-
 // inclusive prefix sum over the lanes of a warp
-__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, v, d);
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
         if (lane >= d) v += u;
     }
     return v;
 }
 
-// byte k of a list kept 4 entries per register
-template <int N>
-__device__ __forceinline__ uint32_t list_byte(const uint32_t (&w)[N], int k) {
-    uint32_t v = w[0];
-#pragma unroll
-    for (int q = 1; q < N; q++) if ((k >> 2) == q) v = w[q];
-    return (v >> (8 * (k & 3))) & 0xFFu;
-}
-template <int N>
-__device__ __forceinline__ void list_set_byte(uint32_t (&w)[N], int k, uint32_t b) {
-    const uint32_t sh = 8u * (uint32_t)(k & 3);
-#pragma unroll
-    for (int q = 0; q < N; q++) if ((k >> 2) == q) w[q] = (w[q] & ~(0xFFu << sh)) | (b << sh);
+// L2 prefetch of a contiguous array slab with one instruction (sm_90+ bulk prefetch; 16-byte granules)
+__device__ __forceinline__ void prefetch_slab_l2(const void* ptr, size_t bytes) {
+#ifndef FASTACE_HAVE_SMEM_OPS
+    const uintptr_t a = reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)15;
+    const uint32_t n = (uint32_t)((reinterpret_cast<uintptr_t>(ptr) + bytes - a + 15) & ~(size_t)15);
+    if (n != 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a), "r"(n) : "memory");
+#else
+    (void)ptr; (void)bytes;
+#endif
 }
 
-// SMAX: compile-time bound of the stack size S (12 or 16).  Request lists are RIGHT-ALIGNED in SMAX/4
-// registers per list (slot i at position i + SMAX - S) so that the fully unrolled evaluation is entered at
-// position SMAX - S through one jump and runs without per-slot bound checks.
-template <int G, int SMAX>
+// Four request bytes of the compact encoding -> four offer numbers.  `take4`: the four slots' take bits; a slot
+// without a request becomes `dummy` (the "no request" row).
+template <bool MODULO>
+__device__ __forceinline__ uint32_t map_request_word(uint32_t x, uint32_t take4, const IndexMap& map, uint32_t dummy) {
+    if (MODULO) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t n = map.mod24((x >> (8 * k)) & 0xFFu);
+            r |= (((take4 >> k) & 1u) ? n : dummy) << (8 * k);
+        }
+        return r;
+    }
+    // absolute indices: keep byte b iff its take bit is set and b < count (count <= 254).  Byte-parallel: the even
+    // and the odd bytes in 16-bit lanes, bit 8 of (b + 256 - count) says b >= count
+    const uint32_t k16 = (256u - map.count) * 0x00010001u;
+    const uint32_t ge_e = ((x & 0x00FF00FFu) + k16) & 0x01000100u;
+    const uint32_t ge_o = (((x >> 8) & 0x00FF00FFu) + k16) & 0x01000100u;
+    const uint32_t ge = (ge_e >> 8) | ge_o;                                  // 0x01 in every byte that is out of range
+    const uint32_t tk = ((take4 & 0xFu) * 0x00204081u) & 0x01010101u;        // take bit k -> byte k
+    const uint32_t keep = (tk & ~ge) * 0xFFu;                                // 0xFF in every byte that is a request
+    return (x & keep) | ((dummy * 0x01010101u) & ~keep);
+}
+
+// All shared-memory traffic goes through explicit 32-bit shared addresses (common.cuh: lds_* / sts_*); the loops
+// over request slots are rolled (the lists live in shared memory), so the hot code of a window is a few hundred
+// instructions.
+template <int G>
 __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     FASTACE_DYN_SMEM(smem);
     const StepParams& p = mp.sp;
@@ -158,104 +178,100 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     const int P = p.P, F = p.F, S = p.S;
     const int cap = F * G;
     const MatchLayout& L = mp.lay;
-    constexpr int NW = SMAX / 4;
-    const int skip = SMAX - S;          // first occupied position of a request list
 
-    unsigned char* matJ = smem + L.off_mat;
-    unsigned char* matM = matJ + (F + 1) * kMatBytes;
-    unsigned char* recJ = smem + L.off_rec;
-    unsigned char* recM = recJ + (F + 1) * kRecBytes;
-    double* s_fmoney = reinterpret_cast<double*>(smem + L.off_fmoney);
-    double* s_finv = reinterpret_cast<double*>(smem + L.off_finv);
-    double* s_flast = reinterpret_cast<double*>(smem + L.off_flast);
-    uint32_t* s_fnh = reinterpret_cast<uint32_t*>(smem + L.off_fnh);
-    uint32_t* s_fok = reinterpret_cast<uint32_t*>(smem + L.off_fok);
-    uint32_t* s_flive = reinterpret_cast<uint32_t*>(smem + L.off_flive);
-    uint8_t* s_evcnt = matJ;                                              // [F][32], commit only
-    uint16_t* s_evpos = reinterpret_cast<uint16_t*>(matJ + 32 * F);       // [F][32], commit only
-    uint16_t* s_evbase = reinterpret_cast<uint16_t*>(smem + L.off_evbase);
-    uint16_t* s_evtot = reinterpret_cast<uint16_t*>(smem + L.off_evtot);
-    uint16_t* s_permf = reinterpret_cast<uint16_t*>(smem + L.off_permf);
-    uint8_t* s_fatt = smem + L.off_fatt;
-    uint8_t* s_fjob = smem + L.off_fjob;
-    uint8_t* s_ffirst = smem + L.off_ffirst;
-    uint8_t* s_fcnt = smem + L.off_fcnt;
-    uint8_t* s_frisk = smem + L.off_frisk;
-    uint8_t* s_evlist = smem + L.off_evlist;
+    const uint32_t sb = smem_addr(smem);
+    const uint32_t aMat = sb + L.off_mat, aRec = sb + L.off_rec;
+    const uint32_t aFmoney = sb + L.off_fmoney, aFinv = sb + L.off_finv, aFlast = sb + L.off_flast;
+    const uint32_t aFnh = sb + L.off_fnh, aFok = sb + L.off_fok, aFlive = sb + L.off_flive, aPermf = sb + L.off_permf;
+    const uint32_t aFatt = sb + L.off_fatt, aFjob = sb + L.off_fjob, aFfirst = sb + L.off_ffirst, aFcnt = sb + L.off_fcnt;
+    const uint32_t aFrisk = sb + L.off_frisk, aEv = sb + L.off_evlist;
+    const uint32_t aReqL = keep_u32(sb + L.off_req + (uint32_t)lane * kReqStride);   // this lane's request lists
 
     const size_t eP = (size_t)e * P, eF = (size_t)e * F, eCap = (size_t)e * cap;
     // a step may be taken in two calls (FASTACE_STEP_PERSONS, then FASTACE_STEP_FIRMS): the state in HBM between
     // them is the economy as it stands when the last person has acted and no firm has (economy.cpp:118-123)
     const bool do_persons = !(p.flags & FASTACE_STEP_FIRMS);
     const bool do_firms = !(p.flags & (FASTACE_STEP_PERSONS | FASTACE_STEP_PERSONS_TRADE));
+    if (do_persons && p.compact) {
+        // the economy's person-side inputs are five contiguous slabs: ask L2 for them now, use them window by window
+        if (lane == 0) prefetch_slab_l2(p.cz.p_job_idx + (size_t)e * P * S, (size_t)P * S);
+        if (lane == 1) prefetch_slab_l2(p.cz.p_good_idx + (size_t)e * P * S, (size_t)P * S);
+        if (lane == 2) prefetch_slab_l2(p.cz.p_job_take + (size_t)e * P, (size_t)P * 2);
+        if (lane == 3) prefetch_slab_l2(p.cz.p_good_take + (size_t)e * P, (size_t)P * 2);
+        if (lane == 4) prefetch_slab_l2(p.cz.perm_person + (size_t)e * P, (size_t)P * 2);
+        if (lane == 5) prefetch_slab_l2(p.st.p_money + (size_t)e * P, (size_t)P * 8);
+    }
     const int NM = p.st.m_count[e];
     const int NJ = p.st.j_count[e];
-    const int NR = NJ + NM;
-    // combined row index R: job offers first, then goods offers
-    auto mat_of = [&](int R) { return R < NJ ? matJ + R * kMatBytes : matM + (R - NJ) * kMatBytes; };
-    auto rec_of = [&](int R) { return R < NJ ? recJ + R * kRecBytes : recM + (R - NJ) * kRecBytes; };
+    const int NT = NJ + NM + 2;                                     // all rows, the two "no request" rows included
+    const uint32_t aRecM = keep_u32(aRec + (uint32_t)(NJ + 1) * kRecBytes);   // record / matrix row of goods offer 0
+    const uint32_t aMatM = keep_u32(aMat + (uint32_t)(NJ + 1) * kMatBytes);
 
     // ------------------------------ stage: books and firms ---------------------------------
     const IndexMap mapJ(NJ, p.flags), mapM(NM, p.flags);
-    for (int n = lane; n <= NJ; n += 32) {
-        unsigned char* rec = recJ + n * kRecBytes;
-        const bool real = n < NJ;   // row NJ = "no request": never has room, costs and pays nothing
-        rec_value(rec) = real ? p.st.j_wage[eF + n] : 0.0;
-        rec_u32(rec, kRecLeft) = real ? p.st.j_left[eF + n] : 0u;
-        rec_u32(rec, kRecTaken) = real ? p.st.j_taken[eF + n] : 0u;
-        rec_u32(rec, kRecMeta) = real ? (uint32_t)(p.st.j_owner[eF + n] & 0xFF) : 0u;
-    }
-    for (int n = lane; n <= NM; n += 32) {
-        unsigned char* rec = recM + n * kRecBytes;
-        const bool real = n < NM;
-        rec_value(rec) = real ? p.st.m_price[eCap + n] : 0.0;
-        rec_u32(rec, kRecLeft) = real ? p.st.m_left[eCap + n] : 0u;
-        rec_u32(rec, kRecTaken) = real ? p.st.m_taken[eCap + n] : 0u;
-        rec_u32(rec, kRecMeta) = real ? (uint32_t)(p.st.m_owner[eCap + n] & 0xFF) | ((uint32_t)(p.st.m_good[eCap + n] & 0xFF) << 8) : 0u;
+    for (int R = lane; R < NT; R += 32) {
+        const bool isJ = R <= NJ;
+        const int n = isJ ? R : R - NJ - 1;
+        const bool real = isJ ? n < NJ : n < NM;
+        double value = 0.0;
+        uint32_t left = 0, taken = 0, meta = 0;
+        if (real && isJ) {
+            value = p.st.j_wage[eF + n]; left = p.st.j_left[eF + n]; taken = p.st.j_taken[eF + n];
+            meta = (uint32_t)(p.st.j_owner[eF + n] & 0xFF);
+        } else if (real) {
+            value = p.st.m_price[eCap + n]; left = p.st.m_left[eCap + n]; taken = p.st.m_taken[eCap + n];
+            meta = (uint32_t)(p.st.m_owner[eCap + n] & 0xFF) | ((uint32_t)(p.st.m_good[eCap + n] & 0xFF) << 8);
+        }
+        const uint32_t rec = aRec + (uint32_t)R * kRecBytes;
+        sts_f64<kRecValue>(rec, value);
+        sts_u32<kRecLeft>(rec, left);
+        sts_u32<kRecTaken>(rec, taken);
+        sts_u32<kRecMeta>(rec, meta);
     }
     for (int f = lane; f < F; f += 32) {
-        s_fmoney[f] = p.st.f_money[eF + f];
-        s_permf[f] = do_firms ? (uint16_t)perm_firm_at(p, eF + f) : (uint16_t)f;
-        s_fnh[f] = 0;
-        s_fok[f] = 0;
-        s_fcnt[f] = 0;
-        s_ffirst[f] = 0;
-        s_frisk[f] = 0;
-        s_fjob[f] = (uint8_t)kNone;
+        sts_f64(aFmoney + 8u * f, p.st.f_money[eF + f]);
+        sts_u16(aPermf + 2u * f, do_firms ? (uint32_t)perm_firm_at(p, eF + f) : (uint32_t)f);
+        sts_u32(aFnh + 4u * f, 0u);
+        sts_u32(aFok + 4u * f, 0u);
+        sts_u8(aFcnt + f, 0u);
+        sts_u8(aFfirst + f, 0u);
+        sts_u8(aFrisk + f, 0u);
+        sts_u8(aFjob + f, (uint32_t)kNone);
 #pragma unroll
-        for (int g = 0; g < G; g++) s_finv[g * F + f] = p.st.f_inv[((size_t)e * G + g) * F + f];
-        if (do_firms) {
-            s_flast[f] = p.st.f_last_money[eF + f];
-            const size_t k0 = (size_t)e * S * F + f;
-            uint32_t w[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-            if (NM > 0) {   // empty book: no requests at all (decisionNetHandler.cpp:398-403)
-                const uint32_t tg = p.compact ? p.cz.f_good_take[eF + f] : 0u;
-#pragma unroll
-                for (int i = 0; i < kMaxStack; i++) {
-                    if (i < S) {
-                        const bool take = p.compact ? ((tg >> i) & 1u) != 0 : p.ac.f_good_take[k0 + (size_t)i * F] != 0;
-                        const int raw = p.compact ? (int)p.cz.f_good_idx[k0 + (size_t)i * F] : p.ac.f_good_idx[k0 + (size_t)i * F];
-                        list_set_byte<4>(w, i, take ? (uint32_t)mapM(raw) : (uint32_t)kNone);
-                    }
-                }
+        for (int g = 0; g < G; g++) sts_f64(aFinv + 8u * (g * F + f), p.st.f_inv[((size_t)e * G + g) * F + f]);
+        if (do_firms) sts_f64(aFlast + 8u * f, p.st.f_last_money[eF + f]);
+    }
+    if (do_firms) {
+        // the firms' own requests: byte i of firm f = goods offer number or kNone (empty book: no requests at all,
+        // decisionNetHandler.cpp:398-403)
+        for (int k = lane; k < F * 16; k += 32) {
+            const int f = k >> 4, i = k & 15;
+            uint32_t n = (uint32_t)kNone;
+            if (i < S && NM > 0) {
+                const size_t a = (size_t)e * S * F + (size_t)i * F + f;     // int32 encoding: [E][S][F]
+                const bool take = p.compact ? ((p.cz.f_good_take[eF + f] >> i) & 1u) != 0 : p.ac.f_good_take[a] != 0;
+                const int raw = p.compact ? (int)p.cz.f_good_idx[(eF + f) * S + i] : p.ac.f_good_idx[a];   // compact: [E][F][S]
+                if (take) n = (uint32_t)mapM(raw);
             }
-            *reinterpret_cast<uint4*>(s_fatt + f * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            sts_u8(aFatt + k, n);
         }
     }
     __syncwarp();
-    for (int n = lane; n < NJ; n += 32) s_fjob[rec_u32(recJ + n * kRecBytes, kRecMeta) & 0xFFu] = (uint8_t)n;
+    for (int n = lane; n < NJ; n += 32) sts_u8(aFjob + (lds_u32<kRecMeta>(aRec + (uint32_t)n * kRecBytes) & 0xFFu), (uint32_t)n);
     for (int n = lane; n < NM; n += 32) {
         // a firm's entries are contiguous in market order (it posts all its goods in one turn)
-        const uint32_t owner = rec_u32(recM + n * kRecBytes, kRecMeta) & 0xFFu;
-        const int prev = (n > 0) ? (int)(rec_u32(recM + (n - 1) * kRecBytes, kRecMeta) & 0xFFu) : -1;
-        if ((int)owner != prev) s_ffirst[owner] = (uint8_t)n;
-        if (!(rec_value(recM + n * kRecBytes) >= 0.0)) s_frisk[owner] = 1;   // a sale would not raise the seller's money
+        const uint32_t rec = aRecM + (uint32_t)n * kRecBytes;
+        const uint32_t owner = lds_u32<kRecMeta>(rec) & 0xFFu;
+        const int prev = (n > 0) ? (int)(lds_u32<kRecMeta - kRecBytes>(rec) & 0xFFu) : -1;
+        if ((int)owner != prev) sts_u8(aFfirst + owner, (uint32_t)n);
+        if (!(lds_f64<kRecValue>(rec) >= 0.0)) sts_u8(aFrisk + owner, 1u);   // a sale would not raise the seller's money
     }
     __syncwarp();
     for (int n = lane; n < NM; n += 32) {
-        const uint32_t owner = rec_u32(recM + n * kRecBytes, kRecMeta) & 0xFFu;
-        const int next = (n + 1 < NM) ? (int)(rec_u32(recM + (n + 1) * kRecBytes, kRecMeta) & 0xFFu) : -1;
-        if ((int)owner != next) s_fcnt[owner] = (uint8_t)(n + 1 - s_ffirst[owner]);
+        const uint32_t rec = aRecM + (uint32_t)n * kRecBytes;
+        const uint32_t owner = lds_u32<kRecMeta>(rec) & 0xFFu;
+        const int next = (n + 1 < NM) ? (int)(lds_u32<kRecMeta + kRecBytes>(rec) & 0xFFu) : -1;
+        if ((int)owner != next) sts_u8(aFcnt + owner, (uint32_t)(n + 1) - lds_u8(aFfirst + owner));
     }
     __syncwarp();
 
@@ -263,38 +279,42 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     const size_t row0 = (size_t)e * S * P;
     for (int base = 0; do_persons && base < P; base += 32) {
         // ---- (1) rows: death ordinals and initial rooms of the window
-        bool lj = false, lm = false;
-        for (int R = lane; R < NR; R += 32) {
-            unsigned char* rec = rec_of(R);
-            const uint32_t left = rec_u32(rec, kRecLeft);
+        bool lj = false, lm = false, rk = false;
+        for (int R = lane; R < NT; R += 32) {
+            const uint32_t rec = aRec + (uint32_t)R * kRecBytes;
+            const uint32_t left = lds_u32<kRecLeft>(rec);
+            const uint32_t meta = lds_u32<kRecMeta>(rec);
+            const int owner = (int)(meta & 0xFFu);
             uint32_t d = left;
-            if (R < NJ) {
+            if (R <= NJ) {
                 lj |= left > 0;
+                if (left > 0) {
+                    // can the firm pay every hire this window could bring?  (sufficient: wages are subtracted one by one,
+                    // rounding error << 1e-9 relative; sales only add money unless a price is negative / NaN)
+                    const double w = lds_f64<kRecValue>(rec), m0 = lds_f64(aFmoney + 8u * owner);
+                    const double most = (double)min(left, (uint32_t)kMaxHiresPerWindow);
+                    rk |= !(w >= 0.0 && lds_u8(aFrisk + owner) == 0u && (m0 - w * most >= w * (1.0 + 1e-9)));
+                }
             } else {
-                const uint32_t meta = rec_u32(rec, kRecMeta);
-                const int sel = (int)(meta & 0xFFu), good = (int)((meta >> 8) & 0xFFu);
-                d = min(left, unit_sales_possible(s_finv[good * F + sel]));
+                const int good = (int)((meta >> 8) & 0xFFu);
+                d = min(left, unit_sales_possible(lds_f64(aFinv + 8u * (good * F + owner))));
 #pragma unroll
                 for (int g = 0; g < G; g++)
-                    if (g != good && s_finv[g * F + sel] < 0.0) d = 0;   // agent.cpp:140 on a zero quantity
+                    if (g != good && lds_f64(aFinv + 8u * (g * F + owner)) < 0.0) d = 0;   // agent.cpp:140 on a zero quantity
                 lm |= left > 0;
             }
-            const int di = (int)min(d, 0x7FFFFFFFu);
-            rec_i32(rec, kRecD) = di;
-            rec_u32(rec, kRecMeta) &= 0xFFFFu;   // not re-scanned yet
-            const uint32_t rm = (uint32_t)min(di, kRoomMax) * 0x01010101u;
-            uint4* q = reinterpret_cast<uint4*>(mat_of(R));
-            q[0] = make_uint4(0u, 0u, 0u, 0u);
-            q[1] = make_uint4(0u, 0u, 0u, 0u);
-            q[2] = make_uint4(rm, rm, rm, rm);
-            q[3] = make_uint4(rm, rm, rm, rm);
-        }
-        if (lane >= 30) {   // the two "no request" rows never have room (their bytes double as sort scratch)
-            uint4* q = reinterpret_cast<uint4*>(lane == 30 ? matJ + NJ * kMatBytes : matM + NM * kMatBytes);
-            q[2] = make_uint4(0u, 0u, 0u, 0u);
-            q[3] = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t di = min(d, 0x7FFFFFFFu);
+            sts_u32<kRecD>(rec, di);
+            sts_u8<kRecScanned>(rec, 0u);
+            const uint32_t rm = min(di, (uint32_t)kRoomMax) * 0x01010101u;
+            const uint32_t mat = aMat + (uint32_t)R * kMatBytes;
+            sts_v4<kMatCnt>(mat, make_uint4(0u, 0u, 0u, 0u));
+            sts_v4<kMatCnt + 16>(mat, make_uint4(0u, 0u, 0u, 0u));
+            sts_v4<kMatRoom>(mat, make_uint4(rm, rm, rm, rm));
+            sts_v4<kMatRoom + 16>(mat, make_uint4(rm, rm, rm, rm));
         }
         const bool liveJ = __any_sync(0xffffffffu, lj), liveM = __any_sync(0xffffffffu, lm);
+        const bool risk_possible = __any_sync(0xffffffffu, rk);
         if (!liveJ && !liveM) {
             // both books are sold out: no person from here on can trade
             if (lane == 0) FASTACE_STAT(kStatDeadExits, 1);
@@ -307,35 +327,50 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             }
             break;
         }
-        // ---- (2) the lane's person: money and request lists (positions skip..SMAX-1; "no request" = row NJ / NM)
+        // ---- (2) the lane's person: money, and its request lists as offer numbers in shared memory
+        //      (slot i of the job list at aReqL + i, of the goods list at aReqL + 16 + i; "no request" = offer NJ / NM)
         const int r = base + lane;
         const bool active = r < P;
         const int pid = active ? (p.compact ? (int)p.cz.perm_person[eP + r] : p.ac.perm_person[eP + r]) : 0;
         const double money0 = active ? p.st.p_money[eP + pid] : 0.0;
-        uint32_t aj[NW], ag[NW];
+        {
+            const bool modulo = (p.flags & FASTACE_IDX_MODULO) != 0;
 #pragma unroll
-        for (int k = 0; k < NW; k++) { aj[k] = (uint32_t)NJ * 0x01010101u; ag[k] = (uint32_t)NM * 0x01010101u; }
-        if (active) {
-            const uint32_t tj = (p.compact && liveJ) ? p.cz.p_job_take[eP + pid] : 0u;
-            const uint32_t tg = (p.compact && liveM) ? p.cz.p_good_take[eP + pid] : 0u;
+            for (int ph = 0; ph < 2; ph++) {
+                const bool live = ph == 0 ? liveJ : liveM;
+                if (!live) continue;                                   // a sold-out book is not evaluated at all
+                const uint32_t dst = aReqL + (ph == 0 ? 0u : (uint32_t)kReqGoods);
+                const uint32_t dummy = (uint32_t)(ph == 0 ? NJ : NM);
+                const IndexMap& map = ph == 0 ? mapJ : mapM;
+                if (!active) {
 #pragma unroll
-            for (int k = 0; k < SMAX; k++) {
-                const int i = k - skip;
-                if (i >= 0) {
-                    const size_t a = row0 + (size_t)i * P + pid;
-                    if (liveJ) {
-                        const bool take = p.compact ? ((tj >> i) & 1u) != 0 : p.ac.p_job_take[a] != 0;
-                        const int raw = p.compact ? (int)p.cz.p_job_idx[a] : p.ac.p_job_idx[a];
-                        uint32_t n = take ? (uint32_t)mapJ(raw) : (uint32_t)kNone;
-                        if (n == (uint32_t)kNone) n = (uint32_t)NJ;
-                        aj[k >> 2] = (aj[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (n << (8 * (k & 3)));
+                    for (int q = 0; q < kMaxStack / 4; q++) sts_u32(dst + 4u * q, dummy * 0x01010101u);
+                } else if (p.compact) {
+                    // agent-major bytes: the aligned words that cover [pid*S, pid*S + S), shifted into place
+                    const uint8_t* lst = (ph == 0 ? p.cz.p_job_idx : p.cz.p_good_idx) + (eP + pid) * (size_t)S;
+                    const uint32_t take = (ph == 0 ? p.cz.p_job_take : p.cz.p_good_take)[eP + pid] & ((1u << S) - 1u);
+                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(lst) & 3u);
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(lst - sh);
+                    uint32_t raw[kMaxStack / 4 + 1];
+#pragma unroll
+                    for (int q = 0; q <= kMaxStack / 4; q++) raw[q] = (4u * q < sh + (uint32_t)S) ? wp[q] : 0u;
+#pragma unroll
+                    for (int q = 0; q < kMaxStack / 4; q++) {
+                        if (4 * q < S) {
+                            const uint32_t x = __funnelshift_r(raw[q], raw[q + 1], 8u * sh);
+                            const uint32_t t4 = take >> (4 * q);
+                            sts_u32(dst + 4u * q, modulo ? map_request_word<true>(x, t4, map, dummy) : map_request_word<false>(x, t4, map, dummy));
+                        }
                     }
-                    if (liveM) {
-                        const bool take = p.compact ? ((tg >> i) & 1u) != 0 : p.ac.p_good_take[a] != 0;
-                        const int raw = p.compact ? (int)p.cz.p_good_idx[a] : p.ac.p_good_idx[a];
-                        uint32_t n = take ? (uint32_t)mapM(raw) : (uint32_t)kNone;
-                        if (n == (uint32_t)kNone) n = (uint32_t)NM;
-                        ag[k >> 2] = (ag[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (n << (8 * (k & 3)));
+                } else {
+                    const size_t a0 = row0 + (size_t)pid;
+                    const int32_t* idx = (ph == 0 ? p.ac.p_job_idx : p.ac.p_good_idx) + a0;
+                    const uint8_t* tk = (ph == 0 ? p.ac.p_job_take : p.ac.p_good_take) + a0;
+                    for (int i = 0; i < S; i++) {
+                        const uint32_t raw = (uint32_t)idx[(size_t)i * P];
+                        uint32_t n = modulo ? map.mod24(map.mod24(raw >> 16) * map.k16 + (raw & 0xFFFFu)) : (raw < map.count ? raw : dummy);
+                        if (tk[(size_t)i * P] == 0) n = dummy;
+                        sts_u8(dst + (uint32_t)i, n);
                     }
                 }
             }
@@ -345,81 +380,63 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         // ---- (3) fixed-point rounds
         double money = money0;
         int nh = 0;
-        uint32_t okm = 0;      // successes: job positions in bits 0..15, goods positions in bits 16..31
-        unsigned char* const matJl = matJ + lane;
-        unsigned char* const matMl = matM + lane;
+        uint32_t okm = 0;      // successes: job slots in bits 0..15, goods slots in bits 16..31
+        const uint32_t aCellJ = keep_u32(aMat + (uint32_t)lane), aCellM = keep_u32(aMatM + (uint32_t)lane);
         if (lane == 0) FASTACE_STAT(kStatWindows, 1);
         for (int round = 0;; round++) {
             if (lane == 0) { FASTACE_STAT(kStatRounds, 1); FASTACE_STAT(kStatRoundsW0 + min(base >> 5, 3), 1); }
             money = money0; nh = 0; okm = 0;
+            // ---- evaluate: job requests (utilMaxer.cpp:76-85; eligible = person.cpp:39: 0.5 * nh + 0.5 <= 1)
             if (liveJ) {
-                // utilMaxer.cpp:76-85; eligible = person.cpp:39 (0.5 * nh + 0.5 <= 1)
-#define FASTACE_JOB_SLOT(K)                                                                   \
-    case K: if (K < SMAX) {                                                                   \
-        const uint32_t n = (aj[(K) >> 2] >> (8 * ((K) & 3))) & 0xFFu;                         \
-        unsigned char* cell = matJl + n * kMatBytes;                                          \
-        const uint32_t c = cell[kMatCnt];                                                     \
-        const bool el = nh < 2;                                                               \
-        if (el) cell[kMatCnt] = (uint8_t)(c + 1u);                                            \
-        if (el && c < cell[kMatRoom]) {                                                       \
-            nh++;                                                                             \
-            money += rec_value(recJ + n * kRecBytes);   /* person.cpp:49 */                   \
-            okm |= 1u << (K);                                                                 \
-        }                                                                                     \
-    }
-                switch (skip) {
-                    FASTACE_JOB_SLOT(0) FASTACE_JOB_SLOT(1) FASTACE_JOB_SLOT(2) FASTACE_JOB_SLOT(3)
-                    FASTACE_JOB_SLOT(4) FASTACE_JOB_SLOT(5) FASTACE_JOB_SLOT(6) FASTACE_JOB_SLOT(7)
-                    FASTACE_JOB_SLOT(8) FASTACE_JOB_SLOT(9) FASTACE_JOB_SLOT(10) FASTACE_JOB_SLOT(11)
-                    FASTACE_JOB_SLOT(12) FASTACE_JOB_SLOT(13) FASTACE_JOB_SLOT(14) FASTACE_JOB_SLOT(15)
-                    default: break;
+                uint32_t bit = 1u;
+#pragma unroll 2
+                for (int i = 0; i < S; i++, bit <<= 1) {
+                    const uint32_t n = lds_u8(aReqL + (uint32_t)i);
+                    const uint32_t cell = aCellJ + n * kMatBytes;
+                    const uint32_t c = lds_u8<kMatCnt>(cell);
+                    const uint32_t rm = lds_u8<kMatRoom>(cell);
+                    const double wage = lds_f64<kRecValue>(aRec + n * kRecBytes);
+                    const bool el = nh < 2;
+                    if (el) sts_u8<kMatCnt>(cell, c + 1u);
+                    const bool ok = el && c < rm;
+                    if (ok) { nh++; money += wage; okm |= bit; }          // person.cpp:49
                 }
-#undef FASTACE_JOB_SLOT
             }
+            // ---- evaluate: goods requests (utilMaxer.cpp:64-73; eligible = agent.cpp:102)
             if (liveM) {
-                // utilMaxer.cpp:64-73; eligible = agent.cpp:102
-#define FASTACE_GOOD_SLOT(K)                                                                  \
-    case K: if (K < SMAX) {                                                                   \
-        const uint32_t n = (ag[(K) >> 2] >> (8 * ((K) & 3))) & 0xFFu;                         \
-        unsigned char* cell = matMl + n * kMatBytes;                                          \
-        const double price = rec_value(recM + n * kRecBytes);                                 \
-        const uint32_t c = cell[kMatCnt];                                                     \
-        const bool el = money >= price;                                                       \
-        if (el) cell[kMatCnt] = (uint8_t)(c + 1u);                                            \
-        if (el && c < cell[kMatRoom]) {                                                       \
-            money -= price;                       /* agent.cpp:108 */                         \
-            okm |= 1u << (16 + (K));                                                          \
-        }                                                                                     \
-    }
-                switch (skip) {
-                    FASTACE_GOOD_SLOT(0) FASTACE_GOOD_SLOT(1) FASTACE_GOOD_SLOT(2) FASTACE_GOOD_SLOT(3)
-                    FASTACE_GOOD_SLOT(4) FASTACE_GOOD_SLOT(5) FASTACE_GOOD_SLOT(6) FASTACE_GOOD_SLOT(7)
-                    FASTACE_GOOD_SLOT(8) FASTACE_GOOD_SLOT(9) FASTACE_GOOD_SLOT(10) FASTACE_GOOD_SLOT(11)
-                    FASTACE_GOOD_SLOT(12) FASTACE_GOOD_SLOT(13) FASTACE_GOOD_SLOT(14) FASTACE_GOOD_SLOT(15)
-                    default: break;
+                uint32_t bit = 1u << 16;
+#pragma unroll 2
+                for (int i = 0; i < S; i++, bit <<= 1) {
+                    const uint32_t n = lds_u8<kReqGoods>(aReqL + (uint32_t)i);
+                    const uint32_t cell = aCellM + n * kMatBytes;
+                    const double price = lds_f64<kRecValue>(aRecM + n * kRecBytes);
+                    const uint32_t c = lds_u8<kMatCnt>(cell);
+                    const uint32_t rm = lds_u8<kMatRoom>(cell);
+                    const bool el = money >= price;
+                    if (el) sts_u8<kMatCnt>(cell, c + 1u);
+                    const bool ok = el && c < rm;
+                    if (ok) { money -= price; okm |= bit; }                // agent.cpp:108
                 }
-#undef FASTACE_GOOD_SLOT
             }
             __syncwarp();
 
             // ---- rows: demand of the window; over-subscribed rows whose counts moved get their rooms re-scanned
             bool changed = false;
-            for (int cb = 0; cb < NR; cb += 32) {
+            for (int cb = 0; cb < NT; cb += 32) {
                 const int R = cb + lane;
                 bool needs = false;
-                if (R < NR) {
-                    unsigned char* rec = rec_of(R);
-                    const uint4* q = reinterpret_cast<const uint4*>(mat_of(R));
-                    const uint4 a = q[0], b = q[1];
+                if (R < NT) {
+                    const uint32_t rec = aRec + (uint32_t)R * kRecBytes, mat = aMat + (uint32_t)R * kMatBytes;
+                    const uint4 a = lds_v4<kMatCnt>(mat), b = lds_v4<kMatCnt + 16>(mat);
                     const uint32_t s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;          // per byte <= 8 * 16
                     const uint32_t t = (s & 0x00FF00FFu) + ((s >> 8) & 0x00FF00FFu);
-                    const int tot = (int)((t + (t >> 16)) & 0xFFFFu);
-                    rec_i32(rec, kRecTot) = tot;
-                    const int d = rec_i32(rec, kRecD);
+                    const uint32_t tot = (t + (t >> 16)) & 0xFFFFu;
+                    sts_u32<kRecTot>(rec, tot);
+                    const uint32_t d = lds_u32<kRecD>(rec);
                     if (d > 0 && tot > 0) {
-                        if ((rec_u32(rec, kRecMeta) >> 16) != 0) {
+                        if (lds_u8<kRecScanned>(rec) != 0u) {
                             // scanned before: its rooms stand as long as the counts they were computed for do
-                            const uint4 c = q[4], dd = q[5];
+                            const uint4 c = lds_v4<kMatPrev>(mat), dd = lds_v4<kMatPrev + 16>(mat);
                             needs = ((a.x ^ c.x) | (a.y ^ c.y) | (a.z ^ c.z) | (a.w ^ c.w) |
                                      (b.x ^ dd.x) | (b.y ^ dd.y) | (b.z ^ dd.z) | (b.w ^ dd.w)) != 0u;
                         } else {
@@ -429,63 +446,69 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                 }
                 unsigned slow = __ballot_sync(0xffffffffu, needs);
                 while (slow) {
+                    // two rows per shuffle scan (16-bit halves: a prefix is at most 32 * 16)
                     const int R0 = cb + __ffs((int)slow) - 1;
                     slow &= slow - 1;
-                    unsigned char* cell = mat_of(R0) + lane;
-                    unsigned char* rec = rec_of(R0);
-                    if (lane == 0) { FASTACE_STAT(kStatRescans, 1); if (base == 0) FASTACE_STAT(kStatRescansW0, 1); }
-                    const int c = cell[kMatCnt];
-                    const int excl = warp_inclusive_scan(c, lane) - c;
-                    const int rm = max(0, min(kRoomMax, rec_i32(rec, kRecD) - excl));
-                    const int old = cell[kMatRoom];
-                    changed |= min(c, rm) != min(c, old);
-                    cell[kMatRoom] = (uint8_t)rm;
-                    cell[kMatPrev] = (uint8_t)c;
-                    if (lane == 0) rec_u32(rec, kRecMeta) |= 0x10000u;
+                    const int R1 = slow ? cb + __ffs((int)slow) - 1 : R0;
+                    slow &= slow - 1;
+                    const uint32_t cell0 = aMat + (uint32_t)R0 * kMatBytes + (uint32_t)lane, cell1 = aMat + (uint32_t)R1 * kMatBytes + (uint32_t)lane;
+                    const uint32_t rec0 = aRec + (uint32_t)R0 * kRecBytes, rec1 = aRec + (uint32_t)R1 * kRecBytes;
+                    if (lane == 0) { FASTACE_STAT(kStatRescans, R1 != R0 ? 2 : 1); if (base == 0) FASTACE_STAT(kStatRescansW0, R1 != R0 ? 2 : 1); }
+                    const uint32_t c0 = lds_u8<kMatCnt>(cell0), c1 = lds_u8<kMatCnt>(cell1);
+                    const uint32_t both = c0 | (c1 << 16);
+                    const uint32_t excl = warp_inclusive_scan(both, lane) - both;
+                    const int rm0 = max(0, min(kRoomMax, (int)lds_u32<kRecD>(rec0) - (int)(excl & 0xFFFFu)));
+                    const int rm1 = max(0, min(kRoomMax, (int)lds_u32<kRecD>(rec1) - (int)(excl >> 16)));
+                    const int old0 = (int)lds_u8<kMatRoom>(cell0), old1 = (int)lds_u8<kMatRoom>(cell1);
+                    changed |= (min((int)c0, rm0) != min((int)c0, old0)) | (min((int)c1, rm1) != min((int)c1, old1));
+                    sts_u8<kMatRoom>(cell0, (uint32_t)rm0);
+                    sts_u8<kMatPrev>(cell0, c0);
+                    sts_u8<kMatRoom>(cell1, (uint32_t)rm1);
+                    sts_u8<kMatPrev>(cell1, c1);
+                    sts_u8<kRecScanned>(rec0, 1u);
+                    sts_u8<kRecScanned>(rec1, 1u);
                 }
             }
             __syncwarp();
 
             // ---- job offers whose firm may run out of money (firm.cpp:80-84): exact running money in visiting order
-            for (int cb = 0; cb < NJ; cb += 32) {
+            for (int cb = 0; risk_possible && cb < NJ; cb += 32) {
                 const int R = cb + lane;
                 bool risky = false;
                 uint32_t left = 0;
-                int f = 0;
+                int f = 0, tot = 0;
                 double w = 0.0, m0 = 0.0;
-                unsigned char* rec = recJ + (R < NJ ? R : 0) * kRecBytes;
-                unsigned char* mat = matJ + (R < NJ ? R : 0) * kMatBytes;
+                const uint32_t rec = aRec + (uint32_t)(R < NJ ? R : 0) * kRecBytes;
+                const uint32_t mat = aMat + (uint32_t)(R < NJ ? R : 0) * kMatBytes;
                 if (R < NJ) {
-                    left = rec_u32(rec, kRecLeft);
-                    f = (int)(rec_u32(rec, kRecMeta) & 0xFFu);
-                    w = rec_value(rec);
-                    m0 = s_fmoney[f];
-                    const int tot = rec_i32(rec, kRecTot);
+                    left = lds_u32<kRecLeft>(rec);
+                    f = (int)(lds_u32<kRecMeta>(rec) & 0xFFu);
+                    w = lds_f64<kRecValue>(rec);
+                    m0 = lds_f64(aFmoney + 8u * f);
+                    tot = (int)lds_u32<kRecTot>(rec);
                     const int most = min((int)min(left, 0x7FFFFFFFu), tot);
-                    // sufficient for "every hire of the window can be paid": wages are subtracted one by one (rounding
-                    // error << 1e-9 relative for most <= 512) and sales only add money unless a price is negative / NaN
-                    const bool safe = w >= 0.0 && s_frisk[f] == 0 && (m0 - w * (double)most >= w * (1.0 + 1e-9));
+                    const bool safe = w >= 0.0 && lds_u8(aFrisk + f) == 0u && (m0 - w * (double)most >= w * (1.0 + 1e-9));
                     risky = tot > 0 && left > 0 && !safe;
                 }
                 if (__any_sync(0xffffffffu, risky)) {
                     // does the firm sell anything in this window?  (its goods rows' successes = min(tot, D))
                     bool fsales = false;
                     if (risky) {
-                        const int first = s_ffirst[f], cnt = s_fcnt[f];
+                        const int first = (int)lds_u8(aFfirst + f), cnt = (int)lds_u8(aFcnt + f);
                         for (int n = first; n < first + cnt; n++) {
-                            unsigned char* g = recM + n * kRecBytes;
-                            fsales |= min(rec_i32(g, kRecTot), rec_i32(g, kRecD)) > 0;
+                            const uint32_t g = aRecM + (uint32_t)n * kRecBytes;
+                            fsales |= min(lds_u32<kRecTot>(g), lds_u32<kRecD>(g)) > 0u;
                         }
                     }
                     if (__any_sync(0xffffffffu, fsales)) {
                         // every lane publishes the goods it currently buys, in request order
-                        int ne = 0;
+                        uint32_t ne = 0;
                         for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {
                             const int k = __ffs((int)m) - 1;
-                            s_evlist[lane * kEvPerLane + 1 + ne] = (uint8_t)list_byte<NW>(ag, k);
+                            sts_u8(aEv + (uint32_t)lane * kEvPerLane + 1u + ne, lds_u8<kReqGoods>(aReqL + (uint32_t)k));
                             ne++;
                         }
-                        s_evlist[lane * kEvPerLane] = (uint8_t)ne;
+                        sts_u8(aEv + (uint32_t)lane * kEvPerLane, ne);
                         __syncwarp();
                     }
                     if (R < NJ) {
@@ -494,7 +517,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                             // hires are the firm's only events: the order of the applicants does not matter
                             FASTACE_STAT(kStatRiskyWalks, 1);
                             double m = m0;
-                            const int most = min(d, rec_i32(rec, kRecTot));
+                            const int most = min(d, tot);
                             for (int h = 0; h < most; h++) {
                                 if (m < w) { d = h; break; }                            // firm.cpp:80-84
                                 m -= w;                                                 // firm.cpp:108
@@ -505,30 +528,30 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                             int h = 0;
                             bool done = false;
                             for (int l = 0; l < 32 && !done; l++) {
-                                const int c = mat[kMatCnt + l];
+                                const int c = (int)lds_u8<kMatCnt>(mat + (uint32_t)l);
                                 for (int k = 0; k < c; k++) {
                                     if (h >= d) { done = true; break; }                 // firm.cpp:64
                                     if (m < w) { d = h; done = true; break; }           // firm.cpp:80-84
                                     m -= w;                                             // firm.cpp:108
                                     h++;
                                 }
-                                const int nb = s_evlist[l * kEvPerLane];
+                                const int nb = (int)lds_u8(aEv + (uint32_t)l * kEvPerLane);
                                 for (int k = 0; k < nb && !done; k++) {
-                                    unsigned char* g = recM + s_evlist[l * kEvPerLane + 1 + k] * kRecBytes;
-                                    if ((int)(rec_u32(g, kRecMeta) & 0xFFu) == f) m += rec_value(g);   // agent.cpp:158
+                                    const uint32_t g = aRecM + lds_u8(aEv + (uint32_t)l * kEvPerLane + 1u + (uint32_t)k) * kRecBytes;
+                                    if ((int)(lds_u32<kRecMeta>(g) & 0xFFu) == f) m += lds_f64<kRecValue>(g);   // agent.cpp:158
                                 }
                             }
                         }
-                        if (d != rec_i32(rec, kRecD)) {
+                        if (d != (int)lds_u32<kRecD>(rec)) {
                             // the offer dies earlier / later than assumed: its rooms follow the new ordinal
                             changed = true;
-                            rec_i32(rec, kRecD) = d;
-                            rec_u32(rec, kRecMeta) |= 0x10000u;
+                            sts_u32<kRecD>(rec, (uint32_t)d);
+                            sts_u8<kRecScanned>(rec, 1u);
                             int run = 0;
                             for (int l = 0; l < 32; l++) {
-                                const int c = mat[kMatCnt + l];
-                                mat[kMatRoom + l] = (uint8_t)max(0, min(kRoomMax, d - run));
-                                mat[kMatPrev + l] = (uint8_t)c;
+                                const int c = (int)lds_u8<kMatCnt>(mat + (uint32_t)l);
+                                sts_u8<kMatRoom>(mat + (uint32_t)l, (uint32_t)max(0, min(kRoomMax, d - run)));
+                                sts_u8<kMatPrev>(mat + (uint32_t)l, (uint32_t)c);
                                 run += c;
                             }
                         }
@@ -536,159 +559,135 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                     __syncwarp();
                 }
             }
+            // ---- round end: converged? reset the counts
             const bool again = __any_sync(0xffffffffu, changed);
             if (!again) break;
             if (round >= kRoundCap) {
                 if (lane == 0) mp.dev_err[kDevErrRounds] = 1u;
                 break;
             }
-            for (int R = lane; R < NR; R += 32) {
-                uint4* q = reinterpret_cast<uint4*>(mat_of(R));
-                q[0] = make_uint4(0u, 0u, 0u, 0u);
-                q[1] = make_uint4(0u, 0u, 0u, 0u);
+            for (int R = lane; R < NT; R += 32) {
+                const uint32_t mat = aMat + (uint32_t)R * kMatBytes;
+                sts_v4<kMatCnt>(mat, make_uint4(0u, 0u, 0u, 0u));
+                sts_v4<kMatCnt + 16>(mat, make_uint4(0u, 0u, 0u, 0u));
             }
             __syncwarp();
         }
 
         // ---- (4) commit the window
-        const bool sales = __any_sync(0xffffffffu, (okm >> 16) != 0);
+        uint32_t hire1 = (uint32_t)kNone, hire2 = (uint32_t)kNone;    // the job offers this person was hired on
         if (active) {
             p.st.p_money[eP + pid] = money;
             mp.scr_pnh[eP + pid] = (uint8_t)nh;
+            uint32_t mj = okm & 0xFFFFu;
+            if (mj) { hire1 = lds_u8(aReqL + (uint32_t)(__ffs((int)mj) - 1)); mj &= mj - 1; }
+            if (mj) hire2 = lds_u8(aReqL + (uint32_t)(__ffs((int)mj) - 1));
+        }
+        uint32_t nbuy = 0;
+        {
+            // purchases: per good for update_kernel, and as an ordered list for the firms' money
             uint32_t nb[G];
 #pragma unroll
             for (int g = 0; g < G; g++) nb[g] = 0;
-            for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {          // one purchase per set bit
-                const int k = __ffs((int)m) - 1;
-                const uint32_t good = (rec_u32(recM + list_byte<NW>(ag, k) * kRecBytes, kRecMeta) >> 8) & 0xFFu;
+            for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {
+                const uint32_t n = lds_u8<kReqGoods>(aReqL + (uint32_t)(__ffs((int)m) - 1));
+                const uint32_t good = (lds_u32<kRecMeta>(aRecM + n * kRecBytes) >> 8) & 0xFFu;
 #pragma unroll
                 for (int g = 0; g < G; g++) nb[g] += (good == (uint32_t)g);
+                sts_u8(aEv + (uint32_t)lane * kEvPerLane + 1u + nbuy, n);
+                nbuy++;
             }
+            sts_u8(aEv + (uint32_t)lane * kEvPerLane, nbuy);
+            if (active) {
 #pragma unroll
-            for (int g = 0; g < G; g++) mp.scr_pnb[((size_t)e * G + g) * P + pid] = (uint8_t)nb[g];
-            write_person_ok(p, e, pid, ((okm & 0xFFFFu) >> skip) | (((okm >> 16) >> skip) << 16));
-        }
-        for (int R = lane; R < NR; R += 32) {
-            unsigned char* rec = rec_of(R);
-            const int tot = rec_i32(rec, kRecTot);
-            const int n = min(tot, rec_i32(rec, kRecD));
-            const uint32_t left = rec_u32(rec, kRecLeft);
-            if (R < NJ) {
-                rec_u32(rec, kRecLeft) = (tot > n) ? 0u : left - (uint32_t)n;    // exhausted or killed (firm.cpp:83)
-            } else {
-                uint32_t nl = left - (uint32_t)n;
-                if (tot > n && nl > 0) nl = 0;                                    // killed (agent.cpp:143)
-                rec_u32(rec, kRecLeft) = nl;
-                const uint32_t meta = rec_u32(rec, kRecMeta);
-                s_finv[((meta >> 8) & 0xFFu) * F + (meta & 0xFFu)] -= (double)n; // n exact unit subtractions (agent.cpp:156)
+                for (int g = 0; g < G; g++) mp.scr_pnb[((size_t)e * G + g) * P + pid] = (uint8_t)nb[g];
+                write_person_ok(p, e, pid, okm);
             }
-            rec_u32(rec, kRecTaken) += (uint32_t)n;
-            rec_i32(rec, kRecTot) = n;
+        }
+        const unsigned buyers = __ballot_sync(0xffffffffu, nbuy != 0u);
+        for (int R = lane; R < NT; R += 32) {
+            const uint32_t rec = aRec + (uint32_t)R * kRecBytes;
+            const uint32_t tot = lds_u32<kRecTot>(rec);
+            const uint32_t n = min(tot, lds_u32<kRecD>(rec));
+            const uint32_t left = lds_u32<kRecLeft>(rec);
+            if (R <= NJ) {
+                sts_u32<kRecLeft>(rec, (tot > n) ? 0u : left - n);                 // exhausted or killed (firm.cpp:83)
+            } else {
+                uint32_t nl = left - n;
+                if (tot > n && nl > 0) nl = 0;                                      // killed (agent.cpp:143)
+                sts_u32<kRecLeft>(rec, nl);
+                if (n > 0) {
+                    const uint32_t meta = lds_u32<kRecMeta>(rec);
+                    const uint32_t a = aFinv + 8u * (((meta >> 8) & 0xFFu) * F + (meta & 0xFFu));
+                    sts_f64(a, lds_f64(a) - (double)n);                             // n exact unit subtractions (agent.cpp:156)
+                }
+            }
+            sts_u32<kRecTaken>(rec, lds_u32<kRecTaken>(rec) + n);
+            sts_u32<kRecTot>(rec, n);
         }
         __syncwarp();
-        if (!sales) {
-            // the window's only events at a firm are hires: firm.cpp:108, one subtraction per hire
-            for (int f = lane; f < F; f += 32) {
-                const int j = s_fjob[f];
-                if (j != kNone) {
-                    unsigned char* rec = recJ + j * kRecBytes;
-                    const int h = rec_i32(rec, kRecTot);
-                    const double w = rec_value(rec);
-                    double m = s_fmoney[f];
-                    for (int k = 0; k < h; k++) m -= w;
-                    s_fmoney[f] = m;
-                    s_fnh[f] += (uint32_t)h;
+        // ---- firm money of the window, event by event in the visiting order
+        for (int fb = 0; fb < F; fb += 32) {
+            const int f = fb + lane;
+            const uint32_t j = f < F ? lds_u8(aFjob + f) : (uint32_t)kNone;
+            const bool has = j != (uint32_t)kNone;
+            const uint32_t rec = aRec + (has ? j : 0u) * kRecBytes;
+            const double w = lds_f64<kRecValue>(rec);
+            double m = f < F ? lds_f64(aFmoney + 8u * f) : 0.0;
+            uint32_t hires = has ? lds_u32<kRecTot>(rec) : 0u;
+            if (buyers == 0u) {
+                // the window's only events at a firm are hires: firm.cpp:108, one subtraction per hire
+                for (uint32_t k = 0; k < hires; k++) m -= w;
+            } else {
+                // sales interleave with hires: which lanes were hired on this firm's offer (once / twice) ...
+                if (lane == 0) FASTACE_STAT(kStatSalesWindows, 1);
+                uint32_t b1 = 0, b2 = 0;
+                for (int R = 0; R < NJ; R++) {
+                    const unsigned x = __ballot_sync(0xffffffffu, hire1 == (uint32_t)R || hire2 == (uint32_t)R);
+                    const unsigned y = __ballot_sync(0xffffffffu, hire1 == (uint32_t)R && hire2 == (uint32_t)R);
+                    if (j == (uint32_t)R) { b1 = x; b2 = y; }
                 }
-            }
-        } else {
-            // events sorted by firm, stable in (lane, jobs before goods, request order): counting sort over (firm, lane)
-            if (lane == 0) FASTACE_STAT(kStatSalesWindows, 1);
-            for (int k = lane; k < F * 8; k += 32) reinterpret_cast<uint32_t*>(s_evcnt)[k] = 0u;
-            __syncwarp();
-            if (active) {
-                for (uint32_t m = okm & 0xFFFFu; m != 0; m &= m - 1) {
-                    const int k = __ffs((int)m) - 1;
-                    const uint32_t f = rec_u32(recJ + list_byte<NW>(aj, k) * kRecBytes, kRecMeta) & 0xFFu;
-                    s_evcnt[f * 32 + lane] += 1;
-                }
-                for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {
-                    const int k = __ffs((int)m) - 1;
-                    const uint32_t f = rec_u32(recM + list_byte<NW>(ag, k) * kRecBytes, kRecMeta) & 0xFFu;
-                    s_evcnt[f * 32 + lane] += 1;
-                }
-            }
-            __syncwarp();
-            int carry = 0;
-            for (int fb = 0; fb < F; fb += 32) {
-                const int f = fb + lane;
-                int run = 0;
-                if (f < F) {
-                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(s_evcnt + f * 32);
-                    uint32_t* pw = reinterpret_cast<uint32_t*>(s_evpos + f * 32);
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const uint32_t x = cw[q];
-                        const int b0 = x & 0xFFu, b1 = (x >> 8) & 0xFFu, b2 = (x >> 16) & 0xFFu, b3 = x >> 24;
-                        pw[2 * q] = (uint32_t)run | ((uint32_t)(run + b0) << 16);
-                        pw[2 * q + 1] = (uint32_t)(run + b0 + b1) | ((uint32_t)(run + b0 + b1 + b2) << 16);
-                        run += b0 + b1 + b2 + b3;
+                // ... then, buyer by buyer: the hires up to and including that lane (jobs precede purchases,
+                // person.cpp:26-29), then its purchases from this firm in request order
+                uint32_t before = 0;
+                for (unsigned bm = buyers; bm != 0; bm &= bm - 1) {
+                    const int l = __ffs((int)bm) - 1;
+                    const uint32_t upto = 0xFFFFFFFFu >> (31 - l);
+                    const uint32_t h = (uint32_t)(__popc(b1 & upto & ~before) + __popc(b2 & upto & ~before));
+                    before = upto;
+                    for (uint32_t k = 0; k < h; k++) m -= w;                                   // firm.cpp:108
+                    const uint32_t ev = aEv + (uint32_t)l * kEvPerLane;
+                    const uint32_t ne = lds_u8(ev);
+                    for (uint32_t k = 0; k < ne; k++) {
+                        const uint32_t g = aRecM + lds_u8(ev + 1u + k) * kRecBytes;
+                        if ((int)(lds_u32<kRecMeta>(g) & 0xFFu) == f) m += lds_f64<kRecValue>(g);   // agent.cpp:158
                     }
                 }
-                const int incl = warp_inclusive_scan(run, lane);
-                if (f < F) { s_evbase[f] = (uint16_t)(carry + incl - run); s_evtot[f] = (uint16_t)run; }
-                carry += __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t h = (uint32_t)(__popc(b1 & ~before) + __popc(b2 & ~before));
+                for (uint32_t k = 0; k < h; k++) m -= w;
             }
-            __syncwarp();
-            // (a hire is list entry 0, a sale of the firm's k-th market entry is 1 + k)
-            if (active) {
-                for (uint32_t m = okm & 0xFFFFu; m != 0; m &= m - 1) {
-                    const int k = __ffs((int)m) - 1;
-                    const uint32_t f = rec_u32(recJ + list_byte<NW>(aj, k) * kRecBytes, kRecMeta) & 0xFFu;
-                    const uint32_t pos = s_evpos[f * 32 + lane];
-                    s_evpos[f * 32 + lane] = (uint16_t)(pos + 1);
-                    s_evlist[s_evbase[f] + pos] = 0;
-                }
-                for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {
-                    const int k = __ffs((int)m) - 1;
-                    const uint32_t n = list_byte<NW>(ag, k);
-                    const uint32_t f = rec_u32(recM + n * kRecBytes, kRecMeta) & 0xFFu;
-                    const uint32_t pos = s_evpos[f * 32 + lane];
-                    s_evpos[f * 32 + lane] = (uint16_t)(pos + 1);
-                    s_evlist[s_evbase[f] + pos] = (uint8_t)(1 + n - s_ffirst[f]);
-                }
-            }
-            __syncwarp();
-            for (int f = lane; f < F; f += 32) {
-                const int j = s_fjob[f];
-                const double w = (j != kNone) ? rec_value(recJ + j * kRecBytes) : 0.0;
-                const int first = s_ffirst[f], b0 = s_evbase[f], n = s_evtot[f];
-                double m = s_fmoney[f];
-                uint32_t h = 0;
-                for (int k = 0; k < n; k++) {
-                    const int t = s_evlist[b0 + k];
-                    if (t == 0) { m -= w; h++; }                                       // firm.cpp:108
-                    else m += rec_value(recM + (first + t - 1) * kRecBytes);           // agent.cpp:158
-                }
-                s_fmoney[f] = m;
-                s_fnh[f] += h;
+            if (f < F) {
+                sts_f64(aFmoney + 8u * f, m);
+                sts_u32(aFnh + 4u * f, lds_u32(aFnh + 4u * f) + hires);
             }
         }
         __syncwarp();
     }
 
+    // ---- person phase: counters to HBM
     // job counters are final after the person phase
-    if (do_persons && p.out.old_j_left) for (int n = lane; n < NJ; n += 32) p.out.old_j_left[eF + n] = rec_u32(recJ + n * kRecBytes, kRecLeft);
-    if (do_persons && p.out.old_j_taken) for (int n = lane; n < NJ; n += 32) p.out.old_j_taken[eF + n] = rec_u32(recJ + n * kRecBytes, kRecTaken);
+    if (do_persons && p.out.old_j_left) for (int n = lane; n < NJ; n += 32) p.out.old_j_left[eF + n] = lds_u32<kRecLeft>(aRec + (uint32_t)n * kRecBytes);
+    if (do_persons && p.out.old_j_taken) for (int n = lane; n < NJ; n += 32) p.out.old_j_taken[eF + n] = lds_u32<kRecTaken>(aRec + (uint32_t)n * kRecBytes);
     if (!do_firms) {
         // persons-only call: the books' counters go back to HBM for the firms call (a full step never needs them
         // there: update_kernel replaces the books)
         for (int n = lane; n < NM; n += 32) {
-            p.st.m_left[eCap + n] = rec_u32(recM + n * kRecBytes, kRecLeft);
-            p.st.m_taken[eCap + n] = rec_u32(recM + n * kRecBytes, kRecTaken);
+            p.st.m_left[eCap + n] = lds_u32<kRecLeft>(aRecM + (uint32_t)n * kRecBytes);
+            p.st.m_taken[eCap + n] = lds_u32<kRecTaken>(aRecM + (uint32_t)n * kRecBytes);
         }
         for (int n = lane; n < NJ; n += 32) {
-            p.st.j_left[eF + n] = rec_u32(recJ + n * kRecBytes, kRecLeft);
-            p.st.j_taken[eF + n] = rec_u32(recJ + n * kRecBytes, kRecTaken);
+            p.st.j_left[eF + n] = lds_u32<kRecLeft>(aRec + (uint32_t)n * kRecBytes);
+            p.st.j_taken[eF + n] = lds_u32<kRecTaken>(aRec + (uint32_t)n * kRecBytes);
         }
     }
 
@@ -697,32 +696,32 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         // requests on entries that are sold out can only fail (amountLeft never grows within a step)
         bool lv = false;
         for (int f = lane; f < F; f += 32) {
-            const uint4 slots = *reinterpret_cast<const uint4*>(s_fatt + f * 16);
+            const uint4 slots = lds_v4(aFatt + 16u * f);
             const uint32_t w[4] = {slots.x, slots.y, slots.z, slots.w};
             uint32_t live = 0;
 #pragma unroll
             for (int i = 0; i < kMaxStack; i++) {
                 const uint32_t n = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;      // kNone beyond S
-                if (n != (uint32_t)kNone && rec_u32(recM + n * kRecBytes, kRecLeft) > 0) live |= 1u << i;
+                if (n != (uint32_t)kNone && lds_u32<kRecLeft>(aRecM + n * kRecBytes) > 0u) live |= 1u << i;
             }
-            s_flive[f] = live;
+            sts_u32(aFlive + 4u * f, live);
             lv |= live != 0;
         }
         const bool anylive = __any_sync(0xffffffffu, lv);
         __syncwarp();
         // one firm's turn up to sell_goods (firm.cpp:23-37); `buys`: walk its live requests
         auto firm_turn = [&](int f, bool buys) {
-            const int first = s_ffirst[f], cnt = s_fcnt[f];
-            double money = s_fmoney[f];
+            const int first = (int)lds_u8(aFfirst + f), cnt = (int)lds_u8(aFcnt + f);
+            double money = lds_f64(aFmoney + 8u * f);
             // Agent::check_my_offers (base/agent.cpp:54-97): running inventoryLeft over own entries
             {
                 double invLeft[G];
 #pragma unroll
-                for (int g = 0; g < G; g++) invLeft[g] = s_finv[g * F + f];
+                for (int g = 0; g < G; g++) invLeft[g] = lds_f64(aFinv + 8u * (g * F + f));
                 for (int n = first; n < first + cnt; n++) {
-                    unsigned char* rec = recM + n * kRecBytes;
-                    const int good = (int)((rec_u32(rec, kRecMeta) >> 8) & 0xFFu);
-                    uint32_t left = rec_u32(rec, kRecLeft);
+                    const uint32_t rec = aRecM + (uint32_t)n * kRecBytes;
+                    const int good = (int)((lds_u32<kRecMeta>(rec) >> 8) & 0xFFu);
+                    uint32_t left = lds_u32<kRecLeft>(rec);
                     double delta = kAmountPerOffer * (double)left;     // agent.cpp:73 (other goods: 0*left = 0)
                     for (;;) {
                         bool okk = true;
@@ -735,60 +734,59 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                         delta -= kAmountPerOffer;                      // agent.cpp:79-80
                         left--;
                     }
-                    rec_u32(rec, kRecLeft) = left;
+                    sts_u32<kRecLeft>(rec, left);
 #pragma unroll
                     for (int g = 0; g < G; g++) if (g == good) invLeft[g] -= delta;  // agent.cpp:83
                 }
             }
             // first decision: profit of the previous step (neuralFirmDecisionMaker.cpp:65-74)
             {
-                const double last = s_flast[f];
-                s_flast[f] = (p.time_before > 0) ? (money - last) : 0.0;   // profit, written out below
+                const double last = lds_f64(aFlast + 8u * f);
+                sts_f64(aFlast + 8u * f, (p.time_before > 0) ? (money - last) : 0.0);   // profit, written out below
                 p.st.f_last_money[eF + f] = money;
             }
             // ProfitMaxer::buy_goods (firms/profitMaxer.cpp:102-111); the buyer's money stays in a register
             uint32_t ok = 0;
             if (buys) {
-                for (uint32_t lm = s_flive[f]; lm != 0; lm &= lm - 1) {
+                for (uint32_t lm = lds_u32(aFlive + 4u * f); lm != 0; lm &= lm - 1) {
                     const int i = __ffs((int)lm) - 1;
-                    const int n = s_fatt[f * 16 + i];
-                    unsigned char* rec = recM + n * kRecBytes;
-                    const double price = rec_value(rec);
+                    const uint32_t rec = aRecM + lds_u8(aFatt + 16u * f + (uint32_t)i) * kRecBytes;
+                    const double price = lds_f64<kRecValue>(rec);
                     if (money >= price) {                                  // agent.cpp:102
-                        const uint32_t left = rec_u32(rec, kRecLeft);
+                        const uint32_t left = lds_u32<kRecLeft>(rec);
                         if (left > 0) {                                    // agent.cpp:124
-                            const uint32_t meta = rec_u32(rec, kRecMeta);
+                            const uint32_t meta = lds_u32<kRecMeta>(rec);
                             const int s = (int)(meta & 0xFFu), good = (int)((meta >> 8) & 0xFFu);
                             bool short_ = false;                           // agent.cpp:140
 #pragma unroll
                             for (int g = 0; g < G; g++) {
                                 const double q = (g == good) ? kAmountPerOffer : 0.0;
-                                if (s_finv[g * F + s] < q) short_ = true;
+                                if (lds_f64(aFinv + 8u * (g * F + s)) < q) short_ = true;
                             }
                             if (short_) {
-                                rec_u32(rec, kRecLeft) = 0;                // agent.cpp:143
+                                sts_u32<kRecLeft>(rec, 0u);                // agent.cpp:143
                             } else {
                                 // seller first (agent.cpp:155-160), then buyer (agent.cpp:108-109)
-                                if (s == f) money += price; else s_fmoney[s] += price;
-                                s_finv[good * F + s] -= kAmountPerOffer;
-                                rec_u32(rec, kRecLeft) = left - 1;
-                                rec_u32(rec, kRecTaken) += 1;
+                                if (s == f) money += price; else sts_f64(aFmoney + 8u * s, lds_f64(aFmoney + 8u * s) + price);
+                                sts_f64(aFinv + 8u * (good * F + s), lds_f64(aFinv + 8u * (good * F + s)) - kAmountPerOffer);
+                                sts_u32<kRecLeft>(rec, left - 1);
+                                sts_u32<kRecTaken>(rec, lds_u32<kRecTaken>(rec) + 1u);
                                 money -= price;
-                                s_finv[good * F + f] += kAmountPerOffer;
+                                sts_f64(aFinv + 8u * (good * F + f), lds_f64(aFinv + 8u * (good * F + f)) + kAmountPerOffer);
                                 ok |= 1u << i;
                             }
                         }
                     }
                 }
             }
-            s_fmoney[f] = money;
-            s_fok[f] = ok;
+            sts_f64(aFmoney + 8u * f, money);
+            sts_u32(aFok + 4u * f, ok);
             // ProfitMaxer::sell_goods withdraws last step's offers (firms/profitMaxer.cpp:79-81);
             // nothing between buy_goods and that point touches another agent.
             for (int n = first; n < first + cnt; n++) {
-                unsigned char* rec = recM + n * kRecBytes;
-                rec_i32(rec, kRecD) = (int)rec_u32(rec, kRecLeft);   // final counter of the withdrawn entry
-                rec_u32(rec, kRecLeft) = 0;
+                const uint32_t rec = aRecM + (uint32_t)n * kRecBytes;
+                sts_u32<kRecD>(rec, lds_u32<kRecLeft>(rec));     // final counter of the withdrawn entry
+                sts_u32<kRecLeft>(rec, 0u);
             }
         };
         if (!anylive) {
@@ -796,24 +794,24 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             for (int f = lane; f < F; f += 32) firm_turn(f, false);
         } else if (lane == 0) {
             FASTACE_STAT(kStatFirmSerial, 1);
-            for (int r = 0; r < F; r++) firm_turn((int)s_permf[r], true);   // visiting order (economy.cpp:121-123)
+            for (int r = 0; r < F; r++) firm_turn((int)lds_u16(aPermf + 2u * r), true);   // visiting order (economy.cpp:121-123)
         }
         __syncwarp();
     }
     // ------------------------------ firms: results to HBM -----------------------------------
-    if (do_firms && p.out.old_m_left) for (int n = lane; n < NM; n += 32) p.out.old_m_left[eCap + n] = (uint32_t)rec_i32(recM + n * kRecBytes, kRecD);
-    if (do_firms && p.out.old_m_taken) for (int n = lane; n < NM; n += 32) p.out.old_m_taken[eCap + n] = rec_u32(recM + n * kRecBytes, kRecTaken);
+    if (do_firms && p.out.old_m_left) for (int n = lane; n < NM; n += 32) p.out.old_m_left[eCap + n] = lds_u32<kRecD>(aRecM + (uint32_t)n * kRecBytes);
+    if (do_firms && p.out.old_m_taken) for (int n = lane; n < NM; n += 32) p.out.old_m_taken[eCap + n] = lds_u32<kRecTaken>(aRecM + (uint32_t)n * kRecBytes);
     for (int f = lane; f < F; f += 32) {
-        p.st.f_money[eF + f] = s_fmoney[f];
-        if (do_firms) p.out.f_profit[eF + f] = s_flast[f];
+        p.st.f_money[eF + f] = lds_f64(aFmoney + 8u * f);
+        if (do_firms) p.out.f_profit[eF + f] = lds_f64(aFlast + 8u * f);
 #pragma unroll
-        for (int g = 0; g < G; g++) p.st.f_inv[((size_t)e * G + g) * F + f] = s_finv[g * F + f];
+        for (int g = 0; g < G; g++) p.st.f_inv[((size_t)e * G + g) * F + f] = lds_f64(aFinv + 8u * (g * F + f));
         double labor = p.st.f_labor[eF + f];
-        const uint32_t nhf = s_fnh[f];
+        const uint32_t nhf = lds_u32(aFnh + 4u * f);
         for (uint32_t k = 0; k < nhf; k++) labor += kLaborPerOffer;  // firm.cpp:109, one add per hire
         p.st.f_labor[eF + f] = labor;
         if (do_firms && p.out.f_good_ok) {
-            const uint32_t ok = s_fok[f];
+            const uint32_t ok = lds_u32(aFok + 4u * f);
             for (int i = 0; i < S; i++) p.out.f_good_ok[((size_t)e * S + i) * F + f] = (ok >> i) & 1u;
         }
     }

@@ -184,6 +184,30 @@ class BatchedEconomy:
         ac = actions if isinstance(actions, _abi.Actions) else _abi.struct_from_numpy("actions", actions, self.dims)
         lib.check(self._lib.fastace_env_step_host(self._h, C.byref(ac), C.byref(ou), int(flags)))
 
+    def shuffle_orders(self, seed=0, restart=False, steps=1, perm_person=None, perm_firm=None, stream=None):
+        """Economy::time_step's visiting orders for the next `steps` steps, generated ON THE DEVICE (bit-identical to
+        std::shuffle with each economy's minstd_rand0; economy.cpp:110-111).  `perm_person` / `perm_firm`: torch CUDA
+        tensors [steps][E][P] / [steps][E][F], int32 or int16 (= the compact encoding's 16-bit orders); allocated
+        (int32) when None.  Returns (perm_person, perm_firm)."""
+        torch = _torch()
+        E, P, F = self.dims.num_econ, self.dims.num_persons, self.dims.num_firms
+        dev = torch.device("cuda", self.device)
+        if perm_person is None:
+            perm_person = torch.empty((steps, E, P), dtype=torch.int32, device=dev)
+        if perm_firm is None:
+            perm_firm = torch.empty((steps, E, F), dtype=torch.int32, device=dev)
+        for t, n in ((perm_person, steps * E * P), (perm_firm, steps * E * F)):
+            if not t.is_cuda or not t.is_contiguous() or t.numel() != n or t.dtype not in (torch.int32, torch.int16):
+                raise ValueError("orders: need contiguous CUDA int32 / int16 tensors of [steps][E][agents]")
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        p32 = lambda t: C.c_void_p(t.data_ptr()) if t.dtype == torch.int32 else None
+        p16 = lambda t: C.c_void_p(t.data_ptr()) if t.dtype == torch.int16 else None
+        lib.check(self._lib.fastace_env_shuffle_orders(self._h, int(seed) & 0xFFFFFFFF, 1 if restart else 0, int(steps),
+                                                       p32(perm_person), p32(perm_firm), p16(perm_person), p16(perm_firm),
+                                                       C.c_void_p(stream)))
+        return perm_person, perm_firm
+
     def large_stats(self):
         """(person-phase rounds, firm-phase rounds) of the last large-economy step"""
         a, b = C.c_uint32(0), C.c_uint32(0)

@@ -188,3 +188,29 @@ def train(scenarioParams, trainingParams, fromPretrained=False, perturbationSize
         setattr(tp, n + "LR", lr)
     env.close()
     return losses
+
+
+# ---- behind the C symbols `run` / `train` (csrc/legacy_capi.cpp): addresses of the caller's structs ---------------------
+def _env_options():
+    return dict(numEconomies=int(os.environ.get("FASTACE_NUM_ECONOMIES", "64")), device=int(os.environ.get("FASTACE_DEVICE", "0")),
+                seed=int(os.environ.get("FASTACE_SEED", "0")))
+
+
+def _c_train(out_addr, sp_addr, tp_addr, from_pretrained, perturbation):
+    """train(double* output, const CustomScenarioParams*, TrainingParams*, bool, double) of src/pybindings.cpp:92-114"""
+    import ctypes as C
+    sp = _abi.CustomScenarioParams.from_address(sp_addr)
+    tp = _abi.TrainingParams.from_address(tp_addr)          # learning rates are written back in place
+    losses = train(sp, tp, fromPretrained=bool(from_pretrained), perturbationSize=float(perturbation), **_env_options())
+    out = (C.c_double * int(tp.numEpisodes)).from_address(out_addr)
+    for i, v in enumerate(losses):
+        out[i] = float(v)
+    return 0
+
+
+def _c_run(sp_addr, tp_addr, _unused, _flag, _value):
+    """run(CustomScenarioParams, TrainingParams) of src/pybindings.cpp:78-89 (the C side hands over its by-value copies)"""
+    sp = _abi.CustomScenarioParams.from_address(sp_addr)
+    tp = _abi.TrainingParams.from_address(tp_addr)
+    run(sp, tp, **_env_options())
+    return 0

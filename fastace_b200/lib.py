@@ -19,8 +19,8 @@ EXPORTED_SYMBOLS = [
     "fastace_env_set_state", "fastace_env_get_state", "fastace_env_device_state",
     "fastace_env_step_device", "fastace_env_step_host", "fastace_env_step_device_compact",
     "fastace_env_step_host_compact", "fastace_env_sync", "fastace_env_launch_count", "fastace_env_kernel_times", "fastace_env_large_stats", "fastace_mlp_stack_layout", "fastace_mlp_residual_tanh_stack", "fastace_mlp_forward", "fastace_layer_forward", "fastace_layer_backward",
-    "create_scenario_params", "create_training_params",
-    "fastace_scenario_custom_init", "fastace_shuffle_orders",
+    "create_scenario_params", "create_training_params", "run", "train",
+    "fastace_scenario_custom_init", "fastace_shuffle_orders", "fastace_env_shuffle_orders",
 ]
 
 
@@ -91,12 +91,19 @@ def load():
     L.create_scenario_params.argtypes = [C.c_uint, C.c_uint]
     L.create_training_params.restype = _abi.TrainingParams
     L.create_training_params.argtypes = []
+    # the reference's own prototypes, py/main.py:96-109
+    L.run.argtypes = [_abi.CustomScenarioParams, _abi.TrainingParams]
+    L.run.restype = None
+    L.train.argtypes = [C.POINTER(C.c_double), C.POINTER(_abi.CustomScenarioParams), C.POINTER(_abi.TrainingParams), C.c_bool, C.c_double]
+    L.train.restype = None
     L.fastace_scenario_custom_init.restype = C.c_int
     L.fastace_scenario_custom_init.argtypes = [C.POINTER(_abi.Dims), C.POINTER(_abi.CustomScenarioParams), C.c_uint32,
                                                C.POINTER(_abi.State), C.POINTER(C.c_double)]
     L.fastace_shuffle_orders.restype = C.c_int
     L.fastace_shuffle_orders.argtypes = [C.POINTER(_abi.Dims), C.c_uint32, C.POINTER(C.c_uint64),
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
+    L.fastace_env_shuffle_orders.restype = C.c_int
+    L.fastace_env_shuffle_orders.argtypes = [vp, C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     if L.fastace_abi_version() != _abi.ABI_VERSION:
         raise FastaceError("libfastace_b200.so ABI version mismatch")
     _lib = L

@@ -32,13 +32,14 @@
 #ifndef FASTACE_B200_H
 #define FASTACE_B200_H
 
+#include <stdbool.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define FASTACE_ABI_VERSION 2
+#define FASTACE_ABI_VERSION 3
 
 typedef enum fastace_status {
     FASTACE_OK = 0,
@@ -183,17 +184,19 @@ typedef struct fastace_actions {
  * (the books of this kernel never exceed 254 entries), the Bernoulli outcomes of an agent's S
  * slots are one bit mask (bit i = slot i), visiting orders are 16-bit.  With FASTACE_IDX_MODULO
  * the byte is a raw draw mapped to draw % count; otherwise it is the index itself (>= count: no
- * request).
+ * request).  The index arrays are AGENT-MAJOR — the S bytes of one agent are contiguous, so that
+ * the lane that owns a person fetches its whole request list with three 32-bit loads; device
+ * arrays must be 4-byte aligned and readable up to the next multiple of 4 bytes.
  */
 typedef struct fastace_actions_compact {
     const uint16_t* perm_person;   /* [E][P]    */
     const uint16_t* perm_firm;     /* [E][F]    */
-    const uint8_t*  p_job_idx;     /* [E][S][P] */
+    const uint8_t*  p_job_idx;     /* [E][P][S] */
     const uint16_t* p_job_take;    /* [E][P]    */
-    const uint8_t*  p_good_idx;    /* [E][S][P] */
+    const uint8_t*  p_good_idx;    /* [E][P][S] */
     const uint16_t* p_good_take;   /* [E][P]    */
     const float*    p_consume;     /* [E][G][P] */
-    const uint8_t*  f_good_idx;    /* [E][S][F] */
+    const uint8_t*  f_good_idx;    /* [E][F][S] */
     const uint16_t* f_good_take;   /* [E][F]    */
     const float*    f_prod;        /* [E][G][F] */
     const float*    f_offer_amt;   /* [E][G][F] */
@@ -392,6 +395,18 @@ typedef struct fastace_training_params {
 /* same names and by-value struct returns as src/pybindings.cpp:8-18 */
 fastace_custom_scenario_params_t create_scenario_params(unsigned int numPeople, unsigned int numFirms);
 fastace_training_params_t        create_training_params(void);
+
+/* `run` and `train` of libpybindings.so, as py/main.py binds and calls them (py/main.py:96-126, 151-155;
+ * src/pybindings.h:16-27, src/pybindings.cpp:78-114): structs BY VALUE for run; for train `output` receives
+ * trainingParams->numEpisodes episode losses (caller-owned) and the learning rates the schedulers end on are written
+ * back into *trainingParams; checkpoints under ../models/ relative to the working directory (neuralConstants.h:32).
+ * The episode loop, the eleven decision networks and the actor-critic trainer live in fastace_b200/legacy.py; these
+ * entry points call it through the CPython C API of the process they are loaded into (py/main.py's own interpreter),
+ * or start an interpreter for a non-Python caller.  Batch size / device of the batched env: environment variables
+ * FASTACE_NUM_ECONOMIES (default 64), FASTACE_DEVICE (default 0), FASTACE_SEED (default 0). */
+void run(fastace_custom_scenario_params_t scenarioParams, fastace_training_params_t trainingParams);
+void train(double* output, const fastace_custom_scenario_params_t* scenarioParams, fastace_training_params_t* trainingParams,
+           bool fromPretrained, double perturbationSize);
 
 /* ---- scenario initial state (host side) ---------------------------------------------- */
 /* Fills a HOST fastace_state_t for E economies with the initial-state distributions of

@@ -22,7 +22,7 @@ def needs_build():
 def build(force=False):
     if not force and not needs_build():
         return LIB
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-attributes", "-Wno-unknown-pragmas",
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-attributes", "-Wno-unknown-pragmas",
            "-x", "c++", "-I", CUDA_INC, "-I", HERE, "-o", LIB, os.path.join(HERE, "emu_step.cpp")]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:

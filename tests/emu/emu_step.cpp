@@ -22,8 +22,7 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
     mp.sp = sp; mp.scr_pnh = pnh.data(); mp.scr_pnb = pnb.data(); mp.dev_err = err;
     mp.lay = make_match_layout(sp.P, sp.F, G, sp.S);
     if (!ph_c) {
-        if (sp.S <= 12) emu::launch(match_kernel<G, 12>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
-        else emu::launch(match_kernel<G, 16>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+        emu::launch(match_kernel<G>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
     }
     UpdateParams up;
     up.sp = sp; up.scr_pnh = pnh.data(); up.scr_pnb = pnb.data();

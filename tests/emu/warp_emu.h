@@ -48,13 +48,15 @@ struct Block {
     std::function<void()> body;
 };
 
-inline Block*& cur_block() { static thread_local Block* b = nullptr; return b; }
+inline Block* g_block = nullptr;            // the emulator is single-threaded
+inline unsigned char* g_smem = nullptr;
+inline Block*& cur_block() { return g_block; }
 
 inline uint3 tid() { Block* b = cur_block(); return b->threads[b->cur].tid; }
 inline uint3 bid() { return cur_block()->bid; }
 inline dim3 bdim() { return cur_block()->bdim; }
 inline dim3 gdim() { return cur_block()->gdim; }
-inline unsigned char* dyn_smem() { return cur_block()->smem.data(); }
+inline unsigned char* dyn_smem() { return g_smem; }
 
 inline void yield_to_scheduler() {
     Block* b = cur_block();
@@ -101,6 +103,7 @@ inline void trampoline() {
 
 inline void run_block(Block& b) {
     cur_block() = &b;
+    g_smem = b.smem.data();
     const int n = (int)b.threads.size();
     for (int t = 0; t < n; t++) {
         Thread& T = b.threads[t];
@@ -183,6 +186,24 @@ template <typename T> inline T from_bits(uint64_t u) { T v; std::memcpy(&v, &u, 
 #define blockDim (emu::bdim())
 #define gridDim (emu::gdim())
 #define FASTACE_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+// the explicit shared-memory accessors of common.cuh over the emulated block buffer (address = offset in it)
+#define FASTACE_HAVE_SMEM_OPS
+namespace fastace {
+inline uint32_t smem_addr(const void* p) { return (uint32_t)(static_cast<const unsigned char*>(p) - emu::dyn_smem()); }
+inline uint32_t keep_u32(uint32_t x) { return x; }
+template <typename T> inline T emu_ld(uint32_t a) { T v; std::memcpy(&v, emu::dyn_smem() + a, sizeof(T)); return v; }
+template <typename T> inline void emu_st(uint32_t a, T v) { std::memcpy(emu::dyn_smem() + a, &v, sizeof(T)); }
+template <int OFF = 0> inline uint32_t lds_u8(uint32_t a) { return emu_ld<uint8_t>(a + OFF); }
+template <int OFF = 0> inline uint32_t lds_u16(uint32_t a) { return emu_ld<uint16_t>(a + OFF); }
+template <int OFF = 0> inline uint32_t lds_u32(uint32_t a) { return emu_ld<uint32_t>(a + OFF); }
+template <int OFF = 0> inline double lds_f64(uint32_t a) { return emu_ld<double>(a + OFF); }
+template <int OFF = 0> inline uint4 lds_v4(uint32_t a) { return emu_ld<uint4>(a + OFF); }
+template <int OFF = 0> inline void sts_u8(uint32_t a, uint32_t v) { emu_st<uint8_t>(a + OFF, (uint8_t)v); }
+template <int OFF = 0> inline void sts_u16(uint32_t a, uint32_t v) { emu_st<uint16_t>(a + OFF, (uint16_t)v); }
+template <int OFF = 0> inline void sts_u32(uint32_t a, uint32_t v) { emu_st<uint32_t>(a + OFF, v); }
+template <int OFF = 0> inline void sts_f64(uint32_t a, double v) { emu_st<double>(a + OFF, v); }
+template <int OFF = 0> inline void sts_v4(uint32_t a, uint4 v) { emu_st<uint4>(a + OFF, v); }
+}
 namespace emu { inline unsigned long long* stats() { static unsigned long long s[16] = {}; return s; } }
 #define FASTACE_STAT(which, n) (emu::stats()[which] += (n))
 

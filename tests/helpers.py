@@ -71,6 +71,34 @@ def compare_outputs(got, want, dims, state_before, rtol=RTOL):
     return worst
 
 
+def compare_all_fast(got_state, want_state, got_out, want_out, dims, state_before, rtol=RTOL):
+    """compare_states + compare_outputs without per-economy Python loops (full-size runs): books over their live
+    prefix through masks; integers exact, floating point `rtol`; money / labour bit-exact."""
+    E, P, F, G, S = dims
+    for k in EXACT_STATE:
+        assert np.array_equal(got_state[k], want_state[k]), k
+    live_m = np.arange(F * G)[None, :] < want_state["m_count"][:, None]
+    live_j = np.arange(F)[None, :] < want_state["j_count"][:, None]
+    for k in EXACT_BOOK_M:
+        assert np.array_equal(got_state[k][live_m], want_state[k][live_m]), k
+    for k in EXACT_BOOK_J:
+        assert np.array_equal(got_state[k][live_j], want_state[k][live_j]), k
+    assert_close("m_price", got_state["m_price"][live_m], want_state["m_price"][live_m], rtol)
+    assert_close("j_wage", got_state["j_wage"][live_j], want_state["j_wage"][live_j], rtol)
+    for k in FLOAT_STATE:
+        assert_close(k, got_state[k], want_state[k], rtol)
+    for k in ("p_money", "f_money", "p_labor", "f_last_money"):
+        assert np.array_equal(got_state[k], want_state[k], equal_nan=True), k + " is not bit-identical"
+    for k in ("p_job_ok", "p_good_ok", "f_good_ok"):
+        assert np.array_equal(got_out[k], want_out[k]), k
+    old_m = np.arange(F * G)[None, :] < state_before["m_count"][:, None]
+    old_j = np.arange(F)[None, :] < state_before["j_count"][:, None]
+    for k, m in (("old_m_left", old_m), ("old_m_taken", old_m), ("old_j_left", old_j), ("old_j_taken", old_j)):
+        assert np.array_equal(got_out[k][m], want_out[k][m]), k
+    assert_close("p_reward", got_out["p_reward"], want_out["p_reward"], rtol)
+    assert_close("f_profit", got_out["f_profit"], want_out["f_profit"], rtol)
+
+
 def copy_state(state):
     return {k: v.copy() for k, v in state.items()}
 

@@ -124,3 +124,22 @@ def test_phase_wise_calls_equal_one_call(emu, oracle):
             assert np.array_equal(one[k], two[k], equal_nan=True), (k, t)
         for k in ("p_reward", "f_profit", "p_job_ok", "p_good_ok", "f_good_ok"):
             assert np.array_equal(o1[k], o2[k], equal_nan=True), (k, t)
+
+
+def test_firm_money_near_tie(emu, oracle):
+    """the third applicant's fate hangs on the last bit of the firm's running money (tests/near_tie.py)"""
+    from tests import near_tie
+    dims, state, acts, ties = near_tie.build(24, seed=3)
+    ost, est = H.copy_state(state), H.copy_state(state)
+    for t, act in enumerate(acts):
+        before = H.copy_state(ost)
+        oout, eout = _abi.alloc_host("out", dims), _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=_abi.IDX_ABSOLUTE, time_before=t)
+        emu.step(dims, est, act, eout, flags=_abi.IDX_ABSOLUTE, time_before=t)
+        H.compare_outputs(eout, oout, dims, before)
+        H.compare_states(est, ost, dims)
+        for k in EXACT_FLOAT:
+            assert np.array_equal(est[k], ost[k], equal_nan=True), (k, t)
+    hired = np.array([h for (_, _, _, h) in ties])
+    assert np.array_equal(oout["p_job_ok"][:, 0, 2].astype(bool), hired)     # the reference decides as constructed ...
+    assert hired.any() and (~hired).any()                                   # ... both ways

@@ -297,3 +297,28 @@ def test_two_call_step_equals_one_call(oracle):
         H.compare_states(s2, s1, dims)
     assert one.get_time() == two.get_time() == 14
     one.close(); two.close()
+
+
+@pytest.mark.parametrize("mode", [0, _abi.STEP_SERIAL, _abi.STEP_LARGE])
+def test_firm_money_near_tie(oracle, mode):
+    """constructed near-ties (tests/near_tie.py): the third applicant is hired / refused by the LAST BIT of the firm's
+    running money, which comes out right only in the reference's operation order (hire, sale, hire)"""
+    from fastace_b200.env import BatchedEconomy
+    from tests import near_tie
+    dims, state, acts, ties = near_tie.build(48, seed=5)
+    env = BatchedEconomy(dims)
+    env.set_state(state)
+    ost = H.copy_state(state)
+    for t, act in enumerate(acts):
+        before = H.copy_state(ost)
+        oout, gout = _abi.alloc_host("out", dims), _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=_abi.IDX_ABSOLUTE, time_before=t)
+        env.time_step_host(act, gout, flags=_abi.IDX_ABSOLUTE | mode)
+        H.compare_outputs(gout, oout, dims, before)
+        got = env.get_state()
+        H.compare_states(got, ost, dims)
+        for k in ("p_money", "f_money", "p_labor"):
+            assert np.array_equal(got[k], ost[k]), (k, t)
+    hired = np.array([h for (_, _, _, h) in ties])
+    assert np.array_equal(gout["p_job_ok"][:, 0, 2].astype(bool), hired) and hired.any() and (~hired).any()
+    env.close()
