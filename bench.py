@@ -278,7 +278,7 @@ def run_ours(args):
     dcz = [env.pack_device("compact", env.alloc_compact_actions(cz)) for cz in host_cz]
     reset_state(0)
 
-    def timed_run(step_structs, n_warm, n_steps):
+    def timed_run(step_structs, n_warm, n_steps, flags=_abi.IDX_MODULO):
         """W untimed + K timed steps, every step bracketed by CUDA events on the launching stream, L2 flushed between
         steps; returns (per-step ms of this rank, launches, wall seconds)."""
         for t in range(n_warm):
@@ -286,7 +286,7 @@ def run_ours(args):
                 reset_state(t)
             if not args.no_flush:
                 flush.zero_()
-            env.time_step(step_structs[t % EPISODE], dout, flags=_abi.IDX_MODULO)
+            env.time_step(step_structs[t % EPISODE], dout, flags=flags)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -302,7 +302,7 @@ def run_ours(args):
             if not args.no_flush:
                 flush.zero_()
             starts[i].record()
-            env.time_step(step_structs[t % EPISODE], dout, flags=_abi.IDX_MODULO)
+            env.time_step(step_structs[t % EPISODE], dout, flags=flags)
             stops[i].record()
         torch.cuda.synchronize()
         w = time.perf_counter() - w0
@@ -318,7 +318,8 @@ def run_ours(args):
 
     sampler = ClockSampler(local)   # samples through warm-up and the timed region (same load)
     sampler.start()
-    step_ms, launches, wall = timed_run(dcz, args.warmup, args.steps)
+    # (a compact index byte is already `draw % book size`: it is used as the index itself)
+    step_ms, launches, wall = timed_run(dcz, args.warmup, args.steps, flags=_abi.IDX_ABSOLUTE)
     sampler.stop_flag = True
     sampler.join()
     total_ms = float(step_ms.sum())
@@ -336,7 +337,7 @@ def run_ours(args):
             reset_state(i)
         if not args.no_flush:
             flush.zero_()
-        env.time_step(dcz[i % EPISODE], dout, flags=_abi.IDX_MODULO | _abi.STEP_PROFILE)
+        env.time_step(dcz[i % EPISODE], dout, flags=_abi.IDX_ABSOLUTE | _abi.STEP_PROFILE)
     match_ms, update_ms, prof_steps = env.kernel_times()
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers) -------------------
@@ -399,7 +400,7 @@ def run_ours(args):
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         return world * E * (P + F) * n / float(t_e.item())
 
-    e2e_value = run_e2e(pinned_c, _abi.IDX_MODULO | _abi.STEP_ASYNC, e2e_steps)
+    e2e_value = run_e2e(pinned_c, _abi.IDX_ABSOLUTE | _abi.STEP_ASYNC, e2e_steps)
     e2e_int32 = run_e2e(pinned_i, _abi.IDX_MODULO, len(pinned_i))
 
     # ---- full rollout (config C flavour): batched policy forward on tensor cores + env step ----------

@@ -11,6 +11,17 @@
 #define FASTACE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
+// Programmatic dependent launch (sm_90+): a kernel launched with programmatic stream serialization may start while
+// its predecessor in the stream is still draining; it must not touch the predecessor's outputs before
+// grid_dependency_wait(), and the predecessor lets it be scheduled early with grid_launch_dependents().
+#ifndef FASTACE_HAVE_SMEM_OPS
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+inline void grid_dependency_wait() {}
+inline void grid_launch_dependents() {}
+#endif
+
 // event counters of the CPU emulation build (how many rounds / re-scans / slow paths a workload takes); nothing
 // on the device
 #ifndef FASTACE_STAT

@@ -209,6 +209,22 @@ static int carve(const std::vector<FieldDesc>& fields, StructT* s, void** block,
     return FASTACE_OK;
 }
 
+// Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor in the stream is
+// still draining (both step kernels call griddepcontrol.wait before they touch the predecessor's outputs), so launch
+// latency and the ramp of one kernel hide under the tail of the other.
+template <typename ParamsT>
+static cudaError_t launch_dependent(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, ParamsT* params) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    void* args[] = {(void*)params};
+    return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
 typedef void (*serial_fn)(const StepParams);
 typedef void (*match_fn)(const MatchParams);
 typedef void (*update_fn)(const UpdateParams);
@@ -681,7 +697,7 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         mp.lay = make_match_layout(sp.P, sp.F, env->dims.num_goods, sp.S);
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[0], stream));
         if (!ph_c) {   // a consume-only call has no matching to do
-            ks.match<<<sp.E, 32, env->match_smem_bytes, stream>>>(mp);
+            FASTACE_CUDA_CHECK(launch_dependent((const void*)ks.match, dim3((unsigned)sp.E), dim3(32), env->match_smem_bytes, stream, &mp));
             FASTACE_CUDA_CHECK(cudaGetLastError());
             env->launches += 1;
         }
@@ -693,7 +709,7 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         const int person_blocks = only_f ? 0 : (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
         up.firm_blocks = only_p ? 0 : (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
         if (person_blocks + up.firm_blocks > 0) {
-            ks.update<<<person_blocks + up.firm_blocks, kUpdateThreads, 0, stream>>>(up);
+            FASTACE_CUDA_CHECK(launch_dependent((const void*)ks.update, dim3((unsigned)(person_blocks + up.firm_blocks)), dim3(kUpdateThreads), 0, stream, &up));
             env->launches += 1;
         }
         FASTACE_CUDA_CHECK(cudaGetLastError());

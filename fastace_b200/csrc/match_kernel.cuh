@@ -63,6 +63,7 @@ constexpr int kRecD = 16;       // i32     death ordinal of the window; firm pha
 constexpr int kRecTot = 20;     // i32     eligible requests of the window; after the commit: successes
 constexpr int kRecMeta = 24;    // u32     owner | good << 8
 constexpr int kRecScanned = 28; // u8      the rooms of this window have been re-scanned (they follow `prev`)
+constexpr int kRecSafe = 30;    // u16     job rows: hires of this window the firm can certainly pay (see the prologue)
 constexpr int kRoomMax = 127;   // rooms are clamped here (a lane has at most FASTACE_MAX_STACK requests)
 constexpr int kRoundCap = 200;  // > 2 * 32 + 2, the proven bound: reaching it raises kDevErrRounds
 constexpr int kEvPerLane = 2 + FASTACE_MAX_STACK;   // list of one lane's purchases: count byte + <= S rows
@@ -201,6 +202,9 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         if (lane == 4) prefetch_slab_l2(p.cz.perm_person + (size_t)e * P, (size_t)P * 2);
         if (lane == 5) prefetch_slab_l2(p.st.p_money + (size_t)e * P, (size_t)P * 8);
     }
+    // everything above touches only this step's inputs; the books and agent state come from the previous step
+    grid_dependency_wait();
+    grid_launch_dependents();
     const int NM = p.st.m_count[e];
     const int NJ = p.st.j_count[e];
     const int NT = NJ + NM + 2;                                     // all rows, the two "no request" rows included
@@ -289,11 +293,21 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             if (R <= NJ) {
                 lj |= left > 0;
                 if (left > 0) {
-                    // can the firm pay every hire this window could bring?  (sufficient: wages are subtracted one by one,
-                    // rounding error << 1e-9 relative; sales only add money unless a price is negative / NaN)
+                    // How many hires of this window can the firm certainly pay?  k is safe when
+                    // m0 - w*k >= w*(1 + 1e-9): wages are subtracted one by one (rounding error << 1e-9 relative for
+                    // k <= 64) and sales only add money unless a price is negative / NaN (frisk).  Largest safe k
+                    // (<= 64, the most a window can hire), found by stepping down from the quotient.
                     const double w = lds_f64<kRecValue>(rec), m0 = lds_f64(aFmoney + 8u * owner);
-                    const double most = (double)min(left, (uint32_t)kMaxHiresPerWindow);
-                    rk |= !(w >= 0.0 && lds_u8(aFrisk + owner) == 0u && (m0 - w * most >= w * (1.0 + 1e-9)));
+                    int k = -1;
+                    if (w >= 0.0 && lds_u8(aFrisk + owner) == 0u && m0 - w * (double)kMaxHiresPerWindow >= w * (1.0 + 1e-9)) {
+                        k = kMaxHiresPerWindow;                            // the firm can pay whatever the window brings
+                    } else if (w >= 0.0 && lds_u8(aFrisk + owner) == 0u) {
+                        const double q = (m0 - w * (1.0 + 1e-9)) / w;
+                        k = q >= (double)kMaxHiresPerWindow ? kMaxHiresPerWindow : (q >= 0.0 ? (int)q : -1);   // NaN -> -1
+                        while (k >= 0 && !(m0 - w * (double)k >= w * (1.0 + 1e-9))) k--;
+                    }
+                    sts_u16<kRecSafe>(rec, (uint32_t)(k + 1));   // 0: not even the first applicant is certain
+                    rk |= k < (int)min(left, (uint32_t)kMaxHiresPerWindow);
                 }
             } else {
                 const int good = (int)((meta >> 8) & 0xFFu);
@@ -333,19 +347,21 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         const bool active = r < P;
         const int pid = active ? (p.compact ? (int)p.cz.perm_person[eP + r] : p.ac.perm_person[eP + r]) : 0;
         const double money0 = active ? p.st.p_money[eP + pid] : 0.0;
+        // keep: the slots that are worth evaluating — requested, on an existing offer that still has lots (a request on a
+        // sold-out offer fails without any effect: firm.cpp:64, agent.cpp:124); jobs in bits 0..15, goods in 16..31
+        uint32_t keep = 0;
         {
             const bool modulo = (p.flags & FASTACE_IDX_MODULO) != 0;
 #pragma unroll
             for (int ph = 0; ph < 2; ph++) {
                 const bool live = ph == 0 ? liveJ : liveM;
-                if (!live) continue;                                   // a sold-out book is not evaluated at all
+                if (!live || !active) continue;                        // a sold-out book is not evaluated at all
                 const uint32_t dst = aReqL + (ph == 0 ? 0u : (uint32_t)kReqGoods);
                 const uint32_t dummy = (uint32_t)(ph == 0 ? NJ : NM);
+                const uint32_t recs = ph == 0 ? aRec : aRecM;
                 const IndexMap& map = ph == 0 ? mapJ : mapM;
-                if (!active) {
-#pragma unroll
-                    for (int q = 0; q < kMaxStack / 4; q++) sts_u32(dst + 4u * q, dummy * 0x01010101u);
-                } else if (p.compact) {
+                uint32_t kp = 0;
+                if (p.compact) {
                     // agent-major bytes: the aligned words that cover [pid*S, pid*S + S), shifted into place
                     const uint8_t* lst = (ph == 0 ? p.cz.p_job_idx : p.cz.p_good_idx) + (eP + pid) * (size_t)S;
                     const uint32_t take = (ph == 0 ? p.cz.p_job_take : p.cz.p_good_take)[eP + pid] & ((1u << S) - 1u);
@@ -359,7 +375,13 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                         if (4 * q < S) {
                             const uint32_t x = __funnelshift_r(raw[q], raw[q + 1], 8u * sh);
                             const uint32_t t4 = take >> (4 * q);
-                            sts_u32(dst + 4u * q, modulo ? map_request_word<true>(x, t4, map, dummy) : map_request_word<false>(x, t4, map, dummy));
+                            const uint32_t w = modulo ? map_request_word<true>(x, t4, map, dummy) : map_request_word<false>(x, t4, map, dummy);
+                            sts_u32(dst + 4u * q, w);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const uint32_t n = __byte_perm(w, 0u, 0x4440u + k);
+                                if (lds_u32<kRecLeft>(recs + n * kRecBytes) > 0u) kp |= 1u << (4 * q + k);   // the "no request" row has none
+                            }
                         }
                     }
                 } else {
@@ -371,8 +393,10 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                         uint32_t n = modulo ? map.mod24(map.mod24(raw >> 16) * map.k16 + (raw & 0xFFFFu)) : (raw < map.count ? raw : dummy);
                         if (tk[(size_t)i * P] == 0) n = dummy;
                         sts_u8(dst + (uint32_t)i, n);
+                        if (lds_u32<kRecLeft>(recs + n * kRecBytes) > 0u) kp |= 1u << i;
                     }
                 }
+                keep |= ph == 0 ? kp : kp << 16;
             }
         }
         __syncwarp();
@@ -386,36 +410,47 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         for (int round = 0;; round++) {
             if (lane == 0) { FASTACE_STAT(kStatRounds, 1); FASTACE_STAT(kStatRoundsW0 + min(base >> 5, 3), 1); }
             money = money0; nh = 0; okm = 0;
-            // ---- evaluate: job requests (utilMaxer.cpp:76-85; eligible = person.cpp:39: 0.5 * nh + 0.5 <= 1)
+            // ---- evaluate: job requests (utilMaxer.cpp:76-85; eligible = person.cpp:39: 0.5 * nh + 0.5 <= 1).  Every
+            //      lane walks ITS OWN kept slots in request order; the loop ends when no lane can apply any more
             if (liveJ) {
-                uint32_t bit = 1u;
-#pragma unroll 2
-                for (int i = 0; i < S; i++, bit <<= 1) {
-                    const uint32_t n = lds_u8(aReqL + (uint32_t)i);
-                    const uint32_t cell = aCellJ + n * kMatBytes;
-                    const uint32_t c = lds_u8<kMatCnt>(cell);
-                    const uint32_t rm = lds_u8<kMatRoom>(cell);
-                    const double wage = lds_f64<kRecValue>(aRec + n * kRecBytes);
-                    const bool el = nh < 2;
-                    if (el) sts_u8<kMatCnt>(cell, c + 1u);
-                    const bool ok = el && c < rm;
-                    if (ok) { nh++; money += wage; okm |= bit; }          // person.cpp:49
+                uint32_t rem = keep & 0xFFFFu;
+                for (;;) {
+                    const bool go = rem != 0u && nh < 2;
+                    if (!__any_sync(0xffffffffu, go)) break;
+                    if (go) {
+                        const int i = __ffs((int)rem) - 1;
+                        rem &= rem - 1;
+                        const uint32_t cell = aCellJ + lds_u8(aReqL + (uint32_t)i) * kMatBytes;
+                        const uint32_t c = lds_u8<kMatCnt>(cell);
+                        const uint32_t rm = lds_u8<kMatRoom>(cell);
+                        sts_u8<kMatCnt>(cell, c + 1u);
+                        if (c < rm) { nh++; okm |= 1u << i; }
+                    }
                 }
+                // the wages of the (at most two) jobs, in request order (person.cpp:49)
+                uint32_t mj = okm;
+                if (mj) { money += lds_f64<kRecValue>(aRec + lds_u8(aReqL + (uint32_t)(__ffs((int)mj) - 1)) * kRecBytes); mj &= mj - 1; }
+                if (mj) money += lds_f64<kRecValue>(aRec + lds_u8(aReqL + (uint32_t)(__ffs((int)mj) - 1)) * kRecBytes);
             }
             // ---- evaluate: goods requests (utilMaxer.cpp:64-73; eligible = agent.cpp:102)
             if (liveM) {
-                uint32_t bit = 1u << 16;
-#pragma unroll 2
-                for (int i = 0; i < S; i++, bit <<= 1) {
-                    const uint32_t n = lds_u8<kReqGoods>(aReqL + (uint32_t)i);
-                    const uint32_t cell = aCellM + n * kMatBytes;
-                    const double price = lds_f64<kRecValue>(aRecM + n * kRecBytes);
-                    const uint32_t c = lds_u8<kMatCnt>(cell);
-                    const uint32_t rm = lds_u8<kMatRoom>(cell);
-                    const bool el = money >= price;
-                    if (el) sts_u8<kMatCnt>(cell, c + 1u);
-                    const bool ok = el && c < rm;
-                    if (ok) { money -= price; okm |= bit; }                // agent.cpp:108
+                uint32_t rem = keep >> 16;
+                for (;;) {
+                    const bool go = rem != 0u;
+                    if (!__any_sync(0xffffffffu, go)) break;
+                    if (go) {
+                        const int i = __ffs((int)rem) - 1;
+                        rem &= rem - 1;
+                        const uint32_t n = lds_u8<kReqGoods>(aReqL + (uint32_t)i);
+                        const double price = lds_f64<kRecValue>(aRecM + n * kRecBytes);
+                        if (money >= price) {
+                            const uint32_t cell = aCellM + n * kMatBytes;
+                            const uint32_t c = lds_u8<kMatCnt>(cell);
+                            const uint32_t rm = lds_u8<kMatRoom>(cell);
+                            sts_u8<kMatCnt>(cell, c + 1u);
+                            if (c < rm) { money -= price; okm |= 1u << (16 + i); }   // agent.cpp:108
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -482,13 +517,14 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                 const uint32_t mat = aMat + (uint32_t)(R < NJ ? R : 0) * kMatBytes;
                 if (R < NJ) {
                     left = lds_u32<kRecLeft>(rec);
-                    f = (int)(lds_u32<kRecMeta>(rec) & 0xFFu);
-                    w = lds_f64<kRecValue>(rec);
-                    m0 = lds_f64(aFmoney + 8u * f);
                     tot = (int)lds_u32<kRecTot>(rec);
-                    const int most = min((int)min(left, 0x7FFFFFFFu), tot);
-                    const bool safe = w >= 0.0 && lds_u8(aFrisk + f) == 0u && (m0 - w * (double)most >= w * (1.0 + 1e-9));
-                    risky = tot > 0 && left > 0 && !safe;
+                    // the applicants that could be hired exceed what the firm can certainly pay
+                    risky = tot > 0 && left > 0 && min(min((int)min(left, 0x7FFFFFFFu), tot), kMaxHiresPerWindow) >= (int)lds_u16<kRecSafe>(rec);
+                    if (risky) {
+                        f = (int)(lds_u32<kRecMeta>(rec) & 0xFFu);
+                        w = lds_f64<kRecValue>(rec);
+                        m0 = lds_f64(aFmoney + 8u * f);
+                    }
                 }
                 if (__any_sync(0xffffffffu, risky)) {
                     // does the firm sell anything in this window?  (its goods rows' successes = min(tot, D))

@@ -34,6 +34,8 @@ template <int G>
 __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateParams up) {
     const StepParams& p = up.sp;
     const int P = p.P, F = p.F;
+    grid_dependency_wait();        // the matching results of this step (programmatic dependent launch)
+    grid_launch_dependents();
     if ((int)blockIdx.x >= up.firm_blocks) {
         // ---- UtilMaxer::consume_goods (utilMaxer.cpp:88-92) + choose_goods_to_consume
         //      (neuralPersonDecisionMaker.cpp:93-111) + UtilMaxer::u (utilMaxer.cpp:54-62)
