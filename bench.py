@@ -179,16 +179,30 @@ def bench_config_d(dev, with_cpu, steps=14, warm=3):
            "unit": METRIC, "steps": len(timed), "warmup": warm, "ms_per_step": mean_ms, "value": 105000 / (mean_ms * 1e-3),
            "iteration_rounds_person_firm_last_step": rounds[-1], "scaling": "replicas only (one economy does not shard)"}
     if with_cpu:
-        from oracle.loader import Oracle
-        orc = Oracle()
-        ost = {k: v.copy() for k, v in state.items()}
-        t0 = time.perf_counter()
-        for t in range(4):
+        from oracle import loader
+        if loader.have_reference():
+            # the reference's own Economy (unmodified sources, single-threaded branch): 2 steps of the same episode
+            ref = loader.Reference(dims, state, seed=38)
             oo = _abi.alloc_host("out", dims, names=("p_reward", "f_profit"))
-            orc.step(dims, ost, host_acts[t], oo, flags=_abi.IDX_MODULO, time_before=t)
-        dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": 105000 * 4 / dt, "unit": METRIC, "cores": 1, "kind": "port",
-                               "sample": "first 4 steps of the same episode, C oracle, single thread (one economy has one visiting order)"}
+            n_cpu = 2
+            t0 = time.perf_counter()
+            for t in range(n_cpu):
+                ref.step(host_acts[t], oo, flags=_abi.IDX_MODULO, nthreads=1, want_perms=False)
+            dt = time.perf_counter() - t0
+            ref.close()
+            kind, what = "reference", "unmodified reference sources (oracle/_ref), single-threaded branch"
+        else:
+            orc = loader.Oracle()
+            ost = {k: v.copy() for k, v in state.items()}
+            n_cpu = 4
+            t0 = time.perf_counter()
+            for t in range(n_cpu):
+                oo = _abi.alloc_host("out", dims, names=("p_reward", "f_profit"))
+                orc.step(dims, ost, host_acts[t], oo, flags=_abi.IDX_MODULO, time_before=t)
+            dt = time.perf_counter() - t0
+            kind, what = "port", "C oracle"
+        res["cpu_baseline"] = {"value": 105000 * n_cpu / dt, "unit": METRIC, "cores": 1, "kind": kind,
+                               "sample": f"first {n_cpu} steps of the same episode, {what}, one thread (one economy has one visiting order)"}
     return res
 
 
@@ -403,39 +417,69 @@ def run_ours(args):
     e2e_value = run_e2e(pinned_c, _abi.IDX_ABSOLUTE | _abi.STEP_ASYNC, e2e_steps)
     e2e_int32 = run_e2e(pinned_i, _abi.IDX_MODULO, len(pinned_i))
 
-    # ---- full rollout (config C flavour): batched policy forward on tensor cores + env step ----------
+    # what the host link alone sustains: the same pinned compact blocks copied to the device back to back, every rank at
+    # once (attributes the end-to-end number at N > 1: all GPUs of a box share the host's memory and PCIe roots)
+    blk_bytes = h2d
+    src = torch.empty(blk_bytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(blk_bytes, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n_copy = 40
+    t0 = time.perf_counter()
+    for _ in range(n_copy):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    t_c = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+    h2d_gbs_per_gpu = blk_bytes * n_copy / float(t_c.item()) / 1e9
+
+    # ---- full rollout (BASELINE config C): batched policy forward on tensor cores + env step, 8192 economies per GPU
+    #      (65 536 on 8), visiting orders generated on the device (fastace_env_shuffle_orders): nothing comes from the host
     rollout = None
     if args.rollout:
         from fastace_b200 import policy
         torch.backends.cuda.matmul.allow_tf32 = True
+        ER = args.rollout_econ
+        rdims = (ER, P, F, G, S)
+        renv = BatchedEconomy(rdims, device=local)
+        renv.set_state(scenario.custom_initial_state(rdims, 5000 + rank * ER)[0])
+        rout = renv.pack_device("out", renv.alloc_outputs())
         nets = policy.DecisionNets(numGoods=G, stackSize=S).to(dev).eval()
         gen = torch.Generator(device=dev)
         gen.manual_seed(1234 + rank)
+        variants = (("fused_two_phase", None, True, True),) if not args.rollout_all else (
+            ("tf32", None, False, False), ("bf16", torch.bfloat16, False, False), ("fused_stack", None, True, False), ("fused_two_phase", None, True, True))
         results = {}
-        for label, dt, fused, two in (("tf32", None, False, False), ("bf16", torch.bfloat16, False, False),
-                                      ("fused_stack", None, True, False), ("fused_two_phase", None, True, True)):
-            pol = policy.BatchedPolicy(env, nets, generator=gen, autocast_dtype=dt, fused=fused, two_phase=two)
-            reset_state(0)
+        for label, dt, fused, two in variants:
+            pol = policy.BatchedPolicy(renv, nets, generator=gen, autocast_dtype=dt, fused=fused, two_phase=two)
             rsteps = 8
-            perm_dev = [(torch.from_numpy(a["perm_person"]).to(dev), torch.from_numpy(a["perm_firm"]).to(dev)) for a in acts[:rsteps + 2]]
+            pp, pf = renv.shuffle_orders(seed=77 + rank * ER, restart=True, steps=rsteps + 2)
             for k in range(2):
-                pol.step(perm_dev[k], dout, flags=_abi.IDX_ABSOLUTE)
+                pol.step((pp[k], pf[k]), rout, flags=_abi.IDX_ABSOLUTE)
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
             for k in range(rsteps):
-                pol.step(perm_dev[2 + k], dout, flags=_abi.IDX_ABSOLUTE)
+                pol.step((pp[2 + k], pf[2 + k]), rout, flags=_abi.IDX_ABSOLUTE)
             ev1.record()
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1) / rsteps
             t_r = torch.tensor([ms], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t_r, op=dist.ReduceOp.MAX)
-            results[label] = {"ms_per_step": float(t_r.item()), "value": world * E * (P + F) / (float(t_r.item()) * 1e-3)}
-        rollout = {"unit": METRIC, "policy": "11 decision nets (hidden 100 x 12 layers), random init, batched over all agents; tf32 / bf16 = eager torch, "
+            results[label] = {"ms_per_step": float(t_r.item()), "value": world * ER * (P + F) / (float(t_r.item()) * 1e-3)}
+        renv.close()
+        rollout = {"unit": METRIC, "workload": f"config C: {ER} economies/GPU x (100 persons + 10 firms), policy forward + env step, orders shuffled on the device",
+                   "policy": "11 decision nets (hidden 100 x 12 layers), random init, batched over all agents; tf32 / bf16 = eager torch, "
                              "fused_* = net bodies through csrc/mlp_stack.cuh (bf16 mma operands, fp32 accumulate + residual)",
-                   "semantics": "decisions taken from the state at the start of the step; fused_two_phase: firms decide after the "
-                                "person phase, on the state they see in the reference (DESIGN.md §7)", **results}
+                   "semantics": "fused_two_phase: consumption and the firms' decisions are taken on the state they see in the reference "
+                                "(DESIGN.md §7)", **results}
 
     # ---- training (row f-2): T-step rollout with recording + one advantage actor-critic update -----------
     training = None
@@ -516,6 +560,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "fastace_env_step_host_compact + FASTACE_STEP_ASYNC, fastace_env_sync at the end (one pinned block per step: "
                            "a single copy each way)"},
+            "h2d_only": {"gb_per_s_per_gpu": h2d_gbs_per_gpu, "gb_per_s_all_gpus": h2d_gbs_per_gpu * world, "block_bytes": blk_bytes,
+                         "agent_steps_per_s_if_link_bound": world * E * (P + F) / (blk_bytes / (h2d_gbs_per_gpu * 1e9)),
+                         "what": "pinned-host -> device copies of one step's compact action block, back to back on all ranks at once"},
             "e2e_int32_sync": {"value": e2e_int32, "unit": METRIC, "h2d_bytes_per_step": h2d_int32, "d2h_bytes_per_step": d2h,
                                "api": "fastace_env_step_host (int32 indices, u8 flags), synchronous"},
             "gpu_launches": int(launches),
@@ -554,11 +601,19 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (diagnostic)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-sample", type=int, default=256)
-    ap.add_argument("--config-d", action="store_true", help="also time BASELINE config D (one 105k-agent economy, large-economy path)")
-    ap.add_argument("--train", action="store_true", help="also time one A2C update (rollout + re-evaluation backward + Adam)")
+    ap.add_argument("--only-step", action="store_true", help="time the env step only: skip the config C / D / E legs")
+    ap.add_argument("--config-d", action=argparse.BooleanOptionalAction, default=True,
+                    help="BASELINE config D (one 105k-agent economy, large-economy path), rank 0")
+    ap.add_argument("--train", action=argparse.BooleanOptionalAction, default=True,
+                    help="BASELINE config E: one A2C update (rollout + re-evaluation backward + Adam, NCCL gradient all-reduce)")
     ap.add_argument("--train-steps", type=int, default=20, help="episode length of the --train leg (DEFAULT_EPISODE_LENGTH)")
-    ap.add_argument("--rollout", action="store_true", help="also time the full rollout with the batched policy forward")
+    ap.add_argument("--rollout", action=argparse.BooleanOptionalAction, default=True,
+                    help="BASELINE config C: full rollout with the batched policy forward")
+    ap.add_argument("--rollout-econ", type=int, default=8192, help="economies per GPU of the rollout leg (65 536 on 8 GPUs)")
+    ap.add_argument("--rollout-all", action="store_true", help="rollout leg: also the eager tf32 / bf16 and one-phase variants")
     args = ap.parse_args()
+    if args.only_step:
+        args.config_d = args.train = args.rollout = False
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

@@ -157,7 +157,10 @@ def train(scenarioParams, trainingParams, fromPretrained=False, perturbationSize
     a2c = trainer.AdvantageActorCritic(
         nets, lrs=lrs, episodeBatchSizeForLRDecay=int(tp.episodeBatchSizeForLRDecay), patienceForLRDecay=int(tp.patienceForLRDecay),
         multiplierForLRDecay=float(tp.multiplierForLRDecay), cosinePeriod=int(tp.reverseAnnealingPeriod), **(trainer_kwargs or {}))
-    pol = policy.BatchedPolicy(env, nets, two_phase=True, fused=fused_rollout)    # phase-wise: decisions see what they see in the reference
+    # phase-wise: the consumption decision and the firms' decisions see what they see in the reference; a person's
+    # purchase decision is still taken from its start-of-step money and labour (in the reference: after its own job
+    # search, neuralPersonDecisionMaker.cpp:56-70) — DESIGN.md §7
+    pol = policy.BatchedPolicy(env, nets, two_phase=True, fused=fused_rollout)
     out = env.alloc_outputs()
     say = (lambda *a: None) if quiet else print
     losses = [0.0] * int(tp.numEpisodes)

@@ -166,8 +166,11 @@ class AdvantageActorCritic:
 
     # ---- pieces of train_on_episode (advantageActorCritic.cpp:602-624) ----
     def zero_all_grads(self):
-        for name in NET_ORDER:
-            self.optims[name].zero_grad(set_to_none=True)
+        # every parameter, not only those an optimiser owns: with the reference's wiring productionNet belongs to no
+        # optimiser (advantageActorCritic.cpp:103-120); its gradient would otherwise pile up from episode to episode
+        # (and be multiplied by the world size at every all-reduce)
+        for p in self._params:
+            p.grad = None
 
     def update_lr_schedulers(self):
         for name in NET_ORDER:

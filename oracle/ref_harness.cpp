@@ -28,6 +28,7 @@
 #include <cstring>
 #include <memory>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "base.h"
@@ -295,6 +296,7 @@ struct RefEconomyBox {
     std::vector<std::shared_ptr<ProfitMaxer>> firms;
     std::vector<std::shared_ptr<ReplayFirm>> firmDMs;
     std::vector<double> scratch_reward, scratch_profit;
+    mutable std::unordered_map<const void*, int> person_ids, firm_ids;   // agent object -> creation index (built on first use)
 };
 
 }  // namespace
@@ -305,12 +307,16 @@ struct fastace_ref {
 };
 
 static int person_id(const RefEconomyBox& b, const Person* p) {
-    for (size_t i = 0; i < b.persons.size(); i++) if (b.persons[i].get() == p) return (int)i;
-    return -1;
+    if (b.person_ids.empty())
+        for (size_t i = 0; i < b.persons.size(); i++) b.person_ids[static_cast<const Person*>(b.persons[i].get())] = (int)i;
+    auto it = b.person_ids.find(p);
+    return it == b.person_ids.end() ? -1 : it->second;
 }
 static int firm_id(const RefEconomyBox& b, const Agent* f) {
-    for (size_t i = 0; i < b.firms.size(); i++) if (static_cast<const Agent*>(b.firms[i].get()) == f) return (int)i;
-    return -1;
+    if (b.firm_ids.empty())
+        for (size_t i = 0; i < b.firms.size(); i++) b.firm_ids[static_cast<const Agent*>(b.firms[i].get())] = (int)i;
+    auto it = b.firm_ids.find(f);
+    return it == b.firm_ids.end() ? -1 : it->second;
 }
 
 static int g_ref_util_kind = FASTACE_FN_CES, g_ref_prod_kind = FASTACE_FN_CES;

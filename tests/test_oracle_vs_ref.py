@@ -13,7 +13,7 @@ pytestmark = pytest.mark.skipif(not loader.have_reference(), reason="oracle/_ref
 OUTS = [n for n, _, _, _ in _abi.OUT_FIELDS if n not in ("p_job_ok", "p_good_ok", "f_good_ok")]
 
 
-def _compare(oracle, dims, steps, seed, flags, preset, mutate=None, generic=False):
+def _compare(oracle, dims, steps, seed, flags, preset, mutate=None, generic=False, outs=OUTS):
     state = scenario.generic_initial_state(dims, seed) if generic else scenario.custom_initial_state(dims, seed)[0]
     ref = loader.Reference(dims, state, seed=seed + 5)
     ost = {k: v.copy() for k, v in state.items()}
@@ -21,8 +21,8 @@ def _compare(oracle, dims, steps, seed, flags, preset, mutate=None, generic=Fals
         act = scenario.synthetic_actions(dims, seed=seed + 1, step=t, **preset)
         if mutate:
             mutate(t, act)
-        rout = _abi.alloc_host("out", dims, names=OUTS)
-        oout = _abi.alloc_host("out", dims, names=OUTS)
+        rout = _abi.alloc_host("out", dims, names=outs)
+        oout = _abi.alloc_host("out", dims, names=outs)
         pp, pf = ref.step(act, rout, flags=flags)
         act["perm_person"], act["perm_firm"] = pp, pf
         before = {k: v.copy() for k, v in ost.items()}
@@ -76,3 +76,22 @@ def test_extreme_actions(oracle):
             act["p_job_take"][:] = 1; act["p_good_take"][:] = 1; act["f_good_take"][:] = 1
 
     _compare(oracle, (3, 40, 5, 2, 10), 15, 4, _abi.IDX_MODULO, scenario.BENCH_PRESET, mutate)
+
+
+def test_config_d_full_size(oracle):
+    """BASELINE config D at full size (one economy of 100 000 persons + 5 000 firms, 8 goods): the oracle that the
+    large-economy GPU tests are checked against is itself bit-identical to the reference here, 3 steps (the first
+    trades against empty books, the next two move ~800 k requests each)"""
+    # (the harness samples the old books' counters at every decision, O(agents x book): state, rewards and profits only)
+    _compare(oracle, (1, 100000, 5000, 8, 10), 3, 21, _abi.IDX_MODULO, scenario.BENCH_PRESET, generic=True,
+             outs=("p_reward", "f_profit"))
+
+
+def test_negative_prices_and_wages(oracle):
+    """a sale that lowers the seller's money, a hire that raises the firm's: the cases the kernels' "can the firm pay"
+    shortcut must not take"""
+    def mutate(t, act):
+        act["f_offer_price"][0, 0, :3] = -0.75
+        act["f_job_wage"][1, 1] = -0.25
+        act["f_offer_price"][2, 1, 2:4] = np.nan
+    _compare(oracle, (3, 40, 5, 2, 10), 12, 33, _abi.IDX_MODULO, scenario.BENCH_PRESET, mutate)
