@@ -145,6 +145,12 @@ class StepOut(C.Structure):
     _fields_ = [(n, t) for n, t, _, _ in OUT_FIELDS]
 
 
+class MarketStats(C.Structure):
+    """fastace_market_stats_t"""
+    _fields_ = [("sum_quantity_per_price", _dp), ("offers", _up), ("lots", _up),
+                ("sum_wage_per_labor", _dp), ("job_offers", _up), ("job_lots", _up)]
+
+
 class CustomScenarioParams(C.Structure):
     """neural::CustomScenarioParams, /root/reference/src/neural/neuralScenarios.h:49-115
     (ctypes mirror as in /root/reference/py/main.py:12-60)."""

@@ -15,6 +15,7 @@
 #include "step_kernel.cuh"
 #include "match_update_kernels.cuh"
 #include "shuffle_kernel.cuh"
+#include "stats_kernel.cuh"
 #include "large_economy.cuh"
 #include "mlp_stack.cuh"
 #include "layer_kernels.cuh"
@@ -853,6 +854,17 @@ int fastace_env_step_host_compact(fastace_env_t* env, const fastace_actions_comp
                                   const fastace_step_out_t* out, uint32_t flags) {
     if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
     return step_host_impl(env, actions, compact_fields(env->dims), env->dcact, env->cact_block, true, out, flags);
+}
+
+int fastace_env_market_stats(const fastace_env_t* env, const fastace_market_stats_t* out, void* cuda_stream) {
+    if (!env || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
+    StatsParams sp;
+    sp.E = env->dims.num_econ; sp.F = env->dims.num_firms; sp.G = env->dims.num_goods;
+    sp.st = env->dstate; sp.out = *out;
+    market_stats_kernel<<<(sp.E + 127) / 128, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(sp);
+    FASTACE_CUDA_CHECK(cudaGetLastError());
+    return FASTACE_OK;
 }
 
 int fastace_env_shuffle_orders(fastace_env_t* env, uint32_t seed, int restart, int steps,

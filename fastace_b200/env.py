@@ -208,6 +208,25 @@ class BatchedEconomy:
                                                        C.c_void_p(stream)))
         return perm_person, perm_firm
 
+    def market_stats(self, stream=None):
+        """Per-economy statistics of the current books, reduced on the device (print_info of src/pybindings.cpp:20-75):
+        dict of torch CUDA tensors — sum_quantity_per_price [E][G], offers [E][G], lots [E][G], sum_wage_per_labor [E],
+        job_offers [E], job_lots [E]; average price of good g = sum_quantity_per_price / offers."""
+        torch = _torch()
+        E, G = self.dims.num_econ, self.dims.num_goods
+        dev = torch.device("cuda", self.device)
+        t = {"sum_quantity_per_price": torch.empty((E, G), dtype=torch.float64, device=dev),
+             "offers": torch.empty((E, G), dtype=torch.int32, device=dev), "lots": torch.empty((E, G), dtype=torch.int32, device=dev),
+             "sum_wage_per_labor": torch.empty((E,), dtype=torch.float64, device=dev),
+             "job_offers": torch.empty((E,), dtype=torch.int32, device=dev), "job_lots": torch.empty((E,), dtype=torch.int32, device=dev)}
+        ms = _abi.MarketStats()
+        for k, v in t.items():
+            setattr(ms, k, C.cast(C.c_void_p(v.data_ptr()), dict(_abi.MarketStats._fields_)[k]))
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        lib.check(self._lib.fastace_env_market_stats(self._h, C.byref(ms), C.c_void_p(stream)))
+        return t
+
     def large_stats(self):
         """(person-phase rounds, firm-phase rounds) of the last large-economy step"""
         a, b = C.c_uint32(0), C.c_uint32(0)

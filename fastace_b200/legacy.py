@@ -103,22 +103,23 @@ def _build(scenarioParams, trainingParams, numEconomies, device):
 
 
 def market_info(env, economy=0, goods=("good1", "good2")):
-    """print_info of src/pybindings.cpp:20-75 for one economy: average price per good and average wage"""
-    st = env.get_state()
+    """print_info of src/pybindings.cpp:20-75 for one economy: average price per good and average wage, from the
+    device-side reduction (fastace_env_market_stats) — a few numbers cross the bus, not the books"""
+    ms = env.market_stats()
+    sums = ms["sum_quantity_per_price"][economy].tolist()
+    counts = ms["offers"][economy].tolist()
     lines = [f"Time = {env.get_time()}:"]
-    n = int(st["m_count"][economy])
-    if n > 0:
+    if sum(counts) > 0:
         for g, gname in enumerate(goods):
-            sel = st["m_good"][economy, :n] == g
-            if sel.any():
-                lines.append(f"{gname}: Avg. price = {float((1.0 / st['m_price'][economy, :n][sel]).mean()):g} (num. offers = {int(sel.sum())})")
+            if counts[g] > 0:
+                lines.append(f"{gname}: Avg. price = {sums[g] / counts[g]:g} (num. offers = {counts[g]})")
             else:
                 lines.append(f"{gname}: Avg. price = NA (num. offers = 0)")
     else:
         lines.append("[No offers]")
-    nj = int(st["j_count"][economy])
+    nj = int(ms["job_offers"][economy])
     if nj > 0:
-        lines.append(f"Avg. wage per unit of labor = {float((st['j_wage'][economy, :nj] / 0.5).mean()):g} (num. offers = {nj})")
+        lines.append(f"Avg. wage per unit of labor = {float(ms['sum_wage_per_labor'][economy]) / nj:g} (num. offers = {nj})")
     else:
         lines.append("[No job offers]")
     return "\n".join(lines)
@@ -130,7 +131,7 @@ def run(scenarioParams, trainingParams, numEconomies=1, device=0, saveDir=DEFAUL
     load_models(nets, saveDir)
     env.set_state(scenario.custom_initial_state(dims, seed, scenarioParams)[0])
     pol = policy.BatchedPolicy(env, nets.eval(), fused=fused, two_phase=True)
-    orders = scenario.OrderStream(dims, seed + 1)
+    orders = scenario.DeviceOrderStream(env, seed + 1, chunk=int(trainingParams.episodeLength))   # std::shuffle on the device
     out = env.alloc_outputs()
     log = []
     for _ in range(int(trainingParams.episodeLength)):
@@ -168,7 +169,7 @@ def train(scenarioParams, trainingParams, fromPretrained=False, perturbationSize
         state, discount = scenario.custom_initial_state(dims, seed + i * numEconomies, scenarioParams)   # scenario->setup()
         env.set_state(state, time=0)
         a2c.discount = torch.from_numpy(discount).to(torch.device("cuda", device))     # UtilMaxer::get_discountRate per person
-        orders = scenario.OrderStream(dims, seed + 7919 * (i + 1))
+        orders = scenario.DeviceOrderStream(env, seed + 7919 * (i + 1), chunk=int(tp.episodeLength))   # economy.cpp:110-111 on the device
         ep = trainer.run_episode(pol, orders, out, int(tp.episodeLength), flags=_abi.IDX_ABSOLUTE)
         loss = a2c.train_on_episode(ep)
         if math.isnan(loss):                              # neuralScenarios.cpp:229-243

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "fastace_env_step_device", "fastace_env_step_host", "fastace_env_step_device_compact",
     "fastace_env_step_host_compact", "fastace_env_sync", "fastace_env_launch_count", "fastace_env_kernel_times", "fastace_env_large_stats", "fastace_mlp_stack_layout", "fastace_mlp_residual_tanh_stack", "fastace_mlp_forward", "fastace_layer_forward", "fastace_layer_backward",
     "create_scenario_params", "create_training_params", "run", "train",
-    "fastace_scenario_custom_init", "fastace_shuffle_orders", "fastace_env_shuffle_orders",
+    "fastace_scenario_custom_init", "fastace_shuffle_orders", "fastace_env_shuffle_orders", "fastace_env_market_stats",
 ]
 
 
@@ -102,6 +102,8 @@ def load():
     L.fastace_shuffle_orders.restype = C.c_int
     L.fastace_shuffle_orders.argtypes = [C.POINTER(_abi.Dims), C.c_uint32, C.POINTER(C.c_uint64),
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
+    L.fastace_env_market_stats.restype = C.c_int
+    L.fastace_env_market_stats.argtypes = [vp, C.POINTER(_abi.MarketStats), vp]
     L.fastace_env_shuffle_orders.restype = C.c_int
     L.fastace_env_shuffle_orders.argtypes = [vp, C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     if L.fastace_abi_version() != _abi.ABI_VERSION:

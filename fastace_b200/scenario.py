@@ -106,6 +106,27 @@ class OrderStream:
         return self.perm_person.copy(), self.perm_firm.copy()
 
 
+class DeviceOrderStream:
+    """The same stream of visiting orders generated ON THE DEVICE by the env (fastace_env_shuffle_orders: one thread
+    per economy replays minstd_rand0 and libstdc++'s std::shuffle, bit for bit) — nothing crosses the bus.  next()
+    returns (perm_person, perm_firm) as int32 CUDA tensors [E][P] / [E][F]; orders are produced `chunk` steps ahead."""
+
+    def __init__(self, env, seed, chunk=32):
+        self.env, self.seed, self.chunk = env, int(seed) & 0xFFFFFFFF, int(chunk)
+        self.started = False
+        self.buf = None
+        self.pos = 0
+
+    def next(self):
+        if self.buf is None or self.pos == self.chunk:
+            self.buf = self.env.shuffle_orders(seed=self.seed, restart=not self.started, steps=self.chunk)
+            self.started = True
+            self.pos = 0
+        k = self.pos
+        self.pos += 1
+        return self.buf[0][k], self.buf[1][k]
+
+
 # Injected-action distributions that keep both books non-empty over a 40-step episode of
 # the default scenario (with SURVEY.md's untuned recipe firms go bankrupt and the goods
 # market is empty after ~12 steps, so a benchmark would time an idle market).  Measured

@@ -320,6 +320,21 @@ int fastace_env_step_device_compact(fastace_env_t* env, const fastace_actions_co
                                     const fastace_step_out_t* out, uint32_t flags, void* cuda_stream);
 int fastace_env_step_host_compact(fastace_env_t* env, const fastace_actions_compact_t* actions,
                                   const fastace_step_out_t* out, uint32_t flags);
+/* Per-economy market statistics of the CURRENT books (what the reference's `run` prints after every step, print_info,
+ * src/pybindings.cpp:20-75), reduced on the device: per good the sum of quantity/price over its offers, the number of
+ * offers and the lots on offer; the sum of wage/labor over the job offers, their number and lots.  The sums are
+ * accumulated in market order like the reference's loops (average = sum / count).  DEVICE pointers, any may be NULL;
+ * enqueued on `cuda_stream`. */
+typedef struct fastace_market_stats {
+    double*   sum_quantity_per_price; /* [E][G] */
+    uint32_t* offers;                 /* [E][G] */
+    uint32_t* lots;                   /* [E][G] */
+    double*   sum_wage_per_labor;     /* [E]    */
+    uint32_t* job_offers;             /* [E]    */
+    uint32_t* job_lots;               /* [E]    */
+} fastace_market_stats_t;
+int fastace_env_market_stats(const fastace_env_t* env, const fastace_market_stats_t* out, void* cuda_stream);
+
 /* Waits for every step enqueued by the host-pointer calls of this env. */
 int fastace_env_sync(fastace_env_t* env);
 /* number of kernel launches issued by this env's step calls so far */
