@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol(native_lib):
     header = open(os.path.join(ROOT, "include", "fastace_b200.h")).read()
     # every function prototype in the header: `name(`
-    declared = set(re.findall(r"^\s*(?:int|const char\*|fastace_custom_scenario_params_t|fastace_training_params_t)\s+\**(\w+)\s*\(",
+    declared = set(re.findall(r"^\s*(?:int|void|const char\*|fastace_custom_scenario_params_t|fastace_training_params_t)\s+\**(\w+)\s*\(",
                               header, flags=re.M))
     assert declared, "no prototypes found"
     assert declared == set(lib.EXPORTED_SYMBOLS)
