@@ -371,9 +371,10 @@ def run_ours(args):
 
     pinned_c, pinned_i = [], []
     for k in range(e2e_steps):
-        cz = pin_block("compact", host_cz[k])
+        # the packed host encoding: bit-field indices, no take masks, no visiting orders (the env shuffles on the device)
+        cz = pin_block("packed", _abi.packed_actions_for_counts(acts[k], counts[k][0], counts[k][1], True, with_orders=False))
         holder = cz.pop("_holder")
-        st_c = _abi.struct_from_numpy("compact", cz, env.dims)
+        st_c = _abi.struct_from_numpy("packed", cz, env.dims)
         st_c._holder = holder
         pinned_c.append((cz, st_c))
     for k in range(min(e2e_steps, 10)):
@@ -394,13 +395,17 @@ def run_ours(args):
     h2d_int32 = int(sum(v.nbytes for v in acts[0].values()))
     d2h = int(sum(v.nbytes for v in houts[0][0].values()))
 
+    order_seed = 1 + rank * E + 1000003        # build_workload's OrderStream: the device shuffle replays the same orders
+
     def run_e2e(structs, flags, n):
         reset_state(0)
+        env.restart_orders(order_seed)
         torch.cuda.synchronize()
         for k in range(min(3, n)):  # warm-up (allocates the staging buffers)
             env.time_step_host(structs[k][1], houts[k][1], flags=flags)
         env.sync()
         reset_state(0)
+        env.restart_orders(order_seed)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -420,21 +425,25 @@ def run_ours(args):
     # what the host link alone sustains: the same pinned compact blocks copied to the device back to back, every rank at
     # once (attributes the end-to-end number at N > 1: all GPUs of a box share the host's memory and PCIe roots)
     blk_bytes = h2d
-    src = torch.empty(blk_bytes, dtype=torch.uint8).pin_memory()
+    src = pinned_c[0][1]._holder[:blk_bytes]            # the very pinned block the e2e leg ships
     dst = torch.empty(blk_bytes, dtype=torch.uint8, device=dev)
-    for _ in range(3):
-        dst.copy_(src, non_blocking=True)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     n_copy = 40
-    t0 = time.perf_counter()
-    for _ in range(n_copy):
-        dst.copy_(src, non_blocking=True)
-    torch.cuda.synchronize()
-    t_c = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+    best = None
+    for rep in range(3):                                 # best of three: the link is shared with whatever else the host does
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_copy):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        t_c = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+        best = float(t_c.item()) if best is None else min(best, float(t_c.item()))
+    t_c = torch.tensor([best], dtype=torch.float64, device=dev)
     h2d_gbs_per_gpu = blk_bytes * n_copy / float(t_c.item()) / 1e9
 
     # ---- full rollout (BASELINE config C): batched policy forward on tensor cores + env step, 8192 economies per GPU
@@ -558,8 +567,8 @@ def run_ours(args):
                             "what": "the same steps with device-resident inputs in the int32 encoding (fastace_actions_t)"},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "fastace_env_step_host_compact + FASTACE_STEP_ASYNC, fastace_env_sync at the end (one pinned block per step: "
-                           "a single copy each way)"},
+                    "api": "fastace_env_step_host_packed + FASTACE_STEP_ASYNC, fastace_env_sync at the end (packed encoding: bit-field "
+                           "offer indices, visiting orders shuffled on the device; one pinned block per step, a single copy each way)"},
             "h2d_only": {"gb_per_s_per_gpu": h2d_gbs_per_gpu, "gb_per_s_all_gpus": h2d_gbs_per_gpu * world, "block_bytes": blk_bytes,
                          "agent_steps_per_s_if_link_bound": world * E * (P + F) / (blk_bytes / (h2d_gbs_per_gpu * 1e9)),
                          "what": "pinned-host -> device copies of one step's compact action block, back to back on all ranks at once"},

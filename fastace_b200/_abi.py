@@ -115,6 +115,33 @@ COMPACT_FIELDS = [
     ("f_job_wage", _fp, np.float32, lambda E, P, F, G, S: (E, F)),
 ]
 
+def packed_layout(F, G, S):
+    """(bits_job, bytes_job, bits_good, bytes_good) of the packed host encoding (fastace_packed_layout): the smallest
+    field width whose all-ones value is not a valid index."""
+    def bits_for(n):
+        b = 1
+        while (1 << b) - 1 < n:
+            b += 1
+        return b
+    bj, bg = bits_for(F), bits_for(F * G)
+    return bj, (S * bj + 7) // 8, bg, (S * bg + 7) // 8
+
+
+# fastace_actions_packed_t: S bit fields per agent, all-ones = no request, no take masks; orders optional
+PACKED_FIELDS = [
+    ("perm_person", _hp, np.uint16, lambda E, P, F, G, S: (E, P)),
+    ("perm_firm", _hp, np.uint16, lambda E, P, F, G, S: (E, F)),
+    ("p_job_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, P, packed_layout(F, G, S)[1])),
+    ("p_good_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, P, packed_layout(F, G, S)[3])),
+    ("p_consume", _fp, np.float32, lambda E, P, F, G, S: (E, G, P)),
+    ("f_good_idx", _bp, np.uint8, lambda E, P, F, G, S: (E, F, packed_layout(F, G, S)[3])),
+    ("f_prod", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
+    ("f_offer_amt", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
+    ("f_offer_price", _fp, np.float32, lambda E, P, F, G, S: (E, G, F)),
+    ("f_job_labor", _fp, np.float32, lambda E, P, F, G, S: (E, F)),
+    ("f_job_wage", _fp, np.float32, lambda E, P, F, G, S: (E, F)),
+]
+
 OUT_FIELDS = [
     ("p_reward", _dp, np.float64, lambda E, P, F, G, S: (E, P)),
     ("f_profit", _dp, np.float64, lambda E, P, F, G, S: (E, F)),
@@ -139,6 +166,10 @@ class Actions(C.Structure):
 
 class ActionsCompact(C.Structure):
     _fields_ = [(n, t) for n, t, _, _ in COMPACT_FIELDS]
+
+
+class ActionsPacked(C.Structure):
+    _fields_ = [(n, t) for n, t, _, _ in PACKED_FIELDS]
 
 
 class StepOut(C.Structure):
@@ -187,7 +218,7 @@ class TrainingParams(C.Structure):
 
 
 def field_table(kind):
-    return {"state": STATE_FIELDS, "actions": ACTION_FIELDS, "compact": COMPACT_FIELDS, "out": OUT_FIELDS}[kind]
+    return {"state": STATE_FIELDS, "actions": ACTION_FIELDS, "compact": COMPACT_FIELDS, "packed": PACKED_FIELDS, "out": OUT_FIELDS}[kind]
 
 
 def shapes(kind, dims):
@@ -231,7 +262,7 @@ def alloc_host_block(kind, dims, names=None, pinned=False):
 def struct_from_numpy(kind, arrays, dims=None):
     """Build the ctypes struct from a dict of numpy arrays (missing names -> NULL).
     Arrays must be C-contiguous with the exact dtype; shapes are checked when dims given."""
-    cls = {"state": State, "actions": Actions, "compact": ActionsCompact, "out": StepOut}[kind]
+    cls = {"state": State, "actions": Actions, "compact": ActionsCompact, "packed": ActionsPacked, "out": StepOut}[kind]
     s = cls()
     shp = shapes(kind, dims) if dims is not None else None
     for n, ptr_t, dt, _ in field_table(kind):
@@ -249,7 +280,7 @@ def struct_from_numpy(kind, arrays, dims=None):
 
 def struct_from_pointers(kind, ptrs):
     """Build the ctypes struct from a dict name -> integer address (device pointers)."""
-    cls = {"state": State, "actions": Actions, "compact": ActionsCompact, "out": StepOut}[kind]
+    cls = {"state": State, "actions": Actions, "compact": ActionsCompact, "packed": ActionsPacked, "out": StepOut}[kind]
     s = cls()
     for n, ptr_t, _, _ in field_table(kind):
         p = ptrs.get(n)
@@ -288,6 +319,56 @@ def compact_actions_for_counts(actions, j_count, m_count, modulo):
         "p_good_idx": idx8(a["p_good_idx"], mc), "p_good_take": mask16(a["p_good_take"]),
         "f_good_idx": idx8(a["f_good_idx"], mc), "f_good_take": mask16(a["f_good_take"]),
     }
+    for k in ("p_consume", "f_prod", "f_offer_amt", "f_offer_price", "f_job_labor", "f_job_wage"):
+        out[k] = a[k]
+    return {k: np.ascontiguousarray(v) for k, v in out.items()}
+
+
+def packed_actions_for_counts(actions, j_count, m_count, modulo, with_orders=True):
+    """Same decisions in the packed host encoding (fastace_actions_packed_t), given the current book sizes: every request
+    slot becomes one bit field holding the offer index (draw % count with `modulo`), all-ones where nothing is
+    requested (not taken, or out of range).  with_orders=False leaves the visiting orders out (the env generates them)."""
+    a = actions
+    E, S, P = a["p_job_idx"].shape
+    F = a["f_good_idx"].shape[2]
+    G = a["p_consume"].shape[1]
+    bj, nbj, bg, nbg = packed_layout(F, G, S)
+    jc = np.asarray(j_count, dtype=np.int64).reshape(E, 1, 1)
+    mc = np.asarray(m_count, dtype=np.int64).reshape(E, 1, 1)
+
+    def fields(raw, take, cnt, bits, nbytes):     # [E][S][N] -> [E][N][nbytes]
+        raw = raw.astype(np.int64)
+        if modulo:
+            v = np.where(cnt > 0, (raw & 0xFFFFFFFF) % np.maximum(cnt, 1), (1 << bits) - 1)
+            ok = (take != 0) & (cnt > 0)
+        else:
+            v = raw
+            ok = (take != 0) & (raw >= 0) & (raw < cnt)
+        v = np.where(ok, v, (1 << bits) - 1).astype(np.uint64).transpose(0, 2, 1)          # [E][N][S]
+        word = np.zeros(v.shape[:2], dtype=np.uint64)       # S * bits <= 128: two 64-bit halves
+        word_hi = np.zeros(v.shape[:2], dtype=np.uint64)
+        for i in range(S):
+            sh = i * bits
+            if sh < 64:
+                word |= v[:, :, i] << np.uint64(sh)
+                if sh + bits > 64:
+                    word_hi |= v[:, :, i] >> np.uint64(64 - sh)
+            else:
+                word_hi |= v[:, :, i] << np.uint64(sh - 64)
+        out = np.zeros(v.shape[:2] + (nbytes,), dtype=np.uint8)
+        for k in range(nbytes):
+            src = word if k < 8 else word_hi
+            out[:, :, k] = ((src >> np.uint64(8 * (k % 8))) & np.uint64(0xFF)).astype(np.uint8)
+        return out
+
+    out = {
+        "p_job_idx": fields(a["p_job_idx"], a["p_job_take"], jc, bj, nbj),
+        "p_good_idx": fields(a["p_good_idx"], a["p_good_take"], mc, bg, nbg),
+        "f_good_idx": fields(a["f_good_idx"], a["f_good_take"], mc, bg, nbg),
+    }
+    if with_orders:
+        out["perm_person"] = a["perm_person"].astype(np.uint16)
+        out["perm_firm"] = a["perm_firm"].astype(np.uint16)
     for k in ("p_consume", "f_prod", "f_offer_amt", "f_offer_price", "f_job_labor", "f_job_wage"):
         out[k] = a[k]
     return {k: np.ascontiguousarray(v) for k, v in out.items()}

@@ -16,6 +16,8 @@
 #include "match_update_kernels.cuh"
 #include "shuffle_kernel.cuh"
 #include "stats_kernel.cuh"
+#include "segmented_sort.cuh"
+#include "packed_kernel.cuh"
 #include "large_economy.cuh"
 #include "mlp_stack.cuh"
 #include "layer_kernels.cuh"
@@ -81,6 +83,38 @@ static std::vector<FieldDesc> action_fields(const fastace_dims_t& d) {
     };
 }
 
+static int bits_for(int max_index_exclusive) {   // smallest width whose all-ones value is not a valid index
+    int b = 1;
+    while (((1 << b) - 1) < max_index_exclusive) b++;
+    return b;
+}
+struct PackedLayout { int bits_job, bytes_job, bits_good, bytes_good; };
+static PackedLayout packed_layout(const fastace_dims_t& d) {
+    PackedLayout L;
+    L.bits_job = bits_for(d.num_firms);
+    L.bits_good = bits_for(d.num_firms * d.num_goods);
+    L.bytes_job = (d.stack_size * L.bits_job + 7) / 8;
+    L.bytes_good = (d.stack_size * L.bits_good + 7) / 8;
+    return L;
+}
+static std::vector<FieldDesc> packed_fields(const fastace_dims_t& d) {
+    const size_t E = d.num_econ, P = d.num_persons, F = d.num_firms, G = d.num_goods;
+    const PackedLayout L = packed_layout(d);
+    return {
+        {offsetof(fastace_actions_packed_t, perm_person), 2, E * P},
+        {offsetof(fastace_actions_packed_t, perm_firm), 2, E * F},
+        {offsetof(fastace_actions_packed_t, p_job_idx), 1, E * P * (size_t)L.bytes_job},
+        {offsetof(fastace_actions_packed_t, p_good_idx), 1, E * P * (size_t)L.bytes_good},
+        {offsetof(fastace_actions_packed_t, p_consume), 4, E * G * P},
+        {offsetof(fastace_actions_packed_t, f_good_idx), 1, E * F * (size_t)L.bytes_good},
+        {offsetof(fastace_actions_packed_t, f_prod), 4, E * G * F},
+        {offsetof(fastace_actions_packed_t, f_offer_amt), 4, E * G * F},
+        {offsetof(fastace_actions_packed_t, f_offer_price), 4, E * G * F},
+        {offsetof(fastace_actions_packed_t, f_job_labor), 4, E * F},
+        {offsetof(fastace_actions_packed_t, f_job_wage), 4, E * F},
+    };
+}
+
 static std::vector<FieldDesc> compact_fields(const fastace_dims_t& d) {
     const size_t E = d.num_econ, P = d.num_persons, F = d.num_firms, G = d.num_goods, S = d.stack_size;
     return {
@@ -139,6 +173,8 @@ struct fastace_env {
     fastace_actions_t dact[2];
     void* cact_block[2];
     fastace_actions_compact_t dcact[2];
+    void* pact_block[2];
+    fastace_actions_packed_t dpact[2];
     void* out_block[2];
     fastace_step_out_t dout[2];
     cudaStream_t stream;        // kernels of the host-pointer calls
@@ -156,6 +192,8 @@ struct fastace_env {
     int32_t* ord_person;      // [E][P] cumulative order of the persons
     int32_t* ord_firm;        // [E][F]
     bool ord_started;
+    bool ord_restart_pending; // a steps = 0 (re)start: the next shuffle seeds from ord_seed
+    uint32_t ord_seed;
     uint32_t* err_host;       // host-mapped error words the kernels raise (match_kernel.cuh: kDevErr*)
     uint32_t* err_dev;        // the same words as the device sees them
     cudaEvent_t ev[3];        // FASTACE_STEP_PROFILE
@@ -170,6 +208,8 @@ struct fastace_env {
     int large_coop_blocks_p, large_coop_blocks_f;   // co-resident CTAs of the two cooperative iteration kernels
     void* large_block;
     fastace::LargeScratch large_sc;
+    uint32_t* sort_hist;      // segmented sort: per-chunk histograms
+    size_t sort_chunk;
 };
 
 #define FASTACE_CUDA_CHECK(expr)                                                              \
@@ -267,8 +307,8 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
         set_error("unsupported dims: need E>=1, F>=1, 1<=G<=8, 0<=S<=16");
         return FASTACE_ERR_INVALID;
     }
-    if (d.num_firms > 65534 || d.num_persons > (1 << 20) || (size_t)2 * d.stack_size * d.num_persons >= (size_t)1 << 27) {
-        set_error("unsupported dims: need F <= 65534, P <= 2^20");
+    if (d.num_firms > 56000 || d.num_persons > (1 << 20) || (size_t)2 * d.stack_size * d.num_persons >= (size_t)1 << 27) {
+        set_error("unsupported dims: need F <= 56000, P <= 2^20");
         return FASTACE_ERR_INVALID;
     }
     bool large_only = d.num_firms * d.num_goods > 254 || d.num_persons > 65535;
@@ -343,6 +383,7 @@ int fastace_env_destroy(fastace_env_t* env) {
     for (int b = 0; b < 2; b++) {
         if (env->act_block[b]) cudaFree(env->act_block[b]);
         if (env->cact_block[b]) cudaFree(env->cact_block[b]);
+        if (env->pact_block[b]) cudaFree(env->pact_block[b]);
         if (env->out_block[b]) cudaFree(env->out_block[b]);
     }
     if (env->have_host_streams) {
@@ -357,7 +398,7 @@ int fastace_env_destroy(fastace_env_t* env) {
     if (env->ord_person) cudaFree(env->ord_person);
     if (env->ord_firm) cudaFree(env->ord_firm);
     if (env->large_block) cudaFree(env->large_block);
-    if (env->large_sc.cub_temp) cudaFree(env->large_sc.cub_temp);
+    if (env->sort_hist) cudaFree(env->sort_hist);
     delete env;
     return FASTACE_OK;
 }
@@ -444,6 +485,33 @@ static LargeKernels large_kernels_for_goods(int G) {
     }
 }
 
+// elements per chunk (= per warp) of the segmented sort: enough chunks to fill the GPU, chunks long enough to amortise
+// the per-chunk bin table, and a histogram matrix of at most 96 MB
+static size_t sort_chunk_for(size_t n, size_t F) {
+    size_t chunk = 256;
+    while (chunk < 4096 && n / chunk > 512) chunk *= 2;
+    const size_t budget_words = (size_t)24 << 20;
+    while ((n + chunk - 1) / chunk * (F + 1) > budget_words) chunk *= 2;
+    return chunk;
+}
+
+// stable sort of n (key, value) pairs by firm id: the events of firm f become the segment [seg[f], seg[f+1])
+static int segmented_sort(fastace_env_t* env, const uint16_t* key_in, const uint32_t* val_in, uint16_t* key_out, uint32_t* val_out,
+                          const uint32_t* seg, size_t n, cudaStream_t stream) {
+    if (n == 0) return FASTACE_OK;
+    SortParams sp;
+    sp.key_in = key_in; sp.val_in = val_in; sp.key_out = key_out; sp.val_out = val_out; sp.seg = seg; sp.hist = env->sort_hist;
+    const size_t chunk = std::min(env->sort_chunk, sort_chunk_for(n, (size_t)env->dims.num_firms));   // never more chunks than allocated
+    sp.n = (int)n; sp.F = env->dims.num_firms; sp.chunk = (int)chunk; sp.chunks = (int)((n + chunk - 1) / chunk);
+    const size_t smem = (size_t)(sp.F + 1) * sizeof(uint32_t);
+    sort_chunk_hist<<<sp.chunks, 32, smem, stream>>>(sp);
+    sort_bin_scan<<<(sp.F + 1 + kSortScanWarps - 1) / kSortScanWarps, 32 * kSortScanWarps, 0, stream>>>(sp);
+    sort_chunk_scatter<<<sp.chunks, 32, smem, stream>>>(sp);
+    FASTACE_CUDA_CHECK(cudaGetLastError());
+    env->launches += 3;
+    return FASTACE_OK;
+}
+
 static int ensure_large_scratch(fastace_env_t* env) {
     if (env->have_large) return FASTACE_OK;
     const size_t P = env->dims.num_persons, F = env->dims.num_firms, G = env->dims.num_goods, S = env->dims.stack_size;
@@ -473,11 +541,20 @@ static int ensure_large_scratch(fastace_env_t* env) {
     FASTACE_CUDA_CHECK(cudaMemset(env->large_block, 0, total));
     size_t off = 0;
     for (auto& it : items) { *it.ptr = static_cast<char*>(env->large_block) + off; off += align_up(it.bytes ? it.bytes : 1, 256); }
-    size_t need = 0;
-    const int n_max = (int)(R > RF ? R : RF);
-    FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, need, sc.key_in, sc.key_out, sc.val_in, sc.val_out, n_max > 0 ? n_max : 1, 0, 16));
-    sc.cub_bytes = need ? need : 1;
-    FASTACE_CUDA_CHECK(cudaMalloc(&sc.cub_temp, sc.cub_bytes));
+    {
+        // per-chunk histograms of the segmented sort (segmented_sort.cuh): chunks x (F + 1) words
+        const size_t n_max = R > RF ? R : RF;
+        env->sort_chunk = sort_chunk_for(n_max, F);
+        // room for the chunk count of ANY list length up to n_max (a shorter list takes shorter chunks, see sort_chunk_for)
+        const size_t by_budget = ((size_t)24 << 20) / (F + 1) + 1;
+        const size_t chunks = std::min(by_budget, std::max<size_t>(513, n_max / 4096 + 1));
+        FASTACE_CUDA_CHECK(cudaMalloc((void**)&env->sort_hist, sizeof(uint32_t) * chunks * (F + 1)));
+        const size_t smem = (F + 1) * sizeof(uint32_t);
+        if (smem > 48 * 1024) {
+            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)sort_chunk_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)sort_chunk_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+    }
     {
         const LargeKernels lk = large_kernels_for_goods(env->dims.num_goods);
         int sms = 0, occ_p = 0, occ_f = 0;
@@ -540,13 +617,12 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
             FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed, 0, 32, stream));
             if (R > 0) {
                 large_prep_persons<<<blocks(R), T, 0, stream>>>(lp);
-                size_t bytes = sc.cub_bytes;
-                FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sc.cub_temp, bytes, sc.key_in, sc.key_out, sc.val_in, sc.val_out,
-                                                                   (int)R, 0, 16, stream));
-                env->launches += 2;
+                env->launches += 1;
             }
             large_scan<<<1, 1024, 0, stream>>>(sc.hist, sc.seg, F);
             env->launches += 1;
+            // the segmented sort of the event lists: requests, enumerated in event order, stably by firm
+            if (int src = segmented_sort(env, sc.key_in, sc.val_in, sc.key_out, sc.val_out, sc.seg, R, stream)) return src;
             if (R > 0) {
                 large_index_events<<<blocks(R), T, 0, stream>>>(lp);
                 env->launches += 1;
@@ -582,12 +658,10 @@ static int launch_step_large(fastace_env_t* env, const fastace_actions_t* dact, 
             FASTACE_CUDA_CHECK(cudaMemsetAsync(sc.changed + 4, 0, 16, stream));
             if (RF > 0) {
                 large_prep_firms<<<blocks(RF), T, 0, stream>>>(lp);
-                size_t bytes = sc.cub_bytes;
-                FASTACE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sc.cub_temp, bytes, sc.fkey_in, sc.fkey_out, sc.fval_in, sc.fval_out,
-                                                                   (int)RF, 0, 16, stream));
-                env->launches += 2;
+                env->launches += 1;
             }
             large_scan<<<1, 1024, 0, stream>>>(sc.fhist, sc.fseg, F);
+            if (int src = segmented_sort(env, sc.fkey_in, sc.fval_in, sc.fkey_out, sc.fval_out, sc.fseg, RF, stream)) return src;
             {
                 int max_rounds = kMaxRounds;
                 void* args[] = {(void*)&lp, (void*)&max_rounds};
@@ -745,14 +819,24 @@ int fastace_env_step_device_compact(fastace_env_t* env, const fastace_actions_co
 
 }  // extern "C"
 
+static int shuffle_one_step_16(fastace_env_t* env, uint16_t* perm_person16, uint16_t* perm_firm16, cudaStream_t stream) {
+    if (env->dims.num_persons > 65535 || env->dims.num_firms > 65535) { set_error("16-bit orders need P, F <= 65535"); return FASTACE_ERR_INVALID; }
+    return fastace_env_shuffle_orders(env, 0u, 0, 1, nullptr, nullptr, perm_person16, perm_firm16, stream);
+}
+
 // Host-pointer step.  Pipeline per call (buffer b = call parity):
 //   copy_in : [wait kernels that last read buffer b] H2D of every action array -> h2d_done[b]
 //   stream  : [wait h2d_done[b], d2h_done[b]] match + update kernels            -> kern_done[b]
 //   copy_out: [wait kern_done[b]] D2H of the requested outputs                   -> d2h_done[b]
 // so with FASTACE_STEP_ASYNC the copies of neighbouring steps overlap the kernels.
+// forward: one shuffle step of the env's own orders into 16-bit device arrays (packed host calls without orders)
+static int shuffle_one_step_16(fastace_env_t* env, uint16_t* perm_person16, uint16_t* perm_firm16, cudaStream_t stream);
+
+// mode: 0 = int32 encoding, 1 = compact, 2 = packed (expanded on the device into the compact staging block)
 template <typename ActT>
 static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::vector<FieldDesc>& fields,
-                          ActT* dacts, void** blocks, bool compact, const fastace_step_out_t* out, uint32_t flags) {
+                          ActT* dacts, void** blocks, int mode, const fastace_step_out_t* out, uint32_t flags) {
+    const bool compact = mode == 1;
     FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
     if (!env->have_host_streams) {
         FASTACE_CUDA_CHECK(cudaStreamCreateWithFlags(&env->copy_in, cudaStreamNonBlocking));
@@ -773,8 +857,17 @@ static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::ve
         int rc = carve(out_fields(env->dims), &env->dout[b], &env->out_block[b], false);
         if (rc != FASTACE_OK) return rc;
     }
-    for (auto& f : fields)
+    if (mode == 2 && !env->cact_block[b]) {
+        int rc = carve(compact_fields(env->dims), &env->dcact[b], &env->cact_block[b], false);
+        if (rc != FASTACE_OK) return rc;
+    }
+    const bool own_orders = mode == 2 && !member(actions, fields[0].offset) && !member(actions, fields[1].offset);
+    if (own_orders && !env->ord_started) { set_error("no visiting orders given and the env's own orders were never started (fastace_env_shuffle_orders)"); return FASTACE_ERR_INVALID; }
+    for (size_t k = 0; k < fields.size(); k++) {
+        const auto& f = fields[k];
+        if (own_orders && k < 2) continue;
         if (f.count && !member(actions, f.offset)) { set_error("actions: every array is mandatory"); return FASTACE_ERR_INVALID; }
+    }
     if (env->buf_used[b]) FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->copy_in, env->kern_done[b], 0));
     {
         // Host arrays that sit in one block with the staging buffer's own layout (fields in struct order, each
@@ -787,7 +880,7 @@ static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::ve
             return e;
         };
         for (auto& f : fields) {
-            if (!f.count) continue;
+            if (!f.count || !member(actions, f.offset)) continue;
             const char* h = static_cast<const char*>(member(actions, f.offset));
             char* d = static_cast<char*>(member(&dacts[b], f.offset));
             const size_t bytes = f.elem * f.count;
@@ -809,8 +902,37 @@ static int step_host_impl(fastace_env_t* env, const ActT* actions, const std::ve
     std::memset(&dout, 0, sizeof(dout));
     for (auto& f : out_fields(env->dims))
         if (member(out, f.offset)) member(&dout, f.offset) = member(&env->dout[b], f.offset);
-    int rc = compact ? launch_step(env, nullptr, reinterpret_cast<const fastace_actions_compact_t*>(&dacts[b]), &dout, flags, env->stream)
+    int rc;
+    if (mode == 2) {
+        // expand the packed block into the compact staging arrays, then step on those
+        const fastace_actions_packed_t& pk = *reinterpret_cast<const fastace_actions_packed_t*>(&dacts[b]);
+        fastace_actions_compact_t cz = env->dcact[b];
+        const fastace_dims_t& dm = env->dims;
+        const PackedLayout PL = packed_layout(dm);
+        if (own_orders) {
+            rc = shuffle_one_step_16(env, const_cast<uint16_t*>(cz.perm_person), const_cast<uint16_t*>(cz.perm_firm), env->stream);
+            if (rc != FASTACE_OK) return rc;
+        } else {
+            cz.perm_person = pk.perm_person; cz.perm_firm = pk.perm_firm;
+        }
+        cz.p_consume = pk.p_consume; cz.f_prod = pk.f_prod; cz.f_offer_amt = pk.f_offer_amt; cz.f_offer_price = pk.f_offer_price;
+        cz.f_job_labor = pk.f_job_labor; cz.f_job_wage = pk.f_job_wage;
+        ExpandParams ej = {dm.num_econ * dm.num_persons, dm.stack_size, PL.bits_job, PL.bytes_job, pk.p_job_idx,
+                           const_cast<uint8_t*>(cz.p_job_idx), const_cast<uint16_t*>(cz.p_job_take)};
+        ExpandParams eg = {dm.num_econ * dm.num_persons, dm.stack_size, PL.bits_good, PL.bytes_good, pk.p_good_idx,
+                           const_cast<uint8_t*>(cz.p_good_idx), const_cast<uint16_t*>(cz.p_good_take)};
+        ExpandParams ef = {dm.num_econ * dm.num_firms, dm.stack_size, PL.bits_good, PL.bytes_good, pk.f_good_idx,
+                           const_cast<uint8_t*>(cz.f_good_idx), const_cast<uint16_t*>(cz.f_good_take)};
+        ExpandParams none = ef; none.agents = 0;
+        if (ej.agents > 0) expand_packed_kernel<<<(ej.agents + 255) / 256, 256, 0, env->stream>>>(ej, eg);
+        expand_packed_kernel<<<(ef.agents + 255) / 256, 256, 0, env->stream>>>(ef, none);
+        FASTACE_CUDA_CHECK(cudaGetLastError());
+        env->launches += 2;
+        rc = launch_step(env, nullptr, &cz, &dout, flags & ~FASTACE_IDX_MODULO, env->stream);
+    } else {
+        rc = compact ? launch_step(env, nullptr, reinterpret_cast<const fastace_actions_compact_t*>(&dacts[b]), &dout, flags, env->stream)
                      : launch_step(env, reinterpret_cast<const fastace_actions_t*>(&dacts[b]), nullptr, &dout, flags, env->stream);
+    }
     if (rc != FASTACE_OK) return rc;
     FASTACE_CUDA_CHECK(cudaEventRecord(env->kern_done[b], env->stream));
     FASTACE_CUDA_CHECK(cudaStreamWaitEvent(env->copy_out, env->kern_done[b], 0));
@@ -847,13 +969,35 @@ extern "C" {
 int fastace_env_step_host(fastace_env_t* env, const fastace_actions_t* actions, const fastace_step_out_t* out,
                           uint32_t flags) {
     if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
-    return step_host_impl(env, actions, action_fields(env->dims), env->dact, env->act_block, false, out, flags);
+    return step_host_impl(env, actions, action_fields(env->dims), env->dact, env->act_block, 0, out, flags);
+}
+
+int fastace_packed_layout(const fastace_dims_t* dims, int* bits_job, int* bytes_job, int* bits_good, int* bytes_good) {
+    if (!dims) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    const PackedLayout L = packed_layout(*dims);
+    if (bits_job) *bits_job = L.bits_job;
+    if (bytes_job) *bytes_job = L.bytes_job;
+    if (bits_good) *bits_good = L.bits_good;
+    if (bytes_good) *bytes_good = L.bytes_good;
+    return FASTACE_OK;
+}
+
+int fastace_env_step_host_packed(fastace_env_t* env, const fastace_actions_packed_t* actions,
+                                 const fastace_step_out_t* out, uint32_t flags) {
+    if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
+    if (env->large_only || (flags & (FASTACE_STEP_LARGE | FASTACE_STEP_SERIAL))) {
+        set_error("the packed encoding feeds the warp-per-economy kernels only"); return FASTACE_ERR_INVALID;
+    }
+    if ((actions->perm_person == nullptr) != (actions->perm_firm == nullptr)) {
+        set_error("give both visiting orders or neither"); return FASTACE_ERR_INVALID;
+    }
+    return step_host_impl(env, actions, packed_fields(env->dims), env->dpact, env->pact_block, 2, out, flags);
 }
 
 int fastace_env_step_host_compact(fastace_env_t* env, const fastace_actions_compact_t* actions,
                                   const fastace_step_out_t* out, uint32_t flags) {
     if (!env || !actions || !out) { set_error("null argument"); return FASTACE_ERR_INVALID; }
-    return step_host_impl(env, actions, compact_fields(env->dims), env->dcact, env->cact_block, true, out, flags);
+    return step_host_impl(env, actions, compact_fields(env->dims), env->dcact, env->cact_block, 1, out, flags);
 }
 
 int fastace_env_market_stats(const fastace_env_t* env, const fastace_market_stats_t* out, void* cuda_stream) {
@@ -870,7 +1014,7 @@ int fastace_env_market_stats(const fastace_env_t* env, const fastace_market_stat
 int fastace_env_shuffle_orders(fastace_env_t* env, uint32_t seed, int restart, int steps,
                                int32_t* perm_person, int32_t* perm_firm, uint16_t* perm_person16, uint16_t* perm_firm16,
                                void* cuda_stream) {
-    if (!env || steps < 1) { set_error("bad argument"); return FASTACE_ERR_INVALID; }
+    if (!env || steps < 0 || (steps == 0 && !restart)) { set_error("bad argument"); return FASTACE_ERR_INVALID; }
     FASTACE_CUDA_CHECK(cudaSetDevice(env->device));
     const int E = env->dims.num_econ, P = env->dims.num_persons, F = env->dims.num_firms;
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
@@ -880,6 +1024,13 @@ int fastace_env_shuffle_orders(fastace_env_t* env, uint32_t seed, int restart, i
         FASTACE_CUDA_CHECK(cudaMalloc((void**)&env->ord_firm, sizeof(int32_t) * ((size_t)E * F + 1)));
     }
     if (!restart && !env->ord_started) { set_error("the first call must (re)start the orders"); return FASTACE_ERR_INVALID; }
+    if (steps == 0) {
+        // (re)start only: the next shuffle seeds the engines and starts from the identity order
+        env->ord_seed = seed; env->ord_restart_pending = true; env->ord_started = true;
+        return FASTACE_OK;
+    }
+    if (env->ord_restart_pending && !restart) { restart = 1; seed = env->ord_seed; }
+    env->ord_restart_pending = false;
     ShuffleParams sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.E = E; sp.P = P; sp.F = F; sp.seed = seed;

@@ -11,7 +11,7 @@
 //                   other side granted  ->  `want` (own-side conditions hold: labour <= 1, money >= price)
 //   firm pass       one warp per firm: ALL events at this firm in the reference's order (visiting rank, jobs before
 //                   goods, slot), given `want`  ->  `ok`; this is the segmented, stably sorted event list: events
-//                   keyed by firm, sorted by a radix sort (cub::DeviceRadixSort, the one library primitive here)
+//                   keyed by firm, sorted stably by firm with the hand-written counting sort of segmented_sort.cuh
 //                   whose input is enumerated in (rank, phase, slot) order.  Goods events are per-good prefix counts
 //                   of `want` bits; only the firm's money (sales, hires) is walked sequentially.
 // iterated until no `ok` flag changes, inside ONE cooperative launch (grid.sync between the passes).  By induction
@@ -26,7 +26,6 @@
 // job offer per firm; inventories are non-negative.
 #pragma once
 #include <cooperative_groups.h>
-#include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
 
@@ -81,8 +80,6 @@ struct LargeScratch {
     uint8_t* dirty_firm;   // [F]   some `want` at this firm changed since its last firm pass
     uint32_t *post_base_m, *post_base_j;   // [F] by visiting rank: first new-book slot of that firm
     int* changed;
-    void* cub_temp;
-    size_t cub_bytes;
 };
 
 struct LargeParams {

@@ -181,8 +181,16 @@ class BatchedEconomy:
         if isinstance(actions, _abi.ActionsCompact):
             lib.check(self._lib.fastace_env_step_host_compact(self._h, C.byref(actions), C.byref(ou), int(flags)))
             return
+        if isinstance(actions, _abi.ActionsPacked):
+            lib.check(self._lib.fastace_env_step_host_packed(self._h, C.byref(actions), C.byref(ou), int(flags)))
+            return
         ac = actions if isinstance(actions, _abi.Actions) else _abi.struct_from_numpy("actions", actions, self.dims)
         lib.check(self._lib.fastace_env_step_host(self._h, C.byref(ac), C.byref(ou), int(flags)))
+
+    def restart_orders(self, seed):
+        """(Re)start the env's own visiting orders: economy e seeds minstd_rand0(seed + e), identity order.  The packed
+        host calls without orders then consume one std::shuffle step each."""
+        lib.check(self._lib.fastace_env_shuffle_orders(self._h, int(seed) & 0xFFFFFFFF, 1, 0, None, None, None, None, None))
 
     def shuffle_orders(self, seed=0, restart=False, steps=1, perm_person=None, perm_firm=None, stream=None):
         """Economy::time_step's visiting orders for the next `steps` steps, generated ON THE DEVICE (bit-identical to

@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "fastace_env_create", "fastace_env_destroy", "fastace_env_dims", "fastace_env_time", "fastace_env_set_function_kinds",
     "fastace_env_set_state", "fastace_env_get_state", "fastace_env_device_state",
     "fastace_env_step_device", "fastace_env_step_host", "fastace_env_step_device_compact",
-    "fastace_env_step_host_compact", "fastace_env_sync", "fastace_env_launch_count", "fastace_env_kernel_times", "fastace_env_large_stats", "fastace_mlp_stack_layout", "fastace_mlp_residual_tanh_stack", "fastace_mlp_forward", "fastace_layer_forward", "fastace_layer_backward",
+    "fastace_env_step_host_compact", "fastace_env_step_host_packed", "fastace_packed_layout", "fastace_env_sync", "fastace_env_launch_count", "fastace_env_kernel_times", "fastace_env_large_stats", "fastace_mlp_stack_layout", "fastace_mlp_residual_tanh_stack", "fastace_mlp_forward", "fastace_layer_forward", "fastace_layer_backward",
     "create_scenario_params", "create_training_params", "run", "train",
     "fastace_scenario_custom_init", "fastace_shuffle_orders", "fastace_env_shuffle_orders", "fastace_env_market_stats",
 ]
@@ -69,6 +69,10 @@ def load():
     L.fastace_env_step_device_compact.argtypes = [vp, C.POINTER(_abi.ActionsCompact), C.POINTER(_abi.StepOut), C.c_uint32, vp]
     L.fastace_env_step_host_compact.restype = C.c_int
     L.fastace_env_step_host_compact.argtypes = [vp, C.POINTER(_abi.ActionsCompact), C.POINTER(_abi.StepOut), C.c_uint32]
+    L.fastace_env_step_host_packed.restype = C.c_int
+    L.fastace_env_step_host_packed.argtypes = [vp, C.POINTER(_abi.ActionsPacked), C.POINTER(_abi.StepOut), C.c_uint32]
+    L.fastace_packed_layout.restype = C.c_int
+    L.fastace_packed_layout.argtypes = [C.POINTER(_abi.Dims)] + [C.POINTER(C.c_int)] * 4
     L.fastace_env_sync.restype = C.c_int
     L.fastace_env_sync.argtypes = [vp]
     L.fastace_env_launch_count.restype = C.c_int

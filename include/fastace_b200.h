@@ -54,7 +54,7 @@ typedef enum fastace_status {
 } fastace_status_t;
 
 /* Limits of every path; the warp-per-economy kernels (one economy = one warp, books in shared memory) additionally
- * need F*G <= 254 and P <= 65535, beyond which the env uses the large-economy path (F <= 65534, P <= 2^20). */
+ * need F*G <= 254 and P <= 65535, beyond which the env uses the large-economy path (F <= 56000, P <= 2^20). */
 #define FASTACE_MAX_GOODS 8
 #define FASTACE_MAX_STACK 16
 
@@ -206,6 +206,30 @@ typedef struct fastace_actions_compact {
 } fastace_actions_compact_t;
 
 /*
+ * Packed host encoding (fastace_env_step_host_packed only): the fewest bytes a step's decisions need on the host link.
+ * An agent's S request slots are S bit fields of `bits` bits each (little-endian bit order inside the agent's
+ * byte string), bits = smallest width whose all-ones value exceeds every valid index — jobs: 2^bits - 1 >= F, goods:
+ * 2^bits - 1 >= F*G (fastace_packed_layout; 4 and 5 bits at 10 firms x 2 goods: 5 + 7 bytes instead of 20 + 4).  A
+ * field holds the offer index itself; the all-ones value (or any value >= the book size) means "no request", so no
+ * take masks travel.  perm_person / perm_firm may both be NULL: the env then uses its own device-generated visiting
+ * orders (fastace_env_shuffle_orders with steps = 0 (re)starts them; every step advances them by one shuffle).
+ * 20 B instead of 34 B per person-step at S = 10, G = 2.  The device expands the block into the compact encoding.
+ */
+typedef struct fastace_actions_packed {
+    const uint16_t* perm_person;   /* [E][P] or NULL */
+    const uint16_t* perm_firm;     /* [E][F] or NULL */
+    const uint8_t*  p_job_idx;     /* [E][P][bytes_job]  */
+    const uint8_t*  p_good_idx;    /* [E][P][bytes_good] */
+    const float*    p_consume;     /* [E][G][P] */
+    const uint8_t*  f_good_idx;    /* [E][F][bytes_good] */
+    const float*    f_prod;        /* [E][G][F] */
+    const float*    f_offer_amt;   /* [E][G][F] */
+    const float*    f_offer_price; /* [E][G][F] */
+    const float*    f_job_labor;   /* [E][F]    */
+    const float*    f_job_wage;    /* [E][F]    */
+} fastace_actions_packed_t;
+
+/*
  * Per-step outputs.  p_reward and f_profit are mandatory; every other pointer may be
  * NULL (then it is not written).
  *   p_reward : utility of this step's consumption (neuralPersonDecisionMaker.cpp:107-108)
@@ -335,6 +359,12 @@ typedef struct fastace_market_stats {
 } fastace_market_stats_t;
 int fastace_env_market_stats(const fastace_env_t* env, const fastace_market_stats_t* out, void* cuda_stream);
 
+/* Field widths and byte-string lengths of the packed encoding for these dims. */
+int fastace_packed_layout(const fastace_dims_t* dims, int* bits_job, int* bytes_job, int* bits_good, int* bytes_good);
+/* The host-pointer step for the packed encoding (FASTACE_STEP_ASYNC as for the other host calls). */
+int fastace_env_step_host_packed(fastace_env_t* env, const fastace_actions_packed_t* actions,
+                                 const fastace_step_out_t* out, uint32_t flags);
+
 /* Waits for every step enqueued by the host-pointer calls of this env. */
 int fastace_env_sync(fastace_env_t* env);
 /* number of kernel launches issued by this env's step calls so far */
@@ -445,7 +475,8 @@ int fastace_shuffle_orders(const fastace_dims_t* dims, uint32_t seed, uint64_t* 
  * std::minstd_rand0 — one thread per economy replays the generator and the pairwise-swap algorithm) and writes step
  * t's orders to slice t of the DEVICE arrays perm_person [steps][E][P] / perm_firm [steps][E][F], in int32 and / or
  * 16-bit form (NULL = not wanted).  restart != 0: economy e seeds minstd_rand0(seed + e) and starts from the identity
- * order, exactly like first_call of fastace_shuffle_orders.  Enqueued on `cuda_stream`; does not synchronise. */
+ * order, exactly like first_call of fastace_shuffle_orders.  steps = 0 with restart != 0 only (re)starts the stream
+ * (the orders the packed host calls then consume one step at a time).  Enqueued on `cuda_stream`; does not synchronise. */
 int fastace_env_shuffle_orders(fastace_env_t* env, uint32_t seed, int restart, int steps,
                                int32_t* perm_person, int32_t* perm_firm, uint16_t* perm_person16, uint16_t* perm_firm16,
                                void* cuda_stream);

@@ -7,6 +7,8 @@
 
 #include "../../fastace_b200/csrc/match_update_kernels.cuh"
 #include "../../fastace_b200/csrc/shuffle_kernel.cuh"
+#include "../../fastace_b200/csrc/segmented_sort.cuh"
+#include "../../fastace_b200/csrc/packed_kernel.cuh"
 
 #include <vector>
 
@@ -94,6 +96,26 @@ void fastace_emu_shuffle(int E, int P, int F, uint32_t seed, int restart, int st
     const unsigned blocks = (unsigned)((E + kShuffleThreads - 1) / kShuffleThreads);
     emu::launch(shuffle_orders_kernel, blocks, (unsigned)kShuffleThreads,
                 use_smem ? (size_t)(P + F) * kShuffleThreads * sizeof(uint16_t) : 0, sp);
+}
+
+// the three kernels of segmented_sort.cuh on HOST arrays; seg = exclusive prefix of the per-firm totals, seg[F] = #requests
+void fastace_emu_segmented_sort(const uint16_t* key_in, const uint32_t* val_in, uint16_t* key_out, uint32_t* val_out,
+                                const uint32_t* seg, uint32_t* hist, int n, int F, int chunk) {
+    SortParams sp;
+    sp.key_in = key_in; sp.val_in = val_in; sp.key_out = key_out; sp.val_out = val_out; sp.seg = seg; sp.hist = hist;
+    sp.n = n; sp.F = F; sp.chunk = chunk; sp.chunks = (n + chunk - 1) / chunk;
+    const size_t smem = (size_t)(F + 1) * sizeof(uint32_t);
+    if (sp.chunks == 0) return;
+    emu::launch(sort_chunk_hist, (unsigned)sp.chunks, 32u, smem, sp);
+    emu::launch(sort_bin_scan, (unsigned)((F + 1 + kSortScanWarps - 1) / kSortScanWarps), (unsigned)(32 * kSortScanWarps), 0, sp);
+    emu::launch(sort_chunk_scatter, (unsigned)sp.chunks, 32u, smem, sp);
+}
+
+// expand_packed_kernel on HOST arrays: one list
+void fastace_emu_expand_packed(int agents, int S, int bits, int bytes, const uint8_t* packed, uint8_t* idx, uint16_t* take) {
+    ExpandParams a = {agents, S, bits, bytes, packed, idx, take};
+    ExpandParams none = a; none.agents = 0;
+    if (agents > 0) emu::launch(expand_packed_kernel, (unsigned)((agents + 255) / 256), 256u, 0, a, none);
 }
 
 // event counters of the kernels since the last call (common.cuh: kStat*); resets them

@@ -173,6 +173,13 @@ void launch(Kernel kernel, unsigned grid, unsigned block, size_t smem_bytes, con
     }
 }
 
+template <typename Kernel, typename P1, typename P2>
+void launch(Kernel kernel, unsigned grid, unsigned block, size_t smem_bytes, const P1& p1, const P2& p2) {
+    struct Both { const P1* a; const P2* b; } both{&p1, &p2};
+    auto call = [kernel](const Both& x) { kernel(*x.a, *x.b); };
+    launch(call, grid, block, smem_bytes, both);
+}
+
 template <typename T> inline uint64_t to_bits(T v) { uint64_t u = 0; static_assert(sizeof(T) <= 8, ""); std::memcpy(&u, &v, sizeof(T)); return u; }
 template <typename T> inline T from_bits(uint64_t u) { T v; std::memcpy(&v, &u, sizeof(T)); return v; }
 
@@ -247,6 +254,15 @@ template <typename T> inline T __shfl_xor_sync(unsigned, T v, int mask, int widt
     const uint64_t* b = emu::warp_exchange(emu::to_bits(v));
     (void)width;
     return emu::from_bits<T>(b[lane ^ mask]);
+}
+inline unsigned __match_any_sync(unsigned, unsigned v) {
+    const unsigned live = emu::live_mask();
+    const int lane = (int)(emu::tid().x % 32);
+    const uint64_t* b = emu::warp_exchange(v);
+    const uint64_t mine = b[lane];
+    unsigned m = 0;
+    for (int l = 0; l < 32; l++) if (((live >> l) & 1u) && b[l] == mine) m |= 1u << l;
+    return m;
 }
 inline unsigned __reduce_add_sync(unsigned, unsigned v) {
     const unsigned live = emu::live_mask();

@@ -143,3 +143,82 @@ def test_firm_money_near_tie(emu, oracle):
     hired = np.array([h for (_, _, _, h) in ties])
     assert np.array_equal(oout["p_job_ok"][:, 0, 2].astype(bool), hired)     # the reference decides as constructed ...
     assert hired.any() and (~hired).any()                                   # ... both ways
+
+
+def test_device_shuffle_equals_libstdcxx(emu):
+    """shuffle_orders_kernel (shared-memory and global-memory variants, pairwise and per-element branches of
+    std::shuffle) against the host's libstdc++ through fastace_shuffle_orders, cumulatively"""
+    import ctypes as C
+    L = emu.lib
+    pt = lambda a: a.ctypes.data_as(C.c_void_p)
+    for (E, P, F, smem, calls) in [(70, 100, 10, 1, (3, 1, 4)), (3, 48, 12, 1, (1, 1)), (5, 1, 1, 1, (2,)), (3, 2, 3, 1, (2, 2)),
+                                   (2, 1000, 37, 0, (1, 1)), (1, 50000, 3, 0, (1,))]:
+        host = scenario.OrderStream((E, P, F, 2, 10), 1234)
+        rng = np.zeros(E, np.uint64)
+        sp_, sf_ = np.zeros((E, P), np.int32), np.zeros((E, F), np.int32)
+        for call, steps in enumerate(calls):
+            op, of = np.zeros((steps, E, P), np.int32), np.zeros((steps, E, F), np.int32)
+            op16, of16 = np.zeros((steps, E, P), np.uint16), np.zeros((steps, E, F), np.uint16)
+            L.fastace_emu_shuffle(E, P, F, C.c_uint32(1234), 1 if call == 0 else 0, steps, pt(rng), pt(sp_), pt(sf_),
+                                  pt(op) if smem else None, pt(of) if smem else None, pt(op16) if smem else None,
+                                  pt(of16) if smem else None, smem)
+            for k in range(steps):
+                hp, hf = host.next()
+                if smem:
+                    assert np.array_equal(op[k], hp) and np.array_equal(of[k], hf) and np.array_equal(op16[k], hp) and np.array_equal(of16[k], hf)
+            assert np.array_equal(sp_, hp) and np.array_equal(sf_, hf) and np.array_equal(rng, host.rng_state)
+    # KAT of SURVEY.md App. C: minstd_rand0(1234), 0..9
+    rng, sp_, sf_ = np.zeros(1, np.uint64), np.zeros((1, 10), np.int32), np.zeros((1, 1), np.int32)
+    op, of = np.zeros((2, 1, 10), np.int32), np.zeros((2, 1, 1), np.int32)
+    L.fastace_emu_shuffle(1, 10, 1, C.c_uint32(1234), 1, 2, pt(rng), pt(sp_), pt(sf_), pt(op), pt(of), None, None, 1)
+    assert op[0, 0].tolist() == [5, 0, 4, 8, 1, 2, 7, 6, 3, 9]
+
+
+def test_segmented_sort_is_a_stable_sort_by_firm(emu):
+    """segmented_sort.cuh (histogram / scan / ranked scatter) == numpy's stable argsort, "no request" keys last"""
+    import ctypes as C
+    L = emu.lib
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(1)
+    for (n, F, chunk) in [(5000, 37, 256), (1, 1, 32), (0, 5, 64), (777, 1000, 96), (20000, 300, 4096), (4097, 2, 4096)]:
+        key = rng.integers(0, F, n).astype(np.uint16)
+        key[rng.random(n) < 0.3] = 0xFFFF
+        val = rng.integers(0, 2**32 - 1, n, dtype=np.uint64).astype(np.uint32)
+        bins = np.where(key == 0xFFFF, F, key).astype(np.int64)
+        seg = np.zeros(F + 1, np.uint32)
+        seg[1:] = np.cumsum(np.bincount(bins, minlength=F + 1)[:F])
+        hist = np.zeros((max((n + chunk - 1) // chunk, 1), F + 1), np.uint32)
+        ko, vo = np.zeros(n, np.uint16), np.zeros(n, np.uint32)
+        L.fastace_emu_segmented_sort(p(key), p(val), p(ko), p(vo), p(seg), p(hist), n, F, chunk)
+        order = np.argsort(bins, kind="stable")
+        assert np.array_equal(ko, key[order]) and np.array_equal(vo, val[order]), (n, F, chunk)
+
+
+def test_packed_encoding_expands_to_the_compact_one(emu):
+    """_abi.packed_actions_for_counts (host packer) -> expand_packed_kernel == _abi.compact_actions_for_counts"""
+    import ctypes as C
+    L = emu.lib
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for dims, modulo in (((3, 7, 5, 3, 10), True), ((2, 33, 10, 2, 10), False), ((2, 5, 40, 6, 16), True), ((1, 4, 1, 1, 1), True)):
+        E, P, F, G, S = dims
+        act = scenario.synthetic_actions(dims, seed=1, step=0, **scenario.BENCH_PRESET)
+        rng = np.random.default_rng(E)
+        jc, mc = rng.integers(0, F + 1, E), rng.integers(0, F * G + 1, E)
+        if not modulo:
+            for k, hi in (("p_job_idx", F + 2), ("p_good_idx", F * G + 2), ("f_good_idx", F * G + 2)):
+                act[k] = rng.integers(-1, hi, act[k].shape, dtype=np.int32)
+        pk = _abi.packed_actions_for_counts(act, jc, mc, modulo)
+        cz = _abi.compact_actions_for_counts(act, jc, mc, modulo)
+        bj, nbj, bg, nbg = _abi.packed_layout(F, G, S)
+        for name, tname, bits, nb, cnt in (("p_job_idx", "p_job_take", bj, nbj, jc), ("p_good_idx", "p_good_take", bg, nbg, mc),
+                                           ("f_good_idx", "f_good_take", bg, nbg, mc)):
+            n = pk[name].shape[0] * pk[name].shape[1]
+            idx, take = np.zeros((n, S), np.uint8), np.zeros(n, np.uint16)
+            L.fastace_emu_expand_packed(n, S, bits, nb, p(pk[name]), p(idx), p(take))
+            idx, take = idx.reshape(cz[name].shape), take.reshape(cz[tname].shape)
+            # a request = take bit set AND index inside the book; both encodings must name the same requests
+            want_idx = cz[name].astype(np.int64)
+            want = ((cz[tname][:, :, None] >> np.arange(S)) & 1).astype(bool) & (want_idx < cnt[:, None, None]) & (cnt[:, None, None] > 0)
+            got = ((take[:, :, None] >> np.arange(S)) & 1).astype(bool)
+            assert np.array_equal(got, want), name
+            assert np.array_equal(np.where(want, idx, 0), np.where(want, want_idx, 0)), name

@@ -322,3 +322,32 @@ def test_firm_money_near_tie(oracle, mode):
     hired = np.array([h for (_, _, _, h) in ties])
     assert np.array_equal(gout["p_job_ok"][:, 0, 2].astype(bool), hired) and hired.any() and (~hired).any()
     env.close()
+
+
+@pytest.mark.parametrize("own_orders", [False, True])
+def test_packed_host_encoding_matches(oracle, own_orders):
+    """fastace_env_step_host_packed: bit-field indices without take masks, optionally without visiting orders (the env
+    shuffles on the device) — same trajectory as the oracle on the int32 encoding with the host's std::shuffle orders"""
+    from fastace_b200.env import BatchedEconomy
+    dims = (9, 100, 10, 2, 10)
+    state = scenario.custom_initial_state(dims, 77)[0]
+    env = BatchedEconomy(dims)
+    env.set_state(state)
+    ost = H.copy_state(state)
+    orders = scenario.OrderStream(dims, 78)
+    if own_orders:
+        env.restart_orders(78)
+    keep = []
+    for t in range(14):
+        act = scenario.synthetic_actions(dims, seed=79, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
+        pk = _abi.packed_actions_for_counts(act, ost["j_count"], ost["m_count"], True, with_orders=not own_orders)
+        before = H.copy_state(ost)
+        oout, gout = _abi.alloc_host("out", dims), _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=_abi.IDX_MODULO, time_before=t)
+        pks = _abi.struct_from_numpy("packed", pk, env.dims)
+        keep.append((pk, pks))
+        env.time_step_host(pks, gout, flags=_abi.STEP_ASYNC if t % 2 else 0)
+        env.sync()
+        H.compare_outputs(gout, oout, dims, before)
+        H.compare_states(env.get_state(), ost, dims)
+    env.close()
