@@ -113,9 +113,58 @@ struct IndexMap {
     }
 };
 
-// pow for the reward path (1e-5 relative tolerance): exp(y*log(x)), fp64 throughout.
-// Relative error ~ |y ln x| * 2^-52, far inside the tolerance; ~3x cheaper than pow().
-__device__ __forceinline__ double pow_reward(double x, double y) { return exp(y * log(x)); }
+// pow for the reward path (utilities are rewards: 1e-5 relative tolerance, they never feed back into state).
+// x^y = exp(y * log x) in fp64 with short polynomials: log by 2*atanh((m-1)/(m+1)) on m in [sqrt(1/2), sqrt(2)) up to
+// s^13 (truncation < 2e-12 relative), exp by a degree-10 Taylor polynomial on |f| <= ln2/2 (< 1e-12); measured
+// against libm pow: <= 2e-11 relative over x in [1e-9, 1e9], |y| <= 30, |y ln x| < 690 (tests/test_emu_kernels.py).  ~45 fp64
+// instructions instead of ~90 for exp(y*log(x)) with the library routines, which remain the path for anything that
+// is not a positive normal number or whose exponent leaves [-700, 700].
+__device__ __forceinline__ double fast_rcp(double d) {
+#ifndef FASTACE_HAVE_SMEM_OPS
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));     // ~2^-23 relative
+    double t = fma(-d, r, 1.0);
+    r = fma(r, t, r);                                          // 2^-46
+    t = fma(-d, r, 1.0);
+    return fma(r, t, r);                                       // full precision
+#else
+    return 1.0 / d;
+#endif
+}
+__device__ __forceinline__ double pow_reward(double x, double y) {
+    if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return exp(y * log(x));
+    const long long b = __double_as_longlong(x);
+    int e = (int)(b >> 52) - 1023;
+    double m = __longlong_as_double((b & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);      // [1, 2)
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    const double s = (m - 1.0) * fast_rcp(m + 1.0);
+    const double s2 = s * s;
+    double p = 1.0 / 13.0;
+    p = fma(p, s2, 1.0 / 11.0);
+    p = fma(p, s2, 1.0 / 9.0);
+    p = fma(p, s2, 1.0 / 7.0);
+    p = fma(p, s2, 1.0 / 5.0);
+    p = fma(p, s2, 1.0 / 3.0);
+    p = fma(p, s2, 1.0);
+    const double lx = fma((double)e, 0.6931471805599453, 2.0 * s * p);                        // log x
+    const double z = y * lx;
+    if (!(fabs(z) < 700.0)) return exp(z);
+    const double kf = rint(z * 1.4426950408889634);
+    double f = fma(kf, -0.6931471803691238, z);                // ln2 split: hi has 32 significant bits
+    f = fma(kf, -1.9082149292705877e-10, f);
+    double q = 1.0 / 3628800.0;
+    q = fma(q, f, 1.0 / 362880.0);
+    q = fma(q, f, 1.0 / 40320.0);
+    q = fma(q, f, 1.0 / 5040.0);
+    q = fma(q, f, 1.0 / 720.0);
+    q = fma(q, f, 1.0 / 120.0);
+    q = fma(q, f, 1.0 / 24.0);
+    q = fma(q, f, 1.0 / 6.0);
+    q = fma(q, f, 0.5);
+    q = fma(q, f, 1.0);
+    q = fma(q, f, 1.0);
+    return __longlong_as_double(__double_as_longlong(q) + ((long long)(int)kf << 52));       // q * 2^k, result normal
+}
 
 // One goods request by a buyer whose money/inventory live at (money, inv[g*istride]).
 // Agent::respond_to_offer -> review_offer_response -> accept_offer_response

@@ -118,6 +118,9 @@ void fastace_emu_expand_packed(int agents, int S, int bits, int bytes, const uin
     if (agents > 0) emu::launch(expand_packed_kernel, (unsigned)((agents + 255) / 256), 256u, 0, a, none);
 }
 
+// pow_reward of common.cuh (the reward path's short-polynomial pow), for the accuracy test
+double fastace_emu_pow_reward(double x, double y) { return pow_reward(x, y); }
+
 // event counters of the kernels since the last call (common.cuh: kStat*); resets them
 void fastace_emu_stats(unsigned long long* out) {
     for (int i = 0; i < kStatCount; i++) { out[i] = emu::stats()[i]; emu::stats()[i] = 0; }

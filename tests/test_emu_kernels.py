@@ -222,3 +222,23 @@ def test_packed_encoding_expands_to_the_compact_one(emu):
             got = ((take[:, :, None] >> np.arange(S)) & 1).astype(bool)
             assert np.array_equal(got, want), name
             assert np.array_equal(np.where(want, idx, 0), np.where(want, want_idx, 0)), name
+
+
+def test_reward_pow_accuracy(emu):
+    """pow_reward (common.cuh: the short-polynomial x^y of the utility path) against libm pow: far inside the 1e-5
+    reward tolerance over the whole range it serves, and the library fallbacks for everything else"""
+    import ctypes as C
+    import math
+    f = emu.lib.fastace_emu_pow_reward
+    f.restype, f.argtypes = C.c_double, [C.c_double, C.c_double]
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for _ in range(20000):
+        x, y = 10 ** rng.uniform(-9, 9), rng.uniform(-30, 30)
+        if abs(y * math.log(x)) > 690:
+            continue
+        worst = max(worst, abs(f(x, y) - math.pow(x, y)) / math.pow(x, y))
+    assert worst < 5e-11, worst
+    assert f(2.0, -9.0) == 2.0 ** -9 and f(1.0, 5.0) == 1.0
+    assert f(float("inf"), -1.0) == 0.0 and math.isinf(f(0.0, -0.1)) and math.isnan(f(float("nan"), 1.0))
+    assert f(1e-8, 80.0) == 0.0 and abs(f(1e-320, 0.5) / 1e-160 - 1) < 1e-5      # underflow / denormal input: library path
