@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from fastace_b200 import _abi, scenario  # noqa: E402
+from fastace_b200 import _abi, scenario, sharding  # noqa: E402
 
 P, F, G, S = 100, 10, 2, 10
 EPISODE = 40
@@ -253,9 +253,11 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
-    E = args.econ
-    # economies shard by index: rank r owns global economies [r*E, (r+1)*E); distinct seeds per rank
-    dims, state, acts = build_workload(E, seed=1 + rank * E)
+    # economies shard by index (fastace_b200/sharding.py): rank r owns a contiguous block of the job's world*econ
+    # economies, seeded by its first global index — no collective in the step
+    lo, hi = sharding.shard_range(world * args.econ, rank, world)
+    E = hi - lo
+    dims, state, acts = build_workload(E, seed=1 + lo)
     env = BatchedEconomy(dims, device=local)
     env.set_state(state)
     dev = torch.device("cuda", local)
@@ -325,10 +327,7 @@ def run_ours(args):
         return np.array([s.elapsed_time(e) for s, e in zip(starts, stops)]), env.launch_count() - l0, w
 
     def whole_job(ms):
-        t_ms = torch.tensor([float(ms.sum())], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        return float(t_ms.item())
+        return sharding.reduce_max(float(ms.sum()), dist if world > 1 else None, dev)
 
     sampler = ClockSampler(local)   # samples through warm-up and the timed region (same load)
     sampler.start()
@@ -395,7 +394,7 @@ def run_ours(args):
     h2d_int32 = int(sum(v.nbytes for v in acts[0].values()))
     d2h = int(sum(v.nbytes for v in houts[0][0].values()))
 
-    order_seed = 1 + rank * E + 1000003        # build_workload's OrderStream: the device shuffle replays the same orders
+    order_seed = 1 + lo + 1000003        # build_workload's OrderStream: the device shuffle replays the same orders
 
     def run_e2e(structs, flags, n):
         reset_state(0)
@@ -577,7 +576,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "peak_source": peak_src,
-                         "kernel": "fastace::match_kernel<2,12> (dominant: %.0f%% of the step's device time)" % (100 * match_s / max(match_s + update_s, 1e-12)),
+                         "kernel": "fastace::match_kernel<2> (dominant: %.0f%% of the step's device time)" % (100 * match_s / max(match_s + update_s, 1e-12)),
                          "algorithmic_bytes_per_launch": BYTES_MATCH_PER_ECON_STEP * E,
                          "launch_ms": match_s * 1e3,
                          "step": {"kernels": {"match_kernel_ms": match_s * 1e3, "update_kernel_ms": update_s * 1e3},
