@@ -47,18 +47,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """`out`: write a variant build (profiling defines in `extra_flags`) somewhere else than the product library."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB] + SOURCES + ["-ldl"]
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-o", out or LIB] + SOURCES + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
+    out_path = out or LIB
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + out.stdout + out.stderr)
     if verbose and (out.stdout or out.stderr):
         print(out.stdout + out.stderr)
-    return LIB
+    return out_path
 
 
 if __name__ == "__main__":

@@ -63,7 +63,7 @@ template <int OFF = 0> __device__ __forceinline__ void sts_v4(uint32_t a, uint4 
 }
 #endif
 
-enum { kStatWindows, kStatRounds, kStatRescans, kStatRiskyWalks, kStatSalesWindows, kStatDeadExits, kStatFirmSerial, kStatRoundsW0, kStatRoundsW1, kStatRoundsW2, kStatRoundsW3, kStatRescansW0, kStatCount };
+enum { kStatWindows, kStatRounds, kStatRescans, kStatRiskyWalks, kStatSalesWindows, kStatDeadExits, kStatFirmSerial, kStatRoundsW0, kStatRoundsW1, kStatRoundsW2, kStatRoundsW3, kStatRescansW0, kStatRiskyCoop, kStatCount };
 
 struct StepParams {
     int E, P, F, S;

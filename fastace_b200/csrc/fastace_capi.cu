@@ -1204,4 +1204,12 @@ int fastace_env_launch_count(const fastace_env_t* env, uint64_t* out_count) {
     return FASTACE_OK;
 }
 
+#ifdef FASTACE_CTA_TIMING
+// profiling build only: (start ns, end ns, SM) of every economy's warp in the last match_kernel launch
+int fastace_debug_cta_times(unsigned long long* out, int economies) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, fastace::g_cta_times, sizeof(unsigned long long) * 3 * (size_t)economies) == cudaSuccess ? FASTACE_OK : FASTACE_ERR_CUDA;
+}
+#endif
+
 }  // extern "C"

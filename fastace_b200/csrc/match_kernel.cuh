@@ -170,9 +170,18 @@ __device__ __forceinline__ uint32_t map_request_word(uint32_t x, uint32_t take4,
 // All shared-memory traffic goes through explicit 32-bit shared addresses (common.cuh: lds_* / sts_*); the loops
 // over request slots are rolled (the lists live in shared memory), so the hot code of a window is a few hundred
 // instructions.
+#ifdef FASTACE_CTA_TIMING
+// profiling build only (tools/cta_timing.py): start / end time and SM of every economy's warp
+__device__ unsigned long long g_cta_times[3 * 65536];
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
+
 template <int G>
 __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     FASTACE_DYN_SMEM(smem);
+#ifdef FASTACE_CTA_TIMING
+    const unsigned long long cta_t0 = global_ns();
+#endif
     const StepParams& p = mp.sp;
     const int e = blockIdx.x;
     const int lane = threadIdx.x;
@@ -479,6 +488,136 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                         }
                     }
                 }
+                // ---- job offers whose firm may run out of money (firm.cpp:80-84): the death ordinal of such a row
+                //      follows the firm's exact running money in visiting order; a row whose ordinal moves is re-scanned
+                if (risk_possible && cb < NJ) {
+                    bool risky = false;
+                    uint32_t left = 0;
+                    int f = 0, tot = 0;
+                    double w = 0.0, m0 = 0.0;
+                    const uint32_t rec = aRec + (uint32_t)(R < NJ ? R : 0) * kRecBytes;
+                    if (R < NJ) {
+                        left = lds_u32<kRecLeft>(rec);
+                        tot = (int)lds_u32<kRecTot>(rec);
+                        // the applicants that could be hired exceed what the firm can certainly pay
+                        risky = tot > 0 && left > 0 && min(min((int)min(left, 0x7FFFFFFFu), tot), kMaxHiresPerWindow) >= (int)lds_u16<kRecSafe>(rec);
+                        if (risky) {
+                            f = (int)(lds_u32<kRecMeta>(rec) & 0xFFu);
+                            w = lds_f64<kRecValue>(rec);
+                            m0 = lds_f64(aFmoney + 8u * f);
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, risky)) {
+                        // does the firm sell anything in this window?  (its goods rows' successes = min(demand, D);
+                        // the demand is summed here: those rows may belong to a later chunk)
+                        bool fsales = false;
+                        if (risky) {
+                            const int first = (int)lds_u8(aFfirst + f), cnt = (int)lds_u8(aFcnt + f);
+                            for (int n = first; n < first + cnt; n++) {
+                                const uint32_t gm = aMatM + (uint32_t)n * kMatBytes;
+                                const uint4 a = lds_v4<kMatCnt>(gm), b = lds_v4<kMatCnt + 16>(gm);
+                                fsales |= (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) != 0u && lds_u32<kRecD>(aRecM + (uint32_t)n * kRecBytes) > 0u;
+                            }
+                        }
+                        int d = (int)min(left, 0x7FFFFFFFu);
+                        if (risky && !fsales) {
+                            // hires are the firm's only events: the order of the applicants does not matter
+                            FASTACE_STAT(kStatRiskyWalks, 1);
+                            double m = m0;
+                            const int most = min(d, tot);
+                            for (int h = 0; h < most; h++) {
+                                if (m < w) { d = h; break; }                            // firm.cpp:80-84
+                                m -= w;                                                 // firm.cpp:108
+                            }
+                        }
+                        // rows whose firm also sells in this window, one at a time with all lanes: lane l holds person l's
+                        // applications to the row and its purchases from the firm
+                        for (unsigned sm = __ballot_sync(0xffffffffu, risky && fsales); sm != 0; sm &= sm - 1) {
+                            const int src = __ffs((int)sm) - 1;
+                            const int fb = __shfl_sync(0xffffffffu, f, src);
+                            const double wb = __shfl_sync(0xffffffffu, w, src), mb = __shfl_sync(0xffffffffu, m0, src);
+                            const int leftb = __shfl_sync(0xffffffffu, d, src);
+                            const uint32_t matb = aMat + (uint32_t)(cb + src) * kMatBytes;
+                            const int c = (int)lds_u8<kMatCnt>(matb + (uint32_t)lane);
+                            double s = 0.0;
+                            for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {
+                                const uint32_t g = aRecM + lds_u8<kReqGoods>(aReqL + (uint32_t)(__ffs((int)m) - 1)) * kRecBytes;
+                                if ((int)(lds_u32<kRecMeta>(g) & 0xFFu) == fb) s += lds_f64<kRecValue>(g);
+                            }
+                            // prefixes over the visiting order: applications and sales before this lane's events
+                            int ac = c;
+                            double sx = s;
+#pragma unroll
+                            for (int dd = 1; dd < 32; dd <<= 1) {
+                                const int uc = __shfl_up_sync(0xffffffffu, ac, dd);
+                                const double us = __shfl_up_sync(0xffffffffu, sx, dd);
+                                if (lane >= dd) { ac += uc; sx += us; }
+                            }
+                            const int atot = __shfl_sync(0xffffffffu, ac, 31);
+                            const double stot = __shfl_sync(0xffffffffu, sx, 31);
+                            ac -= c; sx -= s;
+                            // Application number a (0-based, in visiting order) meets m0 - a*w + (sales before it) as long as
+                            // every earlier one was a hire (jobs precede purchases, person.cpp:26-29).  These sums differ from
+                            // the reference's event-by-event money by a few hundred roundings at most: a comparison that
+                            // clears `tol` is the reference's; anything closer is walked exactly below.
+                            const double tol = 1e-9 * (fabs(mb) + stot + (double)atot * wb);
+                            int failk = -1;
+                            bool unclear = !(wb >= 0.0) || lds_u8(aFrisk + (uint32_t)fb) != 0u;
+                            for (int k = 0; k < c && failk < 0; k++) {
+                                const int a = ac + k;
+                                if (a >= leftb) break;                                  // firm.cpp:64: exhausted
+                                const double gap = (mb - (double)a * wb + sx) - wb;
+                                if (!(fabs(gap) > tol)) unclear = true;
+                                if (gap < 0.0) failk = k;                               // firm.cpp:80-84
+                            }
+                            int db = leftb;
+                            const unsigned failed = __ballot_sync(0xffffffffu, failk >= 0);
+                            if (failed) db = __shfl_sync(0xffffffffu, ac + failk, __ffs((int)failed) - 1);
+                            if (__any_sync(0xffffffffu, unclear)) {
+                                // every lane publishes the goods it currently buys, in request order; the row's lane walks
+                                uint32_t ne = 0;
+                                for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {
+                                    sts_u8(aEv + (uint32_t)lane * kEvPerLane + 1u + ne, lds_u8<kReqGoods>(aReqL + (uint32_t)(__ffs((int)m) - 1)));
+                                    ne++;
+                                }
+                                sts_u8(aEv + (uint32_t)lane * kEvPerLane, ne);
+                                __syncwarp();
+                                if (lane == src) {
+                                    FASTACE_STAT(kStatRiskyWalks, 1);
+                                    double m = mb;
+                                    int h = 0;
+                                    bool done = false;
+                                    db = leftb;
+                                    for (int l = 0; l < 32 && !done; l++) {
+                                        const int cl = (int)lds_u8<kMatCnt>(matb + (uint32_t)l);
+                                        for (int k = 0; k < cl; k++) {
+                                            if (h >= db) { done = true; break; }               // firm.cpp:64
+                                            if (m < wb) { db = h; done = true; break; }        // firm.cpp:80-84
+                                            m -= wb;                                           // firm.cpp:108
+                                            h++;
+                                        }
+                                        const int nb = (int)lds_u8(aEv + (uint32_t)l * kEvPerLane);
+                                        for (int k = 0; k < nb && !done; k++) {
+                                            const uint32_t g = aRecM + lds_u8(aEv + (uint32_t)l * kEvPerLane + 1u + (uint32_t)k) * kRecBytes;
+                                            if ((int)(lds_u32<kRecMeta>(g) & 0xFFu) == fb) m += lds_f64<kRecValue>(g);   // agent.cpp:158
+                                        }
+                                    }
+                                }
+                                __syncwarp();
+                            } else if (lane == src) {
+                                FASTACE_STAT(kStatRiskyCoop, 1);
+                            }
+                            if (lane == src) d = db;
+                        }
+                        if (R < NJ && d != (int)lds_u32<kRecD>(rec)) {
+                            // the offer dies earlier / later than assumed: its rooms follow the new ordinal
+                            changed = true;
+                            needs = true;
+                            sts_u32<kRecD>(rec, (uint32_t)d);
+                        }
+                        __syncwarp();
+                    }
+                }
                 unsigned slow = __ballot_sync(0xffffffffu, needs);
                 while (slow) {
                     // two rows per shuffle scan (16-bit halves: a prefix is at most 32 * 16)
@@ -506,95 +645,6 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             }
             __syncwarp();
 
-            // ---- job offers whose firm may run out of money (firm.cpp:80-84): exact running money in visiting order
-            for (int cb = 0; risk_possible && cb < NJ; cb += 32) {
-                const int R = cb + lane;
-                bool risky = false;
-                uint32_t left = 0;
-                int f = 0, tot = 0;
-                double w = 0.0, m0 = 0.0;
-                const uint32_t rec = aRec + (uint32_t)(R < NJ ? R : 0) * kRecBytes;
-                const uint32_t mat = aMat + (uint32_t)(R < NJ ? R : 0) * kMatBytes;
-                if (R < NJ) {
-                    left = lds_u32<kRecLeft>(rec);
-                    tot = (int)lds_u32<kRecTot>(rec);
-                    // the applicants that could be hired exceed what the firm can certainly pay
-                    risky = tot > 0 && left > 0 && min(min((int)min(left, 0x7FFFFFFFu), tot), kMaxHiresPerWindow) >= (int)lds_u16<kRecSafe>(rec);
-                    if (risky) {
-                        f = (int)(lds_u32<kRecMeta>(rec) & 0xFFu);
-                        w = lds_f64<kRecValue>(rec);
-                        m0 = lds_f64(aFmoney + 8u * f);
-                    }
-                }
-                if (__any_sync(0xffffffffu, risky)) {
-                    // does the firm sell anything in this window?  (its goods rows' successes = min(tot, D))
-                    bool fsales = false;
-                    if (risky) {
-                        const int first = (int)lds_u8(aFfirst + f), cnt = (int)lds_u8(aFcnt + f);
-                        for (int n = first; n < first + cnt; n++) {
-                            const uint32_t g = aRecM + (uint32_t)n * kRecBytes;
-                            fsales |= min(lds_u32<kRecTot>(g), lds_u32<kRecD>(g)) > 0u;
-                        }
-                    }
-                    if (__any_sync(0xffffffffu, fsales)) {
-                        // every lane publishes the goods it currently buys, in request order
-                        uint32_t ne = 0;
-                        for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {
-                            const int k = __ffs((int)m) - 1;
-                            sts_u8(aEv + (uint32_t)lane * kEvPerLane + 1u + ne, lds_u8<kReqGoods>(aReqL + (uint32_t)k));
-                            ne++;
-                        }
-                        sts_u8(aEv + (uint32_t)lane * kEvPerLane, ne);
-                        __syncwarp();
-                    }
-                    if (R < NJ) {
-                        int d = (int)min(left, 0x7FFFFFFFu);
-                        if (risky && !fsales) {
-                            // hires are the firm's only events: the order of the applicants does not matter
-                            FASTACE_STAT(kStatRiskyWalks, 1);
-                            double m = m0;
-                            const int most = min(d, tot);
-                            for (int h = 0; h < most; h++) {
-                                if (m < w) { d = h; break; }                            // firm.cpp:80-84
-                                m -= w;                                                 // firm.cpp:108
-                            }
-                        } else if (risky) {
-                            FASTACE_STAT(kStatRiskyWalks, 1);
-                            double m = m0;
-                            int h = 0;
-                            bool done = false;
-                            for (int l = 0; l < 32 && !done; l++) {
-                                const int c = (int)lds_u8<kMatCnt>(mat + (uint32_t)l);
-                                for (int k = 0; k < c; k++) {
-                                    if (h >= d) { done = true; break; }                 // firm.cpp:64
-                                    if (m < w) { d = h; done = true; break; }           // firm.cpp:80-84
-                                    m -= w;                                             // firm.cpp:108
-                                    h++;
-                                }
-                                const int nb = (int)lds_u8(aEv + (uint32_t)l * kEvPerLane);
-                                for (int k = 0; k < nb && !done; k++) {
-                                    const uint32_t g = aRecM + lds_u8(aEv + (uint32_t)l * kEvPerLane + 1u + (uint32_t)k) * kRecBytes;
-                                    if ((int)(lds_u32<kRecMeta>(g) & 0xFFu) == f) m += lds_f64<kRecValue>(g);   // agent.cpp:158
-                                }
-                            }
-                        }
-                        if (d != (int)lds_u32<kRecD>(rec)) {
-                            // the offer dies earlier / later than assumed: its rooms follow the new ordinal
-                            changed = true;
-                            sts_u32<kRecD>(rec, (uint32_t)d);
-                            sts_u8<kRecScanned>(rec, 1u);
-                            int run = 0;
-                            for (int l = 0; l < 32; l++) {
-                                const int c = (int)lds_u8<kMatCnt>(mat + (uint32_t)l);
-                                sts_u8<kMatRoom>(mat + (uint32_t)l, (uint32_t)max(0, min(kRoomMax, d - run)));
-                                sts_u8<kMatPrev>(mat + (uint32_t)l, (uint32_t)c);
-                                run += c;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
             // ---- round end: converged? reset the counts
             const bool again = __any_sync(0xffffffffu, changed);
             if (!again) break;
@@ -851,6 +901,13 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             for (int i = 0; i < S; i++) p.out.f_good_ok[((size_t)e * S + i) * F + f] = (ok >> i) & 1u;
         }
     }
+#ifdef FASTACE_CTA_TIMING
+    if (lane == 0 && e < 65536) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        g_cta_times[3 * e] = cta_t0; g_cta_times[3 * e + 1] = global_ns(); g_cta_times[3 * e + 2] = smid;
+    }
+#endif
 }
 
 }  // namespace fastace
