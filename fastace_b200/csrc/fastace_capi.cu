@@ -187,6 +187,8 @@ struct fastace_env {
     size_t match_smem_bytes;  // match_kernel
     uint8_t* scr_pnh;         // [E][P]    match_kernel -> update_kernel
     uint8_t* scr_pnb;         // [E][G][P]
+    uint32_t* done_queue;     // completion queue between the two kernels of a full step: [E] slots + the ticket counter
+    uint32_t queue_launches;  // full steps launched through the queue (tickets handed out = queue_launches * E, mod 2^32)
     // visiting orders generated on the device (fastace_env_shuffle_orders)
     uint64_t* ord_rng;        // [E]    one minstd_rand0 per economy
     int32_t* ord_person;      // [E][P] cumulative order of the persons
@@ -228,6 +230,10 @@ using namespace fastace;
 static int check_device_errors(const fastace_env_t* env) {
     if (!env->err_host) return FASTACE_OK;
     volatile const uint32_t* w = env->err_host;
+    if (w[kDevErrQueue]) {
+        set_error("update_kernel: gave up waiting on the completion queue of match_kernel (state is not a valid step result)");
+        return FASTACE_ERR_CUDA;
+    }
     if (w[kDevErrRounds] | w[kDevErrLargeRounds]) {
         set_error(w[kDevErrRounds] ? "match_kernel: a window's fixed-point iteration hit the round cap (state is not a valid step result)"
                                    : "large-economy path: the iteration hit the round cap (state is not a valid step result)");
@@ -358,6 +364,16 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
             cudaGetLastError();
             fastace_env_destroy(env); return FASTACE_ERR_ALLOC;
         }
+        // FASTACE_NO_QUEUE=1 (diagnostics): update_kernel waits for the whole match grid, as the phase-wise calls do
+        const char* noq = getenv("FASTACE_NO_QUEUE");
+        if (!(noq && noq[0] == '1') && d.num_econ > 0 && (uint32_t)d.num_econ <= kQueueEconMask) {
+            const size_t qbytes = ((size_t)d.num_econ + 1) * sizeof(uint32_t);
+            if (cudaMalloc((void**)&env->done_queue, qbytes) != cudaSuccess || cudaMemset(env->done_queue, 0, qbytes) != cudaSuccess) {
+                set_error("cudaMalloc of the completion queue failed");
+                cudaGetLastError();
+                fastace_env_destroy(env); return FASTACE_ERR_ALLOC;
+            }
+        }
     }
     {
         cudaError_t e1 = cudaHostAlloc((void**)&env->err_host, 4 * sizeof(uint32_t), cudaHostAllocMapped);
@@ -393,6 +409,7 @@ int fastace_env_destroy(fastace_env_t* env) {
     if (env->have_ev) for (int i = 0; i < 3; i++) cudaEventDestroy(env->ev[i]);
     if (env->scr_pnh) cudaFree(env->scr_pnh);
     if (env->scr_pnb) cudaFree(env->scr_pnb);
+    if (env->done_queue) cudaFree(env->done_queue);
     if (env->err_host) cudaFreeHost(env->err_host);
     if (env->ord_rng) cudaFree(env->ord_rng);
     if (env->ord_person) cudaFree(env->ord_person);
@@ -770,6 +787,12 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         MatchParams mp;
         mp.sp = sp; mp.scr_pnh = env->scr_pnh; mp.scr_pnb = env->scr_pnb; mp.dev_err = env->err_dev;
         mp.lay = make_match_layout(sp.P, sp.F, env->dims.num_goods, sp.S);
+        // a full step hands finished economies from match_kernel to update_kernel through the completion queue
+        const bool queue = env->done_queue != nullptr && !only_p && !only_f;
+        mp.done_list = queue ? env->done_queue : nullptr;
+        mp.done_count = queue ? env->done_queue + sp.E : nullptr;
+        mp.ticket_base = env->queue_launches * (uint32_t)sp.E;
+        mp.done_tag = (env->queue_launches % 255u) + 1u;
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[0], stream));
         if (!ph_c) {   // a consume-only call has no matching to do
             FASTACE_CUDA_CHECK(launch_dependent((const void*)ks.match, dim3((unsigned)sp.E), dim3(32), env->match_smem_bytes, stream, &mp));
@@ -779,11 +802,19 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[1], stream));
         UpdateParams up;
         up.sp = sp; up.scr_pnh = env->scr_pnh; up.scr_pnb = env->scr_pnb;
+        up.done_list = mp.done_list; up.done_tag = mp.done_tag; up.dev_err = env->err_dev;
         const size_t persons = (size_t)sp.E * sp.P;
         // update_kernel: blocks [0, firm_blocks) do the firms, the rest the persons; a phase call launches only its part
         const int person_blocks = only_f ? 0 : (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
         up.firm_blocks = only_p ? 0 : (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
-        if (person_blocks + up.firm_blocks > 0) {
+        if (queue) {
+            const int qgroups = (sp.E + kQueueGroup - 1) / kQueueGroup;
+            up.group_person_blocks = (kQueueGroup * sp.P + kUpdateThreads - 1) / kUpdateThreads;
+            const int qblocks = qgroups * (kQueueGroup / (kUpdateThreads / 32) + up.group_person_blocks);
+            FASTACE_CUDA_CHECK(launch_dependent((const void*)ks.update, dim3((unsigned)qblocks), dim3(kUpdateThreads), 0, stream, &up));
+            env->launches += 1;
+            env->queue_launches += 1;
+        } else if (person_blocks + up.firm_blocks > 0) {
             FASTACE_CUDA_CHECK(launch_dependent((const void*)ks.update, dim3((unsigned)(person_blocks + up.firm_blocks)), dim3(kUpdateThreads), 0, stream, &up));
             env->launches += 1;
         }

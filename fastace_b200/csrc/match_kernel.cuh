@@ -75,6 +75,14 @@ constexpr int kReqGoods = FASTACE_MAX_STACK;
 // fastace_env_sync, fastace_env_get_state and the next step call
 constexpr int kDevErrRounds = 0;        // the window iteration hit kRoundCap (would break bit-exactness)
 constexpr int kDevErrLargeRounds = 1;   // the large-economy iteration hit its round cap
+constexpr int kDevErrQueue = 2;         // update_kernel gave up waiting on the completion queue
+
+// Completion queue (full steps): a warp of match_kernel that has finished its economy takes a ticket and writes
+// (tag << 24 | economy) into slot `ticket - base`; block k of update_kernel, which may already be resident (programmatic
+// dependent launch), processes the k-th economy to finish.  So the element-wise update of the early economies runs in
+// the SM time the slow ones leave idle.  Tickets count up for ever (`base` = queue launches so far x E, mod 2^32).
+constexpr int kQueueTagShift = 24;
+constexpr uint32_t kQueueEconMask = (1u << kQueueTagShift) - 1u;
 
 struct MatchLayout {
     int off_mat, off_rec;                                 // matrix rows, record rows (F + F*G + 2 each)
@@ -120,6 +128,9 @@ struct MatchParams {
     uint8_t* scr_pnh;    // [E][P]    hires per person (0..2)         -> update_kernel
     uint8_t* scr_pnb;    // [E][G][P] purchases per person and good   -> update_kernel
     volatile uint32_t* dev_err;   // device error words of the env
+    uint32_t* done_list;          // completion queue [E] (null: update_kernel waits for the whole grid instead)
+    uint32_t* done_count;         // its ticket counter
+    uint32_t ticket_base, done_tag;
 };
 
 // inclusive prefix sum over the lanes of a warp
@@ -900,6 +911,12 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             const uint32_t ok = lds_u32(aFok + 4u * f);
             for (int i = 0; i < S; i++) p.out.f_good_ok[((size_t)e * S + i) * F + f] = (ok >> i) & 1u;
         }
+    }
+    if (mp.done_list) {
+        // this economy's matching results are complete: hand it to update_kernel
+        fence_gpu();
+        __syncwarp();
+        if (lane == 0) store_release_u32(mp.done_list + (ticket_add(mp.done_count) - mp.ticket_base), (mp.done_tag << kQueueTagShift) | (uint32_t)e);
     }
 #ifdef FASTACE_CTA_TIMING
     if (lane == 0 && e < 65536) {

@@ -17,77 +17,57 @@
 
 namespace fastace {
 
-// -------------------------------------------------------------------------------------------------
-// update_kernel: blocks [0, firm_blocks) handle firms (one warp per economy, lanes = (visiting rank,
-// output good) pairs; scheduled first because their fp64 pow chains are the longest), the remaining
-// blocks handle persons (one thread each).
-struct UpdateParams {
-    StepParams sp;
-    const uint8_t* scr_pnh;
-    const uint8_t* scr_pnb;
-    int firm_blocks;
-};
-
-constexpr int kUpdateThreads = 128;
-
+// ---- UtilMaxer::consume_goods (utilMaxer.cpp:88-92) + choose_goods_to_consume
+//      (neuralPersonDecisionMaker.cpp:93-111) + UtilMaxer::u (utilMaxer.cpp:54-62)
 template <int G>
-__global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateParams up) {
-    const StepParams& p = up.sp;
-    const int P = p.P, F = p.F;
-    grid_dependency_wait();        // the matching results of this step (programmatic dependent launch)
-    grid_launch_dependents();
-    if ((int)blockIdx.x >= up.firm_blocks) {
-        // ---- UtilMaxer::consume_goods (utilMaxer.cpp:88-92) + choose_goods_to_consume
-        //      (neuralPersonDecisionMaker.cpp:93-111) + UtilMaxer::u (utilMaxer.cpp:54-62)
-        const size_t t = (size_t)((int)blockIdx.x - up.firm_blocks) * kUpdateThreads + threadIdx.x;
-        if (t >= (size_t)p.E * P) return;
-        const int e = (int)(t / P), pid = (int)(t % P);
-        const double labor = kLaborPerOffer * (double)up.scr_pnh[t];       // exact: 0, 0.5 or 1.0
-        if (p.flags & FASTACE_STEP_PERSONS_TRADE) {
-            // trade-only call: purchases and labour go into the state, consumption follows in its own call
-            // (it touches nobody but the person, so deferring it changes nothing: utilMaxer.cpp:88-92)
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                const size_t k = ((size_t)e * G + g) * P + pid;
-                double v = p.st.p_inv[k];
-                const int nb = up.scr_pnb[k];
-                for (int q = 0; q < nb; q++) v += kAmountPerOffer;         // agent.cpp:109, one add per purchase
-                p.st.p_inv[k] = v;
-            }
-            p.st.p_labor[t] = labor;
-            return;
-        }
-        const bool applied = (p.flags & FASTACE_STEP_PERSONS_CONSUME) != 0;   // purchases are already in p_inv
-        double x[G + 1], inv[G];
-        x[0] = 1 - labor;
+__device__ __forceinline__ void update_person(const StepParams& p, const uint8_t* scr_pnh, const uint8_t* scr_pnb, int e, int pid) {
+    const int P = p.P;
+    const size_t t = (size_t)e * P + pid;
+    const double labor = kLaborPerOffer * (double)scr_pnh[t];       // exact: 0, 0.5 or 1.0
+    if (p.flags & FASTACE_STEP_PERSONS_TRADE) {
+        // trade-only call: purchases and labour go into the state, consumption follows in its own call
+        // (it touches nobody but the person, so deferring it changes nothing: utilMaxer.cpp:88-92)
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const size_t k = ((size_t)e * G + g) * P + pid;
             double v = p.st.p_inv[k];
-            const int nb = applied ? 0 : up.scr_pnb[k];
-            for (int q = 0; q < nb; q++) v += kAmountPerOffer;             // agent.cpp:109, one add per purchase
-            const double c = v * (double)p.ac.p_consume[k];                 // neuralPersonDecisionMaker.cpp:99
-            x[g + 1] = c;
-            inv[g] = v - c;                                                 // utilMaxer.cpp:91
+            const int nb = scr_pnb[k];
+            for (int q = 0; q < nb; q++) v += kAmountPerOffer;         // agent.cpp:109, one add per purchase
+            p.st.p_inv[k] = v;
         }
-        double share[G + 1], theta[G + 1];
-#pragma unroll
-        for (int i = 0; i <= G; i++) {
-            share[i] = p.st.p_util_share[((size_t)e * (G + 1) + i) * P + pid];
-            theta[i] = (p.util_kind == FASTACE_FN_STONE_GEARY) ? p.st.p_util_theta[((size_t)e * (G + 1) + i) * P + pid] : 0.0;
-        }
-        p.out.p_reward[t] = eval_function<G + 1, true>(p.util_kind, p.st.p_util_tfp[t], share, theta, p.st.p_util_rho[t], x);
         p.st.p_labor[t] = labor;
-#pragma unroll
-        for (int g = 0; g < G; g++) p.st.p_inv[((size_t)e * G + g) * P + pid] = inv[g];
         return;
     }
-    // ---- firms: produce (profitMaxer.cpp:68-72), sell_goods / search_for_laborers decode
-    //      (neuralFirmDecisionMaker.cpp:111-180), new books in market order (economy.cpp:52-59, 125-126)
-    const int warps_per_block = kUpdateThreads / 32;
-    const int e = (int)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (e >= p.E) return;
-    const int lane = threadIdx.x & 31;
+    const bool applied = (p.flags & FASTACE_STEP_PERSONS_CONSUME) != 0;   // purchases are already in p_inv
+    double x[G + 1], inv[G];
+    x[0] = 1 - labor;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const size_t k = ((size_t)e * G + g) * P + pid;
+        double v = p.st.p_inv[k];
+        const int nb = applied ? 0 : scr_pnb[k];
+        for (int q = 0; q < nb; q++) v += kAmountPerOffer;             // agent.cpp:109, one add per purchase
+        const double c = v * (double)p.ac.p_consume[k];                 // neuralPersonDecisionMaker.cpp:99
+        x[g + 1] = c;
+        inv[g] = v - c;                                                 // utilMaxer.cpp:91
+    }
+    double share[G + 1], theta[G + 1];
+#pragma unroll
+    for (int i = 0; i <= G; i++) {
+        share[i] = p.st.p_util_share[((size_t)e * (G + 1) + i) * P + pid];
+        theta[i] = (p.util_kind == FASTACE_FN_STONE_GEARY) ? p.st.p_util_theta[((size_t)e * (G + 1) + i) * P + pid] : 0.0;
+    }
+    p.out.p_reward[t] = eval_function<G + 1, true>(p.util_kind, p.st.p_util_tfp[t], share, theta, p.st.p_util_rho[t], x);
+    p.st.p_labor[t] = labor;
+#pragma unroll
+    for (int g = 0; g < G; g++) p.st.p_inv[((size_t)e * G + g) * P + pid] = inv[g];
+}
+
+// ---- firms: produce (profitMaxer.cpp:68-72), sell_goods / search_for_laborers decode
+//      (neuralFirmDecisionMaker.cpp:111-180), new books in market order (economy.cpp:52-59, 125-126); one warp
+template <int G>
+__device__ __forceinline__ void update_firms(const StepParams& p, int e, int lane) {
+    const int F = p.F;
     const int cap = F * G;
     const size_t eF = (size_t)e * F, eCap = (size_t)e * cap;
     int base_m = 0, base_j = 0;
@@ -164,6 +144,90 @@ __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateP
         p.st.m_count[e] = base_m;
         p.st.j_count[e] = base_j;
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// update_kernel, two work assignments:
+//   * whole-grid (phase-wise calls, `done_list` null): blocks [0, firm_blocks) handle firms (one warp per economy,
+//     lanes = (visiting rank, output good) pairs; scheduled first because their fp64 pow chains are the longest), the
+//     remaining blocks handle persons (one thread each); everything waits for match_kernel to complete.
+//   * completion queue (full steps): the same firm warps and person threads, but assigned to queue slots instead of
+//     economies — slot k is the k-th economy match_kernel finishes — and each waits only for its own slot
+//     (match_kernel.cuh: completion queue).
+struct UpdateParams {
+    StepParams sp;
+    const uint8_t* scr_pnh;
+    const uint8_t* scr_pnb;
+    int firm_blocks;
+    const uint32_t* done_list;
+    uint32_t done_tag;
+    int group_person_blocks;         // queue mode: person blocks per group of kQueueGroup slots
+    volatile uint32_t* dev_err;
+};
+
+constexpr int kQueueGroup = 32;
+
+constexpr int kUpdateThreads = 128;
+constexpr unsigned kQueuePollNs = 128;
+constexpr uint32_t kQueuePollCap = 1u << 23;     // x 128 ns: about a second, then kDevErrQueue
+
+template <int G>
+__global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateParams up) {
+    const StepParams& p = up.sp;
+    const int P = p.P, F = p.F;
+    const int lane = threadIdx.x & 31;
+    int e = 0, pid = 0, pid_end = 0, pid_step = 1;
+    bool firms_here = false;
+    if (up.done_list) {
+        grid_launch_dependents();
+        // blocks come in groups that consume kQueueGroup consecutive queue slots: first the firm blocks (a warp per
+        // slot), then the person blocks (a thread per person of those slots), so that blocks are dispatched in the
+        // order their economies finish
+        const int firm_blocks = kQueueGroup / (kUpdateThreads / 32);
+        const int per_group = firm_blocks + up.group_person_blocks;
+        const int grp = (int)blockIdx.x / per_group, idx = (int)blockIdx.x % per_group;
+        int slot;
+        bool work = true;
+        if (idx < firm_blocks) {
+            slot = grp * kQueueGroup + idx * (kUpdateThreads / 32) + (int)(threadIdx.x >> 5);
+            firms_here = true;
+        } else {
+            const int v = (idx - firm_blocks) * kUpdateThreads + (int)threadIdx.x;
+            work = v < kQueueGroup * P;
+            slot = grp * kQueueGroup + (work ? v / P : 0);
+            pid = work ? v % P : 0;
+        }
+        work = work && slot < p.E;
+        // every thread polls the slot it needs (the lanes of a warp read one or two words); the previous step's update
+        // has completed before any warp of match_kernel took a ticket, so a matching tag is this step's entry
+        uint32_t v = 0, polls = 0;
+        while (work) {
+            v = load_acquire_u32(up.done_list + slot);
+            if ((v >> kQueueTagShift) == up.done_tag) break;
+            if (++polls >= kQueuePollCap) { up.dev_err[kDevErrQueue] = 1u; work = false; }
+            else backoff_ns(kQueuePollNs);
+        }
+        e = (int)(v & kQueueEconMask);
+        firms_here = firms_here && work;      // warp-uniform: the lanes of a firm warp share one slot
+        pid_end = (work && !firms_here && idx >= firm_blocks) ? pid + 1 : pid;
+    } else {
+        grid_dependency_wait();        // the matching results of this step (programmatic dependent launch)
+        grid_launch_dependents();
+        if ((int)blockIdx.x >= up.firm_blocks) {
+            const size_t t = (size_t)((int)blockIdx.x - up.firm_blocks) * kUpdateThreads + threadIdx.x;
+            if (t >= (size_t)p.E * P) return;
+            e = (int)(t / P); pid = (int)(t % P); pid_end = pid + 1;
+        } else {
+            e = (int)blockIdx.x * (kUpdateThreads / 32) + (int)(threadIdx.x >> 5);
+            if (e >= p.E) return;
+            firms_here = true;
+        }
+    }
+    if (firms_here) update_firms<G>(p, e, lane);
+    for (; pid < pid_end; pid += pid_step) update_person<G>(p, up.scr_pnh, up.scr_pnb, e, pid);
+    // queue mode: the block of the last economy to finish keeps this grid open until match_kernel has completed as a
+    // grid, so that whatever follows in the stream is ordered after both kernels
+    if (up.done_list && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) grid_dependency_wait();
 }
 
 }  // namespace fastace

@@ -15,7 +15,8 @@
 using namespace fastace;
 
 template <int G>
-static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vector<uint8_t>& pnb, uint32_t* err) {
+static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vector<uint8_t>& pnb, uint32_t* err,
+                     std::vector<uint32_t>& queue, uint32_t& queue_launches) {
     const uint32_t flags = sp.flags;
     const bool ph_p = (flags & FASTACE_STEP_PERSONS) != 0, only_f = (flags & FASTACE_STEP_FIRMS) != 0;
     const bool ph_t = (flags & FASTACE_STEP_PERSONS_TRADE) != 0, ph_c = (flags & FASTACE_STEP_PERSONS_CONSUME) != 0;
@@ -23,11 +24,26 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
     MatchParams mp;
     mp.sp = sp; mp.scr_pnh = pnh.data(); mp.scr_pnb = pnb.data(); mp.dev_err = err;
     mp.lay = make_match_layout(sp.P, sp.F, G, sp.S);
+    // as launch_step does: a full step goes through the completion queue
+    const bool use_queue = !only_p && !only_f && sp.E > 0;
+    mp.done_list = use_queue ? queue.data() : nullptr;
+    mp.done_count = use_queue ? queue.data() + sp.E : nullptr;
+    mp.ticket_base = queue_launches * (uint32_t)sp.E;
+    mp.done_tag = (queue_launches % 255u) + 1u;
     if (!ph_c) {
         emu::launch(match_kernel<G>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
     }
     UpdateParams up;
     up.sp = sp; up.scr_pnh = pnh.data(); up.scr_pnb = pnb.data();
+    up.done_list = mp.done_list; up.done_tag = mp.done_tag; up.dev_err = err;
+    if (use_queue) {
+        const int qgroups = (sp.E + kQueueGroup - 1) / kQueueGroup;
+        up.group_person_blocks = (kQueueGroup * sp.P + kUpdateThreads - 1) / kUpdateThreads;
+        const int qblocks = qgroups * (kQueueGroup / (kUpdateThreads / 32) + up.group_person_blocks);
+        emu::launch(update_kernel<G>, (unsigned)qblocks, (unsigned)kUpdateThreads, 0, up);
+        queue_launches += 1;
+        return;
+    }
     const size_t persons = (size_t)sp.E * sp.P;
     const int person_blocks = only_f ? 0 : (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
     up.firm_blocks = only_p ? 0 : (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
@@ -38,6 +54,8 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
 struct EmuEnv {
     std::vector<uint8_t> pnh, pnb;
     uint32_t err[4] = {0, 0, 0, 0};
+    std::vector<uint32_t> queue;
+    uint32_t queue_launches = 0;
 };
 
 extern "C" {
@@ -46,6 +64,7 @@ void* fastace_emu_create(const fastace_dims_t* d) {
     EmuEnv* e = new EmuEnv();
     e->pnh.assign((size_t)d->num_econ * d->num_persons + 1, 0xEE);
     e->pnb.assign((size_t)d->num_econ * d->num_persons * d->num_goods + 1, 0xEE);
+    e->queue.assign((size_t)d->num_econ + 1, 0u);
     return e;
 }
 void fastace_emu_destroy(void* h) { delete static_cast<EmuEnv*>(h); }
@@ -72,12 +91,12 @@ int fastace_emu_step(void* h, const fastace_dims_t* d, fastace_state_t* state, c
     }
     sp.out = *out;
     switch (d->num_goods) {
-        case 1: run_step<1>(sp, env->pnh, env->pnb, env->err); break;
-        case 2: run_step<2>(sp, env->pnh, env->pnb, env->err); break;
-        case 3: run_step<3>(sp, env->pnh, env->pnb, env->err); break;
-        case 4: run_step<4>(sp, env->pnh, env->pnb, env->err); break;
-        case 5: run_step<5>(sp, env->pnh, env->pnb, env->err); break;
-        case 8: run_step<8>(sp, env->pnh, env->pnb, env->err); break;
+        case 1: run_step<1>(sp, env->pnh, env->pnb, env->err, env->queue, env->queue_launches); break;
+        case 2: run_step<2>(sp, env->pnh, env->pnb, env->err, env->queue, env->queue_launches); break;
+        case 3: run_step<3>(sp, env->pnh, env->pnb, env->err, env->queue, env->queue_launches); break;
+        case 4: run_step<4>(sp, env->pnh, env->pnb, env->err, env->queue, env->queue_launches); break;
+        case 5: run_step<5>(sp, env->pnh, env->pnb, env->err, env->queue, env->queue_launches); break;
+        case 8: run_step<8>(sp, env->pnh, env->pnb, env->err, env->queue, env->queue_launches); break;
         default: return -1;
     }
     return (int)(env->err[0] | (env->err[1] << 1));
