@@ -581,7 +581,10 @@ def run_ours(args):
                          "launch_ms": match_s * 1e3,
                          "step": {"kernels": {"match_kernel_ms": match_s * 1e3, "update_kernel_ms": update_s * 1e3},
                                   "algorithmic_bytes_per_step": BYTES_PER_ECON_STEP * E, "achieved": step_achieved,
-                                  "frac": step_achieved / peak}},
+                                  "frac": step_achieved / peak,
+                                  "note": "kernels timed one at a time (FASTACE_STEP_PROFILE serialises them); in the timed steps "
+                                          "update_kernel consumes match_kernel's completion queue and overlaps its tail, so "
+                                          "ms_per_step is below the sum"}},
         }
         if rollout is not None:
             line["full_rollout"] = rollout

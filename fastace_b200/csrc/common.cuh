@@ -77,6 +77,9 @@ template <int OFF = 0> __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
 template <int OFF = 0> __device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0+%1], {%2,%3,%4,%5};" :: "r"(a), "n"(OFF), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
+__device__ __forceinline__ void reds_or_u32(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+// hint: bring the line that holds *p towards this SM (no register, no dependency)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #endif
 
 enum { kStatWindows, kStatRounds, kStatRescans, kStatRiskyWalks, kStatSalesWindows, kStatDeadExits, kStatFirmSerial, kStatRoundsW0, kStatRoundsW1, kStatRoundsW2, kStatRoundsW3, kStatRescansW0, kStatRiskyCoop, kStatCount };

@@ -187,6 +187,8 @@ __device__ unsigned long long g_cta_times[3 * 65536];
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #endif
 
+static_assert(kMaxStack == 16, "request lists are staged as four words");
+
 template <int G>
 __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     FASTACE_DYN_SMEM(smem);
@@ -264,20 +266,45 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
 #pragma unroll
         for (int g = 0; g < G; g++) sts_f64(aFinv + 8u * (g * F + f), p.st.f_inv[((size_t)e * G + g) * F + f]);
         if (do_firms) sts_f64(aFlast + 8u * f, p.st.f_last_money[eF + f]);
+        prefetch_l1(p.st.f_labor + eF + f);          // read at the very end (laborHired += 0.5 per hire)
     }
     if (do_firms) {
         // the firms' own requests: byte i of firm f = goods offer number or kNone (empty book: no requests at all,
         // decisionNetHandler.cpp:398-403)
-        for (int k = lane; k < F * 16; k += 32) {
-            const int f = k >> 4, i = k & 15;
-            uint32_t n = (uint32_t)kNone;
-            if (i < S && NM > 0) {
-                const size_t a = (size_t)e * S * F + (size_t)i * F + f;     // int32 encoding: [E][S][F]
-                const bool take = p.compact ? ((p.cz.f_good_take[eF + f] >> i) & 1u) != 0 : p.ac.f_good_take[a] != 0;
-                const int raw = p.compact ? (int)p.cz.f_good_idx[(eF + f) * S + i] : p.ac.f_good_idx[a];   // compact: [E][F][S]
-                if (take) n = (uint32_t)mapM(raw);
+        const bool modulo = (p.flags & FASTACE_IDX_MODULO) != 0;
+        for (int f = lane; f < F; f += 32) {
+            const uint32_t none4 = (uint32_t)kNone * 0x01010101u;
+            uint32_t w[kMaxStack / 4];
+#pragma unroll
+            for (int q = 0; q < kMaxStack / 4; q++) w[q] = none4;
+            if (NM > 0 && p.compact) {
+                // agent-major bytes: the aligned words that cover the firm's S request bytes, four slots at a time
+                const uint8_t* lst = p.cz.f_good_idx + (eF + f) * (size_t)S;
+                const uint32_t take = p.cz.f_good_take[eF + f] & ((1u << S) - 1u);
+                const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(lst) & 3u);
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(lst - sh);
+                uint32_t raw[kMaxStack / 4 + 1];
+#pragma unroll
+                for (int q = 0; q <= kMaxStack / 4; q++) raw[q] = (4u * q < sh + (uint32_t)S) ? wp[q] : 0u;
+#pragma unroll
+                for (int q = 0; q < kMaxStack / 4; q++) {
+                    if (4 * q < S) {
+                        const uint32_t x = __funnelshift_r(raw[q], raw[q + 1], 8u * sh);
+                        const uint32_t t4 = take >> (4 * q);
+                        w[q] = modulo ? map_request_word<true>(x, t4, mapM, (uint32_t)kNone & 0xFFu) : map_request_word<false>(x, t4, mapM, (uint32_t)kNone & 0xFFu);
+                    }
+                }
             }
-            sts_u8(aFatt + k, n);
+            sts_v4(aFatt + 16u * f, make_uint4(w[0], w[1], w[2], w[3]));
+        }
+        if (NM > 0 && !p.compact) {
+            // int32 encoding ([E][S][F]): one (firm, slot) pair per lane and pass
+            __syncwarp();
+            for (int k = lane; k < F * S; k += 32) {
+                const int i = k / F, f = k - i * F;
+                const size_t a = (size_t)e * S * F + (size_t)k;
+                if (p.ac.f_good_take[a] != 0) sts_u8(aFatt + 16u * f + (uint32_t)i, (uint32_t)mapM(p.ac.f_good_idx[a]));
+            }
         }
     }
     __syncwarp();
@@ -301,6 +328,9 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
 
     // ------------------------------ persons: windows of 32 visiting ranks -------------------
     const size_t row0 = (size_t)e * S * P;
+    // the visiting order is read one window ahead: the load of the next window's person number is in flight during this
+    // window's rounds, and its money / request lines are asked for (L1 prefetch) before the window's firm-money fold
+    int pid_next = (do_persons && lane < P) ? (p.compact ? (int)p.cz.perm_person[eP + lane] : p.ac.perm_person[eP + lane]) : 0;
     for (int base = 0; do_persons && base < P; base += 32) {
         // ---- (1) rows: death ordinals and initial rooms of the window
         bool lj = false, lm = false, rk = false;
@@ -365,7 +395,8 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         //      (slot i of the job list at aReqL + i, of the goods list at aReqL + 16 + i; "no request" = offer NJ / NM)
         const int r = base + lane;
         const bool active = r < P;
-        const int pid = active ? (p.compact ? (int)p.cz.perm_person[eP + r] : p.ac.perm_person[eP + r]) : 0;
+        const int pid = pid_next;
+        if (r + 32 < P) pid_next = p.compact ? (int)p.cz.perm_person[eP + r + 32] : p.ac.perm_person[eP + r + 32];
         const double money0 = active ? p.st.p_money[eP + pid] : 0.0;
         // keep: the slots that are worth evaluating — requested, on an existing offer that still has lots (a request on a
         // sold-out offer fails without any effect: firm.cpp:64, agent.cpp:124); jobs in bits 0..15, goods in 16..31
@@ -681,6 +712,12 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             if (mj) hire2 = lds_u8(aReqL + (uint32_t)(__ffs((int)mj) - 1));
         }
         uint32_t nbuy = 0;
+        const unsigned buyers = __ballot_sync(0xffffffffu, (okm >> 16) != 0u);
+        if (buyers != 0u) {
+            // aFlive (free until the firm phase) collects, per firm, the lanes that bought from it in this window
+            for (int f = lane; f < F; f += 32) sts_u32(aFlive + 4u * f, 0u);
+            __syncwarp();
+        }
         {
             // purchases: per good for update_kernel, and as an ordered list for the firms' money
             uint32_t nb[G];
@@ -688,10 +725,12 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             for (int g = 0; g < G; g++) nb[g] = 0;
             for (uint32_t m = okm >> 16; m != 0; m &= m - 1) {
                 const uint32_t n = lds_u8<kReqGoods>(aReqL + (uint32_t)(__ffs((int)m) - 1));
-                const uint32_t good = (lds_u32<kRecMeta>(aRecM + n * kRecBytes) >> 8) & 0xFFu;
+                const uint32_t meta = lds_u32<kRecMeta>(aRecM + n * kRecBytes);
+                const uint32_t good = (meta >> 8) & 0xFFu;
 #pragma unroll
                 for (int g = 0; g < G; g++) nb[g] += (good == (uint32_t)g);
                 sts_u8(aEv + (uint32_t)lane * kEvPerLane + 1u + nbuy, n);
+                reds_or_u32(aFlive + 4u * (meta & 0xFFu), 1u << lane);
                 nbuy++;
             }
             sts_u8(aEv + (uint32_t)lane * kEvPerLane, nbuy);
@@ -701,7 +740,6 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                 write_person_ok(p, e, pid, okm);
             }
         }
-        const unsigned buyers = __ballot_sync(0xffffffffu, nbuy != 0u);
         for (int R = lane; R < NT; R += 32) {
             const uint32_t rec = aRec + (uint32_t)R * kRecBytes;
             const uint32_t tot = lds_u32<kRecTot>(rec);
@@ -721,6 +759,13 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             }
             sts_u32<kRecTaken>(rec, lds_u32<kRecTaken>(rec) + n);
             sts_u32<kRecTot>(rec, n);
+        }
+        if (r + 32 < P) {
+            prefetch_l1(p.st.p_money + eP + pid_next);
+            if (p.compact) {
+                prefetch_l1(p.cz.p_job_idx + (eP + pid_next) * (size_t)S);
+                prefetch_l1(p.cz.p_good_idx + (eP + pid_next) * (size_t)S);
+            }
         }
         __syncwarp();
         // ---- firm money of the window, event by event in the visiting order
@@ -744,10 +789,10 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                     const unsigned y = __ballot_sync(0xffffffffu, hire1 == (uint32_t)R && hire2 == (uint32_t)R);
                     if (j == (uint32_t)R) { b1 = x; b2 = y; }
                 }
-                // ... then, buyer by buyer: the hires up to and including that lane (jobs precede purchases,
-                // person.cpp:26-29), then its purchases from this firm in request order
+                // ... then, for the lanes that bought from THIS firm, buyer by buyer: the hires up to and including that
+                // lane (jobs precede purchases, person.cpp:26-29), then its purchases from this firm in request order
                 uint32_t before = 0;
-                for (unsigned bm = buyers; bm != 0; bm &= bm - 1) {
+                for (unsigned bm = f < F ? lds_u32(aFlive + 4u * f) : 0u; bm != 0; bm &= bm - 1) {
                     const int l = __ffs((int)bm) - 1;
                     const uint32_t upto = 0xFFFFFFFFu >> (31 - l);
                     const uint32_t h = (uint32_t)(__popc(b1 & upto & ~before) + __popc(b2 & upto & ~before));

@@ -210,6 +210,8 @@ template <int OFF = 0> inline void sts_u16(uint32_t a, uint32_t v) { emu_st<uint
 template <int OFF = 0> inline void sts_u32(uint32_t a, uint32_t v) { emu_st<uint32_t>(a + OFF, v); }
 template <int OFF = 0> inline void sts_f64(uint32_t a, double v) { emu_st<double>(a + OFF, v); }
 template <int OFF = 0> inline void sts_v4(uint32_t a, uint4 v) { emu_st<uint4>(a + OFF, v); }
+inline void reds_or_u32(uint32_t a, uint32_t v) { emu_st<uint32_t>(a, emu_ld<uint32_t>(a) | v); }
+inline void prefetch_l1(const void*) {}
 }
 namespace emu { inline unsigned long long* stats() { static unsigned long long s[16] = {}; return s; } }
 #define FASTACE_STAT(which, n) (emu::stats()[which] += (n))
