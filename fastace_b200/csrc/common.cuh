@@ -18,12 +18,13 @@
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Publishing a finished unit of work to a kernel that runs concurrently (the completion queue between match_kernel
-// and update_kernel): writes -> fence -> release store; acquire load -> fence -> reads.
+// and update_kernel), with ONE fence on either side: writes -> fence.acq_rel.gpu -> strong (relaxed) store of the flag;
+// strong (relaxed) polling loads of the flag -> fence.acq_rel.gpu -> reads.
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void store_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t load_acquire_u32(const uint32_t* p) {
+__device__ __forceinline__ void store_relaxed_u32(uint32_t* p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t load_relaxed_u32(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint32_t ticket_add(uint32_t* p) { return atomicAdd(p, 1u); }
@@ -32,8 +33,8 @@ __device__ __forceinline__ void backoff_ns(unsigned ns) { __nanosleep(ns); }
 inline void grid_dependency_wait() {}
 inline void grid_launch_dependents() {}
 inline void fence_gpu() {}
-inline void store_release_u32(uint32_t* p, uint32_t v) { *p = v; }
-inline uint32_t load_acquire_u32(const uint32_t* p) { return *p; }
+inline void store_relaxed_u32(uint32_t* p, uint32_t v) { *p = v; }
+inline uint32_t load_relaxed_u32(const uint32_t* p) { return *p; }
 inline uint32_t ticket_add(uint32_t* p) { return (*p)++; }
 inline void backoff_ns(unsigned) {}
 #endif

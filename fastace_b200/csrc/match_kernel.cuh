@@ -958,10 +958,11 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         }
     }
     if (mp.done_list) {
-        // this economy's matching results are complete: hand it to update_kernel
+        // this economy's matching results are complete: hand it to update_kernel (every lane fences its own writes,
+        // then lane 0 publishes)
         fence_gpu();
         __syncwarp();
-        if (lane == 0) store_release_u32(mp.done_list + (ticket_add(mp.done_count) - mp.ticket_base), (mp.done_tag << kQueueTagShift) | (uint32_t)e);
+        if (lane == 0) store_relaxed_u32(mp.done_list + (ticket_add(mp.done_count) - mp.ticket_base), (mp.done_tag << kQueueTagShift) | (uint32_t)e);
     }
 #ifdef FASTACE_CTA_TIMING
     if (lane == 0 && e < 65536) {

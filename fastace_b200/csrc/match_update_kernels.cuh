@@ -202,11 +202,12 @@ __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateP
         // has completed before any warp of match_kernel took a ticket, so a matching tag is this step's entry
         uint32_t v = 0, polls = 0;
         while (work) {
-            v = load_acquire_u32(up.done_list + slot);
+            v = load_relaxed_u32(up.done_list + slot);
             if ((v >> kQueueTagShift) == up.done_tag) break;
             if (++polls >= kQueuePollCap) { up.dev_err[kDevErrQueue] = 1u; work = false; }
             else backoff_ns(kQueuePollNs);
         }
+        fence_gpu();                          // acquire: the economy's matching results are visible from here on
         e = (int)(v & kQueueEconMask);
         firms_here = firms_here && work;      // warp-uniform: the lanes of a firm warp share one slot
         pid_end = (work && !firms_here && idx >= firm_blocks) ? pid + 1 : pid;

@@ -10,7 +10,8 @@ import os
 from . import _abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfastace_b200.so")
+# FASTACE_B200_LIB: load a variant build (profiling defines, other launch bounds) instead of the product library
+LIB_PATH = os.environ.get("FASTACE_B200_LIB") or os.path.join(HERE, "libfastace_b200.so")
 
 # every symbol include/fastace_b200.h declares
 EXPORTED_SYMBOLS = [
