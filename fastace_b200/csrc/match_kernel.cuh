@@ -941,6 +941,9 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         __syncwarp();
     }
     // ------------------------------ firms: results to HBM -----------------------------------
+    // the queue ticket is taken now: its round trip overlaps the write-back (only the flag store must follow the fence)
+    uint32_t ticket = 0;
+    if (mp.done_list && lane == 0) ticket = ticket_add(mp.done_count);
     if (do_firms && p.out.old_m_left) for (int n = lane; n < NM; n += 32) p.out.old_m_left[eCap + n] = lds_u32<kRecD>(aRecM + (uint32_t)n * kRecBytes);
     if (do_firms && p.out.old_m_taken) for (int n = lane; n < NM; n += 32) p.out.old_m_taken[eCap + n] = lds_u32<kRecTaken>(aRecM + (uint32_t)n * kRecBytes);
     for (int f = lane; f < F; f += 32) {
@@ -962,7 +965,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         // then lane 0 publishes)
         fence_gpu();
         __syncwarp();
-        if (lane == 0) store_relaxed_u32(mp.done_list + (ticket_add(mp.done_count) - mp.ticket_base), (mp.done_tag << kQueueTagShift) | (uint32_t)e);
+        if (lane == 0) store_relaxed_u32(mp.done_list + (ticket - mp.ticket_base), (mp.done_tag << kQueueTagShift) | (uint32_t)e);
     }
 #ifdef FASTACE_CTA_TIMING
     if (lane == 0 && e < 65536) {
