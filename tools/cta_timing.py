@@ -22,7 +22,7 @@ import torch
 for t in range(STEPS):
     act = scenario.synthetic_actions(DIMS, seed=99, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
     dact = env.alloc_actions(act)
-    dout = env.alloc_outputs(names=None)
+    dout = env.alloc_outputs()
     torch.cuda.synchronize()
     env.time_step(dact, dout, flags=_abi.IDX_MODULO)
     torch.cuda.synchronize()
