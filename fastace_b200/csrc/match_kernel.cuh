@@ -652,8 +652,8 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                             if (lane == src) d = db;
                         }
                         if (R < NJ && d != (int)lds_u32<kRecD>(rec)) {
-                            // the offer dies earlier / later than assumed: its rooms follow the new ordinal
-                            changed = true;
+                            // the offer dies earlier / later than assumed: its rooms follow the new ordinal (the re-scan
+                            // below tells whether that changes anybody's outcome)
                             needs = true;
                             sts_u32<kRecD>(rec, (uint32_t)d);
                         }

@@ -348,7 +348,8 @@ FIRM_SNAPSHOT_KEYS = ("f_money", "f_labor", "f_inv")      # what the person phas
 CONSUME_SNAPSHOT = {"c_money": "p_money", "c_labor": "p_labor", "c_inv": "p_inv"}   # the consumption decision's inputs
 
 
-def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", sides=("persons", "consume", "firms")):
+def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", sides=("persons", "consume", "firms"),
+             enc_cache=None):
     """Forward of the 11 nets for every agent of every economy + sampling with the given draws.
     Differentiable when autograd is enabled (the trainer re-evaluates recorded steps with it).
 
@@ -361,6 +362,9 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
     recorded phase-wise step holds those later inputs (c_money / c_labor / c_inv, and the f_* fields), so
     re-evaluating it with all sides reproduces every decision.
 
+    enc_cache: a dict shared by the phase-wise calls of ONE step (no autograd): the offer encodings are computed by the
+    first call that needs them and reused by the later ones — the books do not change before the firms post.
+
     Returns (decoded, info): decoded = agent-major action tensors, info = log-probabilities [E,agents]
     and state values."""
     E, P, F, G = snapshot_dims(snap)
@@ -370,15 +374,23 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
     ctx = torch.autocast("cuda", dtype=autocast_dtype) if autocast_dtype is not None else _NullCtx()
     with ctx:
         # --- market snapshot + encoder forward (update_encodedOffers / JobOffers, :236-275)
+        do_p, do_c, do_f = "persons" in sides, "consume" in sides, "firms" in sides
         nM, nJ = st["m_count"].long(), st["j_count"].long()
-        good = st["m_good"].long().clamp(0, G - 1)
-        qty = torch.nn.functional.one_hot(good, G).to(f32)                       # quantities = e_g * 1.0
-        feats = torch.cat([qty, st["m_price"].to(f32).unsqueeze(-1)], dim=-1)    # [E, capM, G+1]
-        encM = nets.offerEncoder(feats)                                          # [E, capM, enc]
-        jfeat = torch.stack([torch.full_like(st["j_wage"], 0.5), st["j_wage"]], dim=-1).to(f32)
-        encJ = nets.jobOfferEncoder(jfeat)                                       # [E, F, enc]
         validM = (nM > 0).view(E, 1, 1)
         validJ = (nJ > 0).view(E, 1, 1)
+        encM = encJ = None
+        if do_p or do_f:                                                             # the consumption net reads no offers
+            if enc_cache is not None and "encM" in enc_cache:
+                encM, encJ = enc_cache["encM"], enc_cache["encJ"]
+            else:
+                good = st["m_good"].long().clamp(0, G - 1)
+                qty = torch.nn.functional.one_hot(good, G).to(f32)                   # quantities = e_g * 1.0
+                feats = torch.cat([qty, st["m_price"].to(f32).unsqueeze(-1)], dim=-1)    # [E, capM, G+1]
+                encM = nets.offerEncoder(feats)                                      # [E, capM, enc]
+                jfeat = torch.stack([torch.full_like(st["j_wage"], 0.5), st["j_wage"]], dim=-1).to(f32)
+                encJ = nets.jobOfferEncoder(jfeat)                                   # [E, F, enc]
+                if enc_cache is not None:
+                    enc_cache["encM"], enc_cache["encJ"] = encM, encJ
 
         def gather(enc, idx, valid):    # the agents' stacks of encodings, kept as (table, indices): see IndexedEncodings
             return IndexedEncodings(enc, idx, valid, flat=True)
@@ -386,7 +398,6 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
         # agents as rows of 2-D matrices: nn.Linear then runs as ONE addmm with the bias in the GEMM epilogue
         rows = lambda x: x.reshape(-1, x.shape[-1])
 
-        do_p, do_c, do_f = "persons" in sides, "consume" in sides, "firms" in sides
         decoded, info, heads = {}, {}, {}
         if do_p or do_c:
             # --- persons
@@ -399,9 +410,9 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
             else:
                 labor0 = torch.zeros_like(money)                                  # laborSupplied was just reset (person.cpp:24)
             inv = st["p_inv"].permute(0, 2, 1).to(f32)
-            eM, eJ = gather(encM, pidxM, validM), gather(encJ, pidxJ, validJ)
             util, money, labor0, inv = rows(util), rows(money), rows(labor0), rows(inv)
             if do_p:
+                eM, eJ = gather(encM, pidxM, validM), gather(encJ, pidxJ, validJ)
                 heads["p_value"] = nets.valueNet(eM, eJ, util, money, labor0, inv).reshape(E, P)
                 heads["p_job_p"] = nets.laborSearchNet(eJ, util, money, labor0, inv).reshape(E, P, S)
                 heads["p_good_p"] = nets.purchaseNet(eM, util, money, labor0, inv).reshape(E, P, S)
@@ -516,11 +527,11 @@ class BatchedPolicy:
         for key, value in decoded.items():
             self.actions[key].copy_(value if value.dim() == 2 else value.permute(0, 2, 1))   # agent-major -> [E][slot|good][agent]
 
-    def _evaluate(self, snap, draws, sides):
+    def _evaluate(self, snap, draws, sides, enc_cache=None):
         global _FUSED
         _FUSED = self.fused
         try:
-            return evaluate(self.nets, snap, draws, self.autocast_dtype, sides=sides)
+            return evaluate(self.nets, snap, draws, self.autocast_dtype, sides=sides, enc_cache=enc_cache)
         finally:
             _FUSED = False
 
@@ -547,7 +558,8 @@ class BatchedPolicy:
         a["perm_firm"].copy_(torch.as_tensor(perms[1]))
         snap = snapshot(self.state) if record is not None else self.state
         draws = draw(snap, self.S, self.gen)          # the books (and so the index ranges) do not change before the firms post
-        decoded, info = self._evaluate(snap, draws, ("persons",))
+        enc_cache = {}                                # offer encodings of the step: computed once, used by persons and firms
+        decoded, info = self._evaluate(snap, draws, ("persons",), enc_cache)
         self._write(decoded)
         self.env.time_step(self.packed, phase_out(("p_job_ok", "p_good_ok", "old_j_left", "old_j_taken")),
                            flags=flags | _abi.STEP_PERSONS_TRADE)
@@ -565,7 +577,7 @@ class BatchedPolicy:
             for k in FIRM_SNAPSHOT_KEYS:              # the firms' inputs as they stand after the person phase
                 snap[k] = self.state[k].clone()
             record.append((snap, draws))
-        decoded_f, info_f = self._evaluate(snap, draws, ("firms",))
+        decoded_f, info_f = self._evaluate(snap, draws, ("firms",), enc_cache)
         self._write(decoded_f)
         self.env.time_step(self.packed, phase_out(FIRM_OUT), flags=flags | _abi.STEP_FIRMS)
         info.update(info_f)

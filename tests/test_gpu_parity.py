@@ -351,3 +351,29 @@ def test_packed_host_encoding_matches(oracle, own_orders):
         H.compare_outputs(gout, oout, dims, before)
         H.compare_states(env.get_state(), ost, dims)
     env.close()
+
+
+def test_completion_queue_equals_whole_grid_wait(native_lib, monkeypatch):
+    """update_kernel fed by match_kernel's completion queue (the default for full steps) and update_kernel waiting
+    for the whole matching grid (FASTACE_NO_QUEUE=1, read when the env is created) give bit-identical states, also
+    when the economy count is not a multiple of the queue's group size and over many back-to-back launches."""
+    from fastace_b200.env import BatchedEconomy
+    dims = (333, 100, 10, 2, 10)
+    state0 = scenario.custom_initial_state(dims, 77)[0]
+    runs = []
+    for no_queue in ("0", "1"):
+        monkeypatch.setenv("FASTACE_NO_QUEUE", no_queue)
+        env = BatchedEconomy(dims)
+        env.set_state(state0)
+        orders = scenario.OrderStream(dims, 5)
+        dout = env.alloc_outputs(names=None)
+        for t in range(30):
+            act = scenario.synthetic_actions(dims, seed=11, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
+            env.time_step(env.alloc_actions(act), dout, flags=_abi.IDX_MODULO)
+        runs.append((env.get_state(), {k: v.cpu().numpy().copy() for k, v in dout.items()}))
+        env.close()
+    (sa, oa), (sb, ob) = runs
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k], equal_nan=True), k
+    for k in oa:
+        assert np.array_equal(oa[k].view(np.uint8), ob[k].view(np.uint8)), k
