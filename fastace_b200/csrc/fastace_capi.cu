@@ -20,6 +20,7 @@
 #include "packed_kernel.cuh"
 #include "large_economy.cuh"
 #include "mlp_stack.cuh"
+#include "policy_kernels.cuh"
 #include "layer_kernels.cuh"
 
 namespace fastace {
@@ -1205,6 +1206,38 @@ int fastace_layer_backward(const float* dy, const float* t, float* dz, int64_t n
     if (n == 0) return FASTACE_OK;
     const unsigned blocks = (unsigned)((n / 4 + 1 + 255) / 256);
     layer_backward_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(dy, t, dz, (long long)n);
+    FASTACE_CUDA_CHECK(cudaGetLastError());
+    return FASTACE_OK;
+}
+
+int fastace_policy_bernoulli(const float* probas, const float* uniforms, const int64_t* idx, const uint8_t* valid,
+                             int num_econ, int agents, int stack, int invalid_nan,
+                             int32_t* out_idx, uint8_t* out_take, float* out_logp, void* cuda_stream) {
+    if (!probas || !uniforms || !idx || !valid || !out_idx || !out_take || !out_logp || num_econ < 0 || agents < 0 || stack < 0) {
+        set_error("bad argument"); return FASTACE_ERR_INVALID;
+    }
+    const long long n = (long long)num_econ * agents;
+    if (n == 0) return FASTACE_OK;
+    BernoulliParams q = {probas, uniforms, idx, valid, num_econ, agents, stack, invalid_nan, out_idx, out_take, out_logp};
+    policy_bernoulli_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(q);
+    FASTACE_CUDA_CHECK(cudaGetLastError());
+    return FASTACE_OK;
+}
+
+int fastace_policy_normal(const float* params, int stride, int offset, const float* noise,
+                          int num_econ, int agents, int components, int kind, int accumulate,
+                          float* out_x, float* out_logp, void* cuda_stream) {
+    if (!params || !noise || !out_x || !out_logp || num_econ < 0 || agents < 0 || components < 1 || stride < 2 || offset < 0 ||
+        offset + 2 > stride || kind < 0 || kind > 1) {
+        set_error("bad argument"); return FASTACE_ERR_INVALID;
+    }
+    const long long n = (long long)num_econ * agents;
+    if (n == 0) return FASTACE_OK;
+    NormalParams q;
+    q.params = params; q.noise = noise; q.stride = stride; q.offset = offset; q.E = num_econ; q.A = agents; q.C = components;
+    q.kind = kind; q.accumulate = accumulate; q.out_x = out_x; q.out_logp = out_logp;
+    q.log_sqrt2pi_scale = (float)(2.0 / (1.1283791670955126 * 0.70710678118654752));   // neuralConstants.h:10
+    policy_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(q);
     FASTACE_CUDA_CHECK(cudaGetLastError());
     return FASTACE_OK;
 }

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "fastace_env_create", "fastace_env_destroy", "fastace_env_dims", "fastace_env_time", "fastace_env_set_function_kinds",
     "fastace_env_set_state", "fastace_env_get_state", "fastace_env_device_state",
     "fastace_env_step_device", "fastace_env_step_host", "fastace_env_step_device_compact",
-    "fastace_env_step_host_compact", "fastace_env_step_host_packed", "fastace_packed_layout", "fastace_env_sync", "fastace_env_launch_count", "fastace_env_kernel_times", "fastace_env_large_stats", "fastace_mlp_stack_layout", "fastace_mlp_residual_tanh_stack", "fastace_mlp_forward", "fastace_layer_forward", "fastace_layer_backward",
+    "fastace_env_step_host_compact", "fastace_env_step_host_packed", "fastace_packed_layout", "fastace_env_sync", "fastace_env_launch_count", "fastace_env_kernel_times", "fastace_env_large_stats", "fastace_mlp_stack_layout", "fastace_mlp_residual_tanh_stack", "fastace_mlp_forward", "fastace_layer_forward", "fastace_layer_backward", "fastace_policy_bernoulli", "fastace_policy_normal",
     "create_scenario_params", "create_training_params", "run", "train",
     "fastace_scenario_custom_init", "fastace_shuffle_orders", "fastace_env_shuffle_orders", "fastace_env_market_stats",
 ]
@@ -88,6 +88,10 @@ def load():
     L.fastace_layer_forward.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_int, vp]
     L.fastace_layer_backward.restype = C.c_int
     L.fastace_layer_backward.argtypes = [vp, vp, vp, C.c_int64, vp]
+    L.fastace_policy_bernoulli.restype = C.c_int
+    L.fastace_policy_bernoulli.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.fastace_policy_normal.restype = C.c_int
+    L.fastace_policy_normal.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.fastace_env_large_stats.restype = C.c_int
     L.fastace_env_large_stats.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.fastace_env_kernel_times.restype = C.c_int

@@ -349,7 +349,7 @@ CONSUME_SNAPSHOT = {"c_money": "p_money", "c_labor": "p_labor", "c_inv": "p_inv"
 
 
 def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", sides=("persons", "consume", "firms"),
-             enc_cache=None):
+             enc_cache=None, sink=None):
     """Forward of the 11 nets for every agent of every economy + sampling with the given draws.
     Differentiable when autograd is enabled (the trainer re-evaluates recorded steps with it).
 
@@ -364,6 +364,10 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
 
     enc_cache: a dict shared by the phase-wise calls of ONE step (no autograd): the offer encodings are computed by the
     first call that needs them and reused by the later ones — the books do not change before the firms post.
+
+    sink: the env's action tensors (fastace_actions_t layout).  Given (no autograd, CUDA), the sampling rules run as the
+    kernels of csrc/policy_kernels.cuh, which write the decisions straight into `sink`; `decoded` then holds nothing
+    for those keys.
 
     Returns (decoded, info): decoded = agent-major action tensors, info = log-probabilities [E,agents]
     and state values."""
@@ -440,6 +444,25 @@ def evaluate(nets, snap, draws, autocast_dtype=None, sample_grad="reference", si
     # --- sampling (fp32) and the empty-market conventions: purchase log-prob NaN = "no decision", job search 0.0
     #     (decisionNetHandler.cpp:398-403, 476-480)
     detach = sample_grad != "reference"
+    if sink is not None and not torch.is_grad_enabled() and st["p_money"].is_cuda:
+        from . import fused_sampling as fs
+        if do_p:
+            lp_job = fs.bernoulli(heads["p_job_p"], draws["u_job"], draws["pidxJ"], validJ, False, sink["p_job_idx"], sink["p_job_take"])
+            lp_good = fs.bernoulli(heads["p_good_p"], draws["u_good"], draws["pidxM"], validM, True, sink["p_good_idx"], sink["p_good_take"])
+            info.update({"value_person": heads["p_value"].float(), "logp_purchase": lp_good, "logp_laborSearch": lp_job})
+        if do_c:
+            info["logp_consumption"] = fs.normal(heads["cons"], 0, draws["n_cons"], "logit", sink["p_consume"])
+        if do_f:
+            lp_fgood = fs.bernoulli(heads["f_good_p"], draws["u_fgood"], draws["fidxM"], validM, True, sink["f_good_idx"], sink["f_good_take"])
+            lp_offer = fs.normal(heads["offer"], 0, draws["n_amt"], "logit", sink["f_offer_amt"])
+            fs.normal(heads["offer"], 2, draws["n_price"], "log", sink["f_offer_price"], logp=lp_offer)
+            lp_jobo = fs.normal(heads["job"], 0, draws["n_lab"], "log", sink["f_job_labor"])
+            fs.normal(heads["job"], 2, draws["n_wage"], "log", sink["f_job_wage"], logp=lp_jobo)
+            info.update({"value_firm": heads["f_value"].float(), "logp_firmPurchase": lp_fgood,
+                         "logp_production": fs.normal(heads["prod"], 0, draws["n_prod"], "logit", sink["f_prod"]),
+                         "logp_offer": lp_offer, "logp_jobOffer": lp_jobo})
+        return decoded, info
+    detach = sample_grad != "reference"
     if do_p:
         p_job_take, lp_job = sample_bernoulli(heads["p_job_p"].float(), draws["u_job"])
         p_good_take, lp_good = sample_bernoulli(heads["p_good_p"].float(), draws["u_good"])
@@ -511,7 +534,7 @@ class BatchedPolicy:
         draws = draw(snap, self.S, self.gen)
         _FUSED = self.fused
         try:
-            decoded, info = evaluate(self.nets, snap, draws, self.autocast_dtype)
+            decoded, info = evaluate(self.nets, snap, draws, self.autocast_dtype, sink=self.actions if self.fused else None)
         finally:
             _FUSED = False
         if record is not None:
@@ -531,7 +554,8 @@ class BatchedPolicy:
         global _FUSED
         _FUSED = self.fused
         try:
-            return evaluate(self.nets, snap, draws, self.autocast_dtype, sides=sides, enc_cache=enc_cache)
+            return evaluate(self.nets, snap, draws, self.autocast_dtype, sides=sides, enc_cache=enc_cache,
+                            sink=self.actions if self.fused else None)
         finally:
             _FUSED = False
 

@@ -407,6 +407,22 @@ int fastace_layer_forward(const float* z, const float* bias, const float* x, flo
                           void* cuda_stream);
 int fastace_layer_backward(const float* dy, const float* t, float* dz, int64_t n, void* cuda_stream);
 
+/* Sampling rules of the decision nets for all agents at once (DEVICE pointers, fp32; rollout-only fast path — the
+ * reference's per-agent versions: src/neural/decisionNetHandler.cpp:27-46 sample_normal / sample_logitNormal /
+ * sample_logNormal, :368-387 the Bernoulli takes).  Inputs are agent-major rows ([E*A][...]), outputs are written in the
+ * env's action layout.
+ * bernoulli: take = u < p, log pi = sum_s log p or log(1-p); out_take[E][S][A] = take & valid[e], out_idx[E][S][A] =
+ *   idx, out_logp[E][A] (an agent of an economy whose book is empty: NaN if invalid_nan else 0.0, :398-403, 476-480).
+ * normal: per component c the pair (mu, log sigma) sits at params[(row*C + c)*stride + offset]; x = noise*sigma + mu,
+ *   out_x[E][C][A] = sigmoid(x) (kind 0) or exp(x) (kind 1), out_logp[E][A] (+)= sum_c -0.5((x-mu)/sigma)^2 -
+ *   log(sigma*sqrt(2 pi)) (no Jacobian term, as in the reference). */
+int fastace_policy_bernoulli(const float* probas, const float* uniforms, const int64_t* idx, const uint8_t* valid,
+                             int num_econ, int agents, int stack, int invalid_nan,
+                             int32_t* out_idx, uint8_t* out_take, float* out_logp, void* cuda_stream);
+int fastace_policy_normal(const float* params, int stride, int offset, const float* noise,
+                          int num_econ, int agents, int components, int kind, int accumulate,
+                          float* out_x, float* out_logp, void* cuda_stream);
+
 /* ---- legacy entry points of libpybindings.so (src/pybindings.h:8-28) ------------------ */
 /* Byte-identical layouts of neural::CustomScenarioParams (344 B) and
  * neural::TrainingParams (136 B), src/neural/neuralScenarios.h:49-186, py/main.py:12-85. */
