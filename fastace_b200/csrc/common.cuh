@@ -83,7 +83,7 @@ __device__ __forceinline__ void reds_or_u32(uint32_t a, uint32_t v) { asm volati
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #endif
 
-enum { kStatWindows, kStatRounds, kStatRescans, kStatRiskyWalks, kStatSalesWindows, kStatDeadExits, kStatFirmSerial, kStatRoundsW0, kStatRoundsW1, kStatRoundsW2, kStatRoundsW3, kStatRescansW0, kStatRiskyCoop, kStatCount };
+enum { kStatWindows, kStatRounds, kStatRescans, kStatRiskyWalks, kStatSalesWindows, kStatDeadExits, kStatFirmSerial, kStatRoundsW0, kStatRoundsW1, kStatRoundsW2, kStatRoundsW3, kStatRescansW0, kStatRiskyCoop, kStatRiskyKept, kStatCount };
 
 struct StepParams {
     int E, P, F, S;

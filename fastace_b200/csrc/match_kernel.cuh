@@ -63,6 +63,7 @@ constexpr int kRecD = 16;       // i32     death ordinal of the window; firm pha
 constexpr int kRecTot = 20;     // i32     eligible requests of the window; after the commit: successes
 constexpr int kRecMeta = 24;    // u32     owner | good << 8
 constexpr int kRecScanned = 28; // u8      the rooms of this window have been re-scanned (they follow `prev`)
+constexpr int kRecEval = 29;    // u8      job rows: the death ordinal has been derived from the firm's money in this window
 constexpr int kRecSafe = 30;    // u16     job rows: hires of this window the firm can certainly pay (see the prologue)
 constexpr int kRoomMax = 127;   // rooms are clamped here (a lane has at most FASTACE_MAX_STACK requests)
 constexpr int kRoundCap = 200;  // > 2 * 32 + 2, the proven bound: reaching it raises kDevErrRounds
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             }
             const uint32_t di = min(d, 0x7FFFFFFFu);
             sts_u32<kRecD>(rec, di);
-            sts_u8<kRecScanned>(rec, 0u);
+            sts_u16<kRecScanned>(rec, 0u);                               // kRecScanned and kRecEval
             const uint32_t rm = min(di, (uint32_t)kRoomMax) * 0x01010101u;
             const uint32_t mat = aMat + (uint32_t)R * kMatBytes;
             sts_v4<kMatCnt>(mat, make_uint4(0u, 0u, 0u, 0u));
@@ -456,6 +457,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         double money = money0;
         int nh = 0;
         uint32_t okm = 0;      // successes: job slots in bits 0..15, goods slots in bits 16..31
+        uint32_t last_goods = 0xFFFFFFFFu;   // the goods successes of the previous round
         const uint32_t aCellJ = keep_u32(aMat + (uint32_t)lane), aCellM = keep_u32(aMatM + (uint32_t)lane);
         if (lane == 0) FASTACE_STAT(kStatWindows, 1);
         for (int round = 0;; round++) {
@@ -508,6 +510,10 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
 
             // ---- rows: demand of the window; over-subscribed rows whose counts moved get their rooms re-scanned
             bool changed = false;
+            // did any lane's purchases move since the last round?  (a death ordinal derived from the firm's money stands
+            // while the applications to the row and everybody's purchases do)
+            const bool goods_moved = risk_possible && __any_sync(0xffffffffu, (okm >> 16) != last_goods);
+            last_goods = okm >> 16;
             for (int cb = 0; cb < NT; cb += 32) {
                 const int R = cb + lane;
                 bool needs = false;
@@ -543,6 +549,15 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                         tot = (int)lds_u32<kRecTot>(rec);
                         // the applicants that could be hired exceed what the firm can certainly pay
                         risky = tot > 0 && left > 0 && min(min((int)min(left, 0x7FFFFFFFu), tot), kMaxHiresPerWindow) >= (int)lds_u16<kRecSafe>(rec);
+                        if (risky && !goods_moved && lds_u16<kRecScanned>(rec) == 0x0101u) {
+                            // evaluated before in this window and re-scanned since: if `prev` (the applications the
+                            // rooms were computed for) is still what the lanes apply, the ordinal in the record stands
+                            const uint32_t mat = aMat + (uint32_t)R * kMatBytes;
+                            const uint4 a = lds_v4<kMatCnt>(mat), b = lds_v4<kMatCnt + 16>(mat);
+                            const uint4 c = lds_v4<kMatPrev>(mat), dd = lds_v4<kMatPrev + 16>(mat);
+                            risky = ((a.x ^ c.x) | (a.y ^ c.y) | (a.z ^ c.z) | (a.w ^ c.w) | (b.x ^ dd.x) | (b.y ^ dd.y) | (b.z ^ dd.z) | (b.w ^ dd.w)) != 0u;
+                            if (!risky) FASTACE_STAT(kStatRiskyKept, 1);
+                        }
                         if (risky) {
                             f = (int)(lds_u32<kRecMeta>(rec) & 0xFFu);
                             w = lds_f64<kRecValue>(rec);
@@ -646,12 +661,28 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                                     }
                                 }
                                 __syncwarp();
+                                db = __shfl_sync(0xffffffffu, db, src);
                             } else if (lane == src) {
                                 FASTACE_STAT(kStatRiskyCoop, 1);
                             }
-                            if (lane == src) d = db;
+                            // every lane holds the applications before it (ac): the row's rooms follow the ordinal right
+                            // here, and `prev` records what they were computed for — no separate re-scan of this row
+                            {
+                                const int rmn = max(0, min(kRoomMax, db - ac));
+                                const int old = (int)lds_u8<kMatRoom>(matb + (uint32_t)lane);
+                                changed |= min(c, rmn) != min(c, old);
+                                sts_u8<kMatRoom>(matb + (uint32_t)lane, (uint32_t)rmn);
+                                sts_u8<kMatPrev>(matb + (uint32_t)lane, (uint32_t)c);
+                            }
+                            if (lane == src) {
+                                d = db;
+                                needs = false;
+                                sts_u32<kRecD>(rec, (uint32_t)db);
+                                sts_u8<kRecScanned>(rec, 1u);
+                            }
                         }
-                        if (R < NJ && d != (int)lds_u32<kRecD>(rec)) {
+                        if (risky) sts_u8<kRecEval>(rec, 1u);
+                        if (risky && d != (int)lds_u32<kRecD>(rec)) {
                             // the offer dies earlier / later than assumed: its rooms follow the new ordinal (the re-scan
                             // below tells whether that changes anybody's outcome)
                             needs = true;

@@ -42,7 +42,7 @@ class EmuKernels:
             raise RuntimeError(f"emulated kernels raised error words {rc}")
 
     STAT_NAMES = ("windows", "rounds", "rescans", "risky_walks", "sales_windows", "dead_exits", "firm_serial",
-                  "rounds_w0", "rounds_w1", "rounds_w2", "rounds_w3", "rescans_w0", "risky_coop")
+                  "rounds_w0", "rounds_w1", "rounds_w2", "rounds_w3", "rescans_w0", "risky_coop", "risky_kept")
 
     def stats(self):
         """event counters of the kernels since the last call"""
