@@ -121,9 +121,11 @@ __device__ __forceinline__ int x86_double_to_int(double x) {
 struct IndexMap {
     uint32_t magic, count, k16;   // k16 = 65536 mod count
     bool modulo;
-    __device__ __forceinline__ IndexMap(int cnt, uint32_t flags)
-        : magic(cnt > 0 ? 0xFFFFFFFFu / (uint32_t)cnt + 1u : 0u), count(cnt > 0 ? (uint32_t)cnt : 0u),
-          k16(cnt > 0 ? 65536u % (uint32_t)cnt : 0u), modulo((flags & FASTACE_IDX_MODULO) != 0) {}
+    __device__ __forceinline__ IndexMap(int cnt, uint32_t flags) : IndexMap(cnt, (flags & FASTACE_IDX_MODULO) != 0) {}
+    // (the reciprocal and the remainder are only computed for the modulo mapping)
+    __device__ __forceinline__ IndexMap(int cnt, bool mod)
+        : magic(mod && cnt > 0 ? 0xFFFFFFFFu / (uint32_t)cnt + 1u : 0u), count(cnt > 0 ? (uint32_t)cnt : 0u),
+          k16(mod && cnt > 0 ? 65536u % (uint32_t)cnt : 0u), modulo(mod) {}
     __device__ __forceinline__ uint32_t mod24(uint32_t x) const { return __umulhi(magic * x, count); }
     // precondition: count > 0 (callers skip mapping for an empty book)
     __device__ __forceinline__ int operator()(int raw) const {

@@ -276,9 +276,13 @@ static cudaError_t launch_dependent(const void* fn, dim3 grid, dim3 block, size_
 typedef void (*serial_fn)(const StepParams);
 typedef void (*match_fn)(const MatchParams);
 typedef void (*update_fn)(const UpdateParams);
-struct KernelSet { serial_fn serial; match_fn match; update_fn update; };
+// match: the generic kernel; match_compact[modulo]: specialised for the compact encoding without per-person success flags
+struct KernelSet { serial_fn serial; match_fn match; update_fn update; match_fn match_compact[2]; };
 template <int G>
-static KernelSet kernels_of() { return {step_kernel<G>, match_kernel<G>, update_kernel<G>}; }
+static KernelSet kernels_of() {
+    return {step_kernel<G>, match_kernel<G, kModeGeneric>, update_kernel<G>,
+            {match_kernel<G, kModeCompact>, match_kernel<G, kModeCompact | kModeModulo>}};
+}
 static KernelSet kernels_for_goods(int G) {
     switch (G) {
         case 1: return kernels_of<1>();
@@ -289,7 +293,7 @@ static KernelSet kernels_for_goods(int G) {
         case 6: return kernels_of<6>();
         case 7: return kernels_of<7>();
         case 8: return kernels_of<8>();
-        default: return {nullptr, nullptr, nullptr};
+        default: return {nullptr, nullptr, nullptr, {nullptr, nullptr}};
     }
 }
 
@@ -343,6 +347,8 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
             FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.serial, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         if (ML.total > 48 * 1024) {
             FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
+            for (int m = 0; m < 2; m++)
+                FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match_compact[m], cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
         }
     }
 
@@ -796,7 +802,10 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         mp.done_tag = (env->queue_launches % 255u) + 1u;
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[0], stream));
         if (!ph_c) {   // a consume-only call has no matching to do
-            FASTACE_CUDA_CHECK(launch_dependent((const void*)ks.match, dim3((unsigned)sp.E), dim3(32), env->match_smem_bytes, stream, &mp));
+            // the specialised kernel when the call is what it was compiled for (match_kernel.cuh: MODE)
+            const bool special = dcz != nullptr && !dout->p_job_ok && !dout->p_good_ok;
+            const match_fn fn = special ? ks.match_compact[(flags & FASTACE_IDX_MODULO) ? 1 : 0] : ks.match;
+            FASTACE_CUDA_CHECK(launch_dependent((const void*)fn, dim3((unsigned)sp.E), dim3(32), env->match_smem_bytes, stream, &mp));
             FASTACE_CUDA_CHECK(cudaGetLastError());
             env->launches += 1;
         }

@@ -190,13 +190,23 @@ __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t
 
 static_assert(kMaxStack == 16, "request lists are staged as four words");
 
-template <int G>
+// MODE specialises the kernel for an input encoding, so that the code of the other encodings is not interleaved with
+// the hot path (a quarter of the generic kernel's instructions belong to paths a given launch never takes, and the
+// instruction fetch stall is the one issue stall that is not inherent to the algorithm):
+//   kModeGeneric  everything decided at run time (any encoding, any output set)
+//   kModeCompact  compact encoding, per-person success flags not requested; bit kModeModulo: FASTACE_IDX_MODULO
+constexpr int kModeGeneric = 0, kModeCompact = 1, kModeModulo = 2;
+
+template <int G, int MODE = kModeGeneric>
 __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     FASTACE_DYN_SMEM(smem);
 #ifdef FASTACE_CTA_TIMING
     const unsigned long long cta_t0 = global_ns();
 #endif
     const StepParams& p = mp.sp;
+    const bool compact = (MODE & kModeCompact) ? true : p.compact != 0;
+    const bool modulo = (MODE & kModeCompact) ? (MODE & kModeModulo) != 0 : (p.flags & FASTACE_IDX_MODULO) != 0;
+    const bool person_flags = (MODE & kModeCompact) ? false : (p.out.p_job_ok != nullptr || p.out.p_good_ok != nullptr);
     const int e = blockIdx.x;
     const int lane = threadIdx.x;
     const int P = p.P, F = p.F, S = p.S;
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     // them is the economy as it stands when the last person has acted and no firm has (economy.cpp:118-123)
     const bool do_persons = !(p.flags & FASTACE_STEP_FIRMS);
     const bool do_firms = !(p.flags & (FASTACE_STEP_PERSONS | FASTACE_STEP_PERSONS_TRADE));
-    if (do_persons && p.compact) {
+    if (do_persons && compact) {
         // the economy's person-side inputs are five contiguous slabs: ask L2 for them now, use them window by window
         if (lane == 0) prefetch_slab_l2(p.cz.p_job_idx + (size_t)e * P * S, (size_t)P * S);
         if (lane == 1) prefetch_slab_l2(p.cz.p_good_idx + (size_t)e * P * S, (size_t)P * S);
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     const uint32_t aMatM = keep_u32(aMat + (uint32_t)(NJ + 1) * kMatBytes);
 
     // ------------------------------ stage: books and firms ---------------------------------
-    const IndexMap mapJ(NJ, p.flags), mapM(NM, p.flags);
+    const IndexMap mapJ(NJ, modulo), mapM(NM, modulo);
     for (int R = lane; R < NT; R += 32) {
         const bool isJ = R <= NJ;
         const int n = isJ ? R : R - NJ - 1;
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     }
     for (int f = lane; f < F; f += 32) {
         sts_f64(aFmoney + 8u * f, p.st.f_money[eF + f]);
-        sts_u16(aPermf + 2u * f, do_firms ? (uint32_t)perm_firm_at(p, eF + f) : (uint32_t)f);
+        sts_u16(aPermf + 2u * f, do_firms ? (uint32_t)(compact ? (int)p.cz.perm_firm[eF + f] : p.ac.perm_firm[eF + f]) : (uint32_t)f);
         sts_u32(aFnh + 4u * f, 0u);
         sts_u32(aFok + 4u * f, 0u);
         sts_u8(aFcnt + f, 0u);
@@ -272,13 +282,12 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     if (do_firms) {
         // the firms' own requests: byte i of firm f = goods offer number or kNone (empty book: no requests at all,
         // decisionNetHandler.cpp:398-403)
-        const bool modulo = (p.flags & FASTACE_IDX_MODULO) != 0;
         for (int f = lane; f < F; f += 32) {
             const uint32_t none4 = (uint32_t)kNone * 0x01010101u;
             uint32_t w[kMaxStack / 4];
 #pragma unroll
             for (int q = 0; q < kMaxStack / 4; q++) w[q] = none4;
-            if (NM > 0 && p.compact) {
+            if (NM > 0 && compact) {
                 // agent-major bytes: the aligned words that cover the firm's S request bytes, four slots at a time
                 const uint8_t* lst = p.cz.f_good_idx + (eF + f) * (size_t)S;
                 const uint32_t take = p.cz.f_good_take[eF + f] & ((1u << S) - 1u);
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             }
             sts_v4(aFatt + 16u * f, make_uint4(w[0], w[1], w[2], w[3]));
         }
-        if (NM > 0 && !p.compact) {
+        if (NM > 0 && !compact) {
             // int32 encoding ([E][S][F]): one (firm, slot) pair per lane and pass
             __syncwarp();
             for (int k = lane; k < F * S; k += 32) {
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     const size_t row0 = (size_t)e * S * P;
     // the visiting order is read one window ahead: the load of the next window's person number is in flight during this
     // window's rounds, and its money / request lines are asked for (L1 prefetch) before the window's firm-money fold
-    int pid_next = (do_persons && lane < P) ? (p.compact ? (int)p.cz.perm_person[eP + lane] : p.ac.perm_person[eP + lane]) : 0;
+    int pid_next = (do_persons && lane < P) ? (compact ? (int)p.cz.perm_person[eP + lane] : p.ac.perm_person[eP + lane]) : 0;
     for (int base = 0; do_persons && base < P; base += 32) {
         // ---- (1) rows: death ordinals and initial rooms of the window
         bool lj = false, lm = false, rk = false;
@@ -384,11 +393,11 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             // both books are sold out: no person from here on can trade
             if (lane == 0) FASTACE_STAT(kStatDeadExits, 1);
             for (int r = base + lane; r < P; r += 32) {
-                const int pid = p.compact ? (int)p.cz.perm_person[eP + r] : p.ac.perm_person[eP + r];
+                const int pid = compact ? (int)p.cz.perm_person[eP + r] : p.ac.perm_person[eP + r];
                 mp.scr_pnh[eP + pid] = 0;
 #pragma unroll
                 for (int g = 0; g < G; g++) mp.scr_pnb[((size_t)e * G + g) * P + pid] = 0;
-                write_person_ok(p, e, pid, 0u);
+                if (person_flags) write_person_ok(p, e, pid, 0u);
             }
             break;
         }
@@ -397,14 +406,13 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         const int r = base + lane;
         const bool active = r < P;
         const int pid = pid_next;
-        if (r + 32 < P) pid_next = p.compact ? (int)p.cz.perm_person[eP + r + 32] : p.ac.perm_person[eP + r + 32];
+        if (r + 32 < P) pid_next = compact ? (int)p.cz.perm_person[eP + r + 32] : p.ac.perm_person[eP + r + 32];
         const double money0 = active ? p.st.p_money[eP + pid] : 0.0;
         // keep: the slots that are worth evaluating — requested, on an existing offer that still has lots (a request on a
         // sold-out offer fails without any effect: firm.cpp:64, agent.cpp:124); jobs in bits 0..15, goods in 16..31
         uint32_t keep = 0;
         {
-            const bool modulo = (p.flags & FASTACE_IDX_MODULO) != 0;
-#pragma unroll
+    #pragma unroll
             for (int ph = 0; ph < 2; ph++) {
                 const bool live = ph == 0 ? liveJ : liveM;
                 if (!live || !active) continue;                        // a sold-out book is not evaluated at all
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                 const uint32_t recs = ph == 0 ? aRec : aRecM;
                 const IndexMap& map = ph == 0 ? mapJ : mapM;
                 uint32_t kp = 0;
-                if (p.compact) {
+                if (compact) {
                     // agent-major bytes: the aligned words that cover [pid*S, pid*S + S), shifted into place
                     const uint8_t* lst = (ph == 0 ? p.cz.p_job_idx : p.cz.p_good_idx) + (eP + pid) * (size_t)S;
                     const uint32_t take = (ph == 0 ? p.cz.p_job_take : p.cz.p_good_take)[eP + pid] & ((1u << S) - 1u);
@@ -768,7 +776,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             if (active) {
 #pragma unroll
                 for (int g = 0; g < G; g++) mp.scr_pnb[((size_t)e * G + g) * P + pid] = (uint8_t)nb[g];
-                write_person_ok(p, e, pid, okm);
+                if (person_flags) write_person_ok(p, e, pid, okm);
             }
         }
         for (int R = lane; R < NT; R += 32) {
@@ -793,7 +801,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         }
         if (r + 32 < P) {
             prefetch_l1(p.st.p_money + eP + pid_next);
-            if (p.compact) {
+            if (compact) {
                 prefetch_l1(p.cz.p_job_idx + (eP + pid_next) * (size_t)S);
                 prefetch_l1(p.cz.p_good_idx + (eP + pid_next) * (size_t)S);
             }

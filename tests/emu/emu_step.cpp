@@ -31,7 +31,11 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
     mp.ticket_base = queue_launches * (uint32_t)sp.E;
     mp.done_tag = (queue_launches % 255u) + 1u;
     if (!ph_c) {
-        emu::launch(match_kernel<G>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+        // as launch_step does: the specialised kernel when the call is what it was compiled for
+        const bool special = sp.compact && !sp.out.p_job_ok && !sp.out.p_good_ok;
+        if (!special) emu::launch(match_kernel<G, kModeGeneric>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+        else if (sp.flags & FASTACE_IDX_MODULO) emu::launch(match_kernel<G, kModeCompact | kModeModulo>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+        else emu::launch(match_kernel<G, kModeCompact>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
     }
     UpdateParams up;
     up.sp = sp; up.scr_pnh = pnh.data(); up.scr_pnb = pnb.data();

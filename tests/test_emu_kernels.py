@@ -22,7 +22,9 @@ def emu():
     k.close()
 
 
-def _episode(emu, oracle, dims, steps, seed, preset, flags=_abi.IDX_MODULO, compact=False, tweak=None):
+def _episode(emu, oracle, dims, steps, seed, preset, flags=_abi.IDX_MODULO, compact=False, tweak=None, drop_out=()):
+    """drop_out: outputs the emulated kernels are not asked for (compact encoding without the persons' success flags =
+    the call the specialised match_kernel<G, kModeCompact...> is compiled for)"""
     E, P, F, G, S = dims
     state = scenario.custom_initial_state(dims, seed)[0] if G == 2 else scenario.generic_initial_state(_abi.make_dims(*dims), seed)
     ost, est = H.copy_state(state), H.copy_state(state)
@@ -34,6 +36,8 @@ def _episode(emu, oracle, dims, steps, seed, preset, flags=_abi.IDX_MODULO, comp
             tweak(t, act)
         before = H.copy_state(ost)
         oout, eout = _abi.alloc_host("out", dims), _abi.alloc_host("out", dims)
+        for k in drop_out:
+            del eout[k]
         oracle.step(dims, ost, act, oout, flags=flags, time_before=t)
         if compact:
             cz = _abi.compact_actions_for_counts(act, before["j_count"], before["m_count"], bool(flags & _abi.IDX_MODULO))
@@ -74,6 +78,23 @@ def test_compact_encoding(emu, oracle, modulo):
                 act[k][...] = rng.integers(-1, hi, act[k].shape, dtype=np.int32)
     _episode(emu, oracle, dims, 10, 77, scenario.BENCH_PRESET, flags=_abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE,
              compact=True, tweak=tweak)
+
+
+@pytest.mark.parametrize("modulo", [True, False])
+def test_specialised_compact_kernels(emu, oracle, modulo):
+    """compact encoding, persons' success flags not requested: launch_step (and the emulator harness) pick
+    match_kernel<G, kModeCompact [| kModeModulo]> — the same source with the other encodings compiled out"""
+    rng = np.random.default_rng(8)
+
+    def tweak(t, act):                       # absolute indices: in range, with a few out-of-range ones
+        if not modulo:
+            for k in ("p_job_idx", "p_good_idx", "f_good_idx"):
+                act[k][...] = rng.integers(-1, 14, act[k].shape, dtype=np.int32)
+    st = _episode(emu, oracle, (5, 100, 10, 2, 10), 24, 31, scenario.BENCH_PRESET, tweak=tweak,
+                  flags=_abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE, compact=True, drop_out=("p_job_ok", "p_good_ok"))
+    assert st["sales_windows"] > 0 and st["rescans"] > 0
+    _episode(emu, oracle, (3, 64, 40, 3, 16), 8, 9, dict(take_prob=0.7, prod_scale=0.8, wage_scale=3.0, price_scale=0.3, labor_mu=1.5),
+             flags=_abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE, compact=True, tweak=tweak, drop_out=("p_job_ok", "p_good_ok"))
 
 
 def test_goods_rich_market_firms_buy(emu, oracle):
@@ -134,6 +155,8 @@ def test_firm_money_near_tie(emu, oracle):
     for t, act in enumerate(acts):
         before = H.copy_state(ost)
         oout, eout = _abi.alloc_host("out", dims), _abi.alloc_host("out", dims)
+        for k in drop_out:
+            del eout[k]
         oracle.step(dims, ost, act, oout, flags=_abi.IDX_ABSOLUTE, time_before=t)
         emu.step(dims, est, act, eout, flags=_abi.IDX_ABSOLUTE, time_before=t)
         H.compare_outputs(eout, oout, dims, before)

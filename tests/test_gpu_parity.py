@@ -377,3 +377,36 @@ def test_completion_queue_equals_whole_grid_wait(native_lib, monkeypatch):
         assert np.array_equal(sa[k], sb[k], equal_nan=True), k
     for k in oa:
         assert np.array_equal(oa[k].view(np.uint8), ob[k].view(np.uint8)), k
+
+
+@pytest.mark.parametrize("modulo", [True, False])
+def test_specialised_compact_kernels_match(oracle, modulo):
+    """compact encoding on the device path with only the mandatory outputs: launch_step picks
+    match_kernel<G, kModeCompact [| kModeModulo]> (the other encodings compiled out); states against the oracle"""
+    from fastace_b200.env import BatchedEconomy
+    dims = (37, 100, 10, 2, 10)
+    E, P, F, G, S = dims
+    state = scenario.custom_initial_state(dims, 177)[0]
+    env = BatchedEconomy(dims)
+    env.set_state(state)
+    ost = H.copy_state(state)
+    orders = scenario.OrderStream(dims, 178)
+    flags = _abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE
+    rng = np.random.default_rng(6)
+    for t in range(30):
+        act = scenario.synthetic_actions(dims, seed=179, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
+        if not modulo:
+            for k, hi in (("p_job_idx", F + 2), ("p_good_idx", F * G + 2), ("f_good_idx", F * G + 2)):
+                act[k] = rng.integers(-1, hi, act[k].shape, dtype=np.int32)
+        cz = _abi.compact_actions_for_counts(act, ost["j_count"], ost["m_count"], modulo)
+        oout = _abi.alloc_host("out", dims)
+        oracle.step(dims, ost, act, oout, flags=flags, time_before=t)
+        dout = env.alloc_outputs()                                   # p_reward and f_profit only
+        env.time_step(env.pack_device("compact", env.alloc_compact_actions(cz)), dout, flags=flags)
+        got = env.get_state()
+        H.compare_states(got, ost, dims)
+        for k in ("p_money", "f_money", "p_labor", "f_last_money"):
+            assert np.array_equal(got[k], ost[k], equal_nan=True), (k, t)
+        assert np.allclose(dout["p_reward"].cpu().numpy(), oout["p_reward"], rtol=1e-5, equal_nan=True)
+        assert np.allclose(dout["f_profit"].cpu().numpy(), oout["f_profit"], rtol=1e-5, atol=1e-9, equal_nan=True)
+    env.close()
