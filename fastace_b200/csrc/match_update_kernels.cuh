@@ -19,8 +19,11 @@ namespace fastace {
 
 // ---- UtilMaxer::consume_goods (utilMaxer.cpp:88-92) + choose_goods_to_consume
 //      (neuralPersonDecisionMaker.cpp:93-111) + UtilMaxer::u (utilMaxer.cpp:54-62)
-template <int G>
+// CES: both function families are the reference's default CES — the other families' code (accurate pow chains of
+// Cobb-Douglas / Stone-Geary, theta loads) is compiled out of the specialised kernel
+template <int G, bool CES>
 __device__ __forceinline__ void update_person(const StepParams& p, const uint8_t* scr_pnh, const uint8_t* scr_pnb, int e, int pid) {
+    const int util_kind = CES ? (int)FASTACE_FN_CES : p.util_kind;
     const int P = p.P;
     const size_t t = (size_t)e * P + pid;
     const double labor = kLaborPerOffer * (double)scr_pnh[t];       // exact: 0, 0.5 or 1.0
@@ -55,9 +58,9 @@ __device__ __forceinline__ void update_person(const StepParams& p, const uint8_t
 #pragma unroll
     for (int i = 0; i <= G; i++) {
         share[i] = p.st.p_util_share[((size_t)e * (G + 1) + i) * P + pid];
-        theta[i] = (p.util_kind == FASTACE_FN_STONE_GEARY) ? p.st.p_util_theta[((size_t)e * (G + 1) + i) * P + pid] : 0.0;
+        theta[i] = (util_kind == FASTACE_FN_STONE_GEARY) ? p.st.p_util_theta[((size_t)e * (G + 1) + i) * P + pid] : 0.0;
     }
-    p.out.p_reward[t] = eval_function<G + 1, true>(p.util_kind, p.st.p_util_tfp[t], share, theta, p.st.p_util_rho[t], x);
+    p.out.p_reward[t] = eval_function<G + 1, true>(util_kind, p.st.p_util_tfp[t], share, theta, p.st.p_util_rho[t], x);
     p.st.p_labor[t] = labor;
 #pragma unroll
     for (int g = 0; g < G; g++) p.st.p_inv[((size_t)e * G + g) * P + pid] = inv[g];
@@ -65,8 +68,9 @@ __device__ __forceinline__ void update_person(const StepParams& p, const uint8_t
 
 // ---- firms: produce (profitMaxer.cpp:68-72), sell_goods / search_for_laborers decode
 //      (neuralFirmDecisionMaker.cpp:111-180), new books in market order (economy.cpp:52-59, 125-126); one warp
-template <int G>
+template <int G, bool CES>
 __device__ __forceinline__ void update_firms(const StepParams& p, int e, int lane) {
+    const int prod_kind = CES ? (int)FASTACE_FN_CES : p.prod_kind;
     const int F = p.F;
     const int cap = F * G;
     const size_t eF = (size_t)e * F, eCap = (size_t)e * cap;
@@ -98,9 +102,9 @@ __device__ __forceinline__ void update_firms(const StepParams& p, int e, int lan
             for (int i = 0; i <= G; i++) {
                 const size_t k = (((size_t)e * G + g) * (G + 1) + i) * F + f;
                 share[i] = p.st.f_prod_share[k];
-                theta[i] = (p.prod_kind == FASTACE_FN_STONE_GEARY) ? p.st.f_prod_theta[k] : 0.0;
+                theta[i] = (prod_kind == FASTACE_FN_STONE_GEARY) ? p.st.f_prod_theta[k] : 0.0;
             }
-            const double outg = eval_function<G + 1, false>(p.prod_kind, p.st.f_prod_tfp[ag], share, theta, p.st.f_prod_rho[ag], in);
+            const double outg = eval_function<G + 1, false>(prod_kind, p.st.f_prod_tfp[ag], share, theta, p.st.f_prod_rho[ag], in);
             newinv = invg + (outg - xg);                                    // profitMaxer.cpp:71
             // decisionNetHandler.cpp:591 amounts = proportion * inventory; neuralFirmDecisionMaker.cpp:129
             const double amount = (double)p.ac.f_offer_amt[ag] * newinv;
@@ -171,7 +175,7 @@ constexpr int kUpdateThreads = 128;
 constexpr unsigned kQueuePollNs = 128;
 constexpr uint32_t kQueuePollCap = 1u << 23;     // x 128 ns: about a second, then kDevErrQueue
 
-template <int G>
+template <int G, bool CES = false>
 __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateParams up) {
     const StepParams& p = up.sp;
     const int P = p.P, F = p.F;
@@ -224,8 +228,8 @@ __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateP
             firms_here = true;
         }
     }
-    if (firms_here) update_firms<G>(p, e, lane);
-    for (; pid < pid_end; pid += pid_step) update_person<G>(p, up.scr_pnh, up.scr_pnb, e, pid);
+    if (firms_here) update_firms<G, CES>(p, e, lane);
+    for (; pid < pid_end; pid += pid_step) update_person<G, CES>(p, up.scr_pnh, up.scr_pnb, e, pid);
     // queue mode: the block of the last economy to finish keeps this grid open until match_kernel has completed as a
     // grid, so that whatever follows in the stream is ordered after both kernels
     if (up.done_list && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) grid_dependency_wait();

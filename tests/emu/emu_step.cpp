@@ -37,6 +37,7 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
         else if (sp.flags & FASTACE_IDX_MODULO) emu::launch(match_kernel<G, kModeCompact | kModeModulo>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
         else emu::launch(match_kernel<G, kModeCompact>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
     }
+    const bool ces = sp.util_kind == FASTACE_FN_CES && sp.prod_kind == FASTACE_FN_CES;   // as launch_step does
     UpdateParams up;
     up.sp = sp; up.scr_pnh = pnh.data(); up.scr_pnb = pnb.data();
     up.done_list = mp.done_list; up.done_tag = mp.done_tag; up.dev_err = err;
@@ -44,7 +45,8 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
         const int qgroups = (sp.E + kQueueGroup - 1) / kQueueGroup;
         up.group_person_blocks = (kQueueGroup * sp.P + kUpdateThreads - 1) / kUpdateThreads;
         const int qblocks = qgroups * (kQueueGroup / (kUpdateThreads / 32) + up.group_person_blocks);
-        emu::launch(update_kernel<G>, (unsigned)qblocks, (unsigned)kUpdateThreads, 0, up);
+        if (ces) emu::launch(update_kernel<G, true>, (unsigned)qblocks, (unsigned)kUpdateThreads, 0, up);
+        else emu::launch(update_kernel<G, false>, (unsigned)qblocks, (unsigned)kUpdateThreads, 0, up);
         queue_launches += 1;
         return;
     }
@@ -52,7 +54,8 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
     const int person_blocks = only_f ? 0 : (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
     up.firm_blocks = only_p ? 0 : (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
     if (person_blocks + up.firm_blocks > 0)
-        emu::launch(update_kernel<G>, (unsigned)(person_blocks + up.firm_blocks), (unsigned)kUpdateThreads, 0, up);
+        if (ces) emu::launch(update_kernel<G, true>, (unsigned)(person_blocks + up.firm_blocks), (unsigned)kUpdateThreads, 0, up);
+        else emu::launch(update_kernel<G, false>, (unsigned)(person_blocks + up.firm_blocks), (unsigned)kUpdateThreads, 0, up);
 }
 
 struct EmuEnv {
