@@ -804,7 +804,8 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[0], stream));
         if (!ph_c) {   // a consume-only call has no matching to do
             // the specialised kernel when the call is what it was compiled for (match_kernel.cuh: MODE)
-            const bool special = dcz != nullptr && !dout->p_job_ok && !dout->p_good_ok;
+            const bool special = dcz != nullptr && !only_p && !only_f && !dout->p_job_ok && !dout->p_good_ok && !dout->f_good_ok &&
+                                 !dout->old_j_left && !dout->old_j_taken && !dout->old_m_left && !dout->old_m_taken;
             const match_fn fn = special ? ks.match_compact[(flags & FASTACE_IDX_MODULO) ? 1 : 0] : ks.match;
             FASTACE_CUDA_CHECK(launch_dependent((const void*)fn, dim3((unsigned)sp.E), dim3(32), env->match_smem_bytes, stream, &mp));
             FASTACE_CUDA_CHECK(cudaGetLastError());

@@ -194,7 +194,8 @@ static_assert(kMaxStack == 16, "request lists are staged as four words");
 // the hot path (a quarter of the generic kernel's instructions belong to paths a given launch never takes, and the
 // instruction fetch stall is the one issue stall that is not inherent to the algorithm):
 //   kModeGeneric  everything decided at run time (any encoding, any output set)
-//   kModeCompact  compact encoding, per-person success flags not requested; bit kModeModulo: FASTACE_IDX_MODULO
+//   kModeCompact  compact encoding (full steps only), none of the optional outputs requested; bit kModeModulo:
+//                 FASTACE_IDX_MODULO
 constexpr int kModeGeneric = 0, kModeCompact = 1, kModeModulo = 2;
 
 template <int G, int MODE = kModeGeneric>
@@ -224,8 +225,11 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     const size_t eP = (size_t)e * P, eF = (size_t)e * F, eCap = (size_t)e * cap;
     // a step may be taken in two calls (FASTACE_STEP_PERSONS, then FASTACE_STEP_FIRMS): the state in HBM between
     // them is the economy as it stands when the last person has acted and no firm has (economy.cpp:118-123)
-    const bool do_persons = !(p.flags & FASTACE_STEP_FIRMS);
-    const bool do_firms = !(p.flags & (FASTACE_STEP_PERSONS | FASTACE_STEP_PERSONS_TRADE));
+    // (the compact encoding is only accepted for full steps; the specialised kernel is launched only when none of the
+    // optional outputs is requested)
+    const bool do_persons = (MODE & kModeCompact) ? true : !(p.flags & FASTACE_STEP_FIRMS);
+    const bool do_firms = (MODE & kModeCompact) ? true : !(p.flags & (FASTACE_STEP_PERSONS | FASTACE_STEP_PERSONS_TRADE));
+    const bool optional_out = !(MODE & kModeCompact);
     if (do_persons && compact) {
         // the economy's person-side inputs are five contiguous slabs: ask L2 for them now, use them window by window
         if (lane == 0) prefetch_slab_l2(p.cz.p_job_idx + (size_t)e * P * S, (size_t)P * S);
@@ -857,8 +861,8 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
 
     // ---- person phase: counters to HBM
     // job counters are final after the person phase
-    if (do_persons && p.out.old_j_left) for (int n = lane; n < NJ; n += 32) p.out.old_j_left[eF + n] = lds_u32<kRecLeft>(aRec + (uint32_t)n * kRecBytes);
-    if (do_persons && p.out.old_j_taken) for (int n = lane; n < NJ; n += 32) p.out.old_j_taken[eF + n] = lds_u32<kRecTaken>(aRec + (uint32_t)n * kRecBytes);
+    if (do_persons && optional_out && p.out.old_j_left) for (int n = lane; n < NJ; n += 32) p.out.old_j_left[eF + n] = lds_u32<kRecLeft>(aRec + (uint32_t)n * kRecBytes);
+    if (do_persons && optional_out && p.out.old_j_taken) for (int n = lane; n < NJ; n += 32) p.out.old_j_taken[eF + n] = lds_u32<kRecTaken>(aRec + (uint32_t)n * kRecBytes);
     if (!do_firms) {
         // persons-only call: the books' counters go back to HBM for the firms call (a full step never needs them
         // there: update_kernel replaces the books)
@@ -983,8 +987,8 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     // the queue ticket is taken now: its round trip overlaps the write-back (only the flag store must follow the fence)
     uint32_t ticket = 0;
     if (mp.done_list && lane == 0) ticket = ticket_add(mp.done_count);
-    if (do_firms && p.out.old_m_left) for (int n = lane; n < NM; n += 32) p.out.old_m_left[eCap + n] = lds_u32<kRecD>(aRecM + (uint32_t)n * kRecBytes);
-    if (do_firms && p.out.old_m_taken) for (int n = lane; n < NM; n += 32) p.out.old_m_taken[eCap + n] = lds_u32<kRecTaken>(aRecM + (uint32_t)n * kRecBytes);
+    if (do_firms && optional_out && p.out.old_m_left) for (int n = lane; n < NM; n += 32) p.out.old_m_left[eCap + n] = lds_u32<kRecD>(aRecM + (uint32_t)n * kRecBytes);
+    if (do_firms && optional_out && p.out.old_m_taken) for (int n = lane; n < NM; n += 32) p.out.old_m_taken[eCap + n] = lds_u32<kRecTaken>(aRecM + (uint32_t)n * kRecBytes);
     for (int f = lane; f < F; f += 32) {
         p.st.f_money[eF + f] = lds_f64(aFmoney + 8u * f);
         if (do_firms) p.out.f_profit[eF + f] = lds_f64(aFlast + 8u * f);
@@ -994,7 +998,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         const uint32_t nhf = lds_u32(aFnh + 4u * f);
         for (uint32_t k = 0; k < nhf; k++) labor += kLaborPerOffer;  // firm.cpp:109, one add per hire
         p.st.f_labor[eF + f] = labor;
-        if (do_firms && p.out.f_good_ok) {
+        if (do_firms && optional_out && p.out.f_good_ok) {
             const uint32_t ok = lds_u32(aFok + 4u * f);
             for (int i = 0; i < S; i++) p.out.f_good_ok[((size_t)e * S + i) * F + f] = (ok >> i) & 1u;
         }

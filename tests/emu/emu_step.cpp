@@ -32,7 +32,8 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
     mp.done_tag = (queue_launches % 255u) + 1u;
     if (!ph_c) {
         // as launch_step does: the specialised kernel when the call is what it was compiled for
-        const bool special = sp.compact && !sp.out.p_job_ok && !sp.out.p_good_ok;
+        const bool special = sp.compact && !only_p && !only_f && !sp.out.p_job_ok && !sp.out.p_good_ok && !sp.out.f_good_ok &&
+                             !sp.out.old_j_left && !sp.out.old_j_taken && !sp.out.old_m_left && !sp.out.old_m_taken;
         if (!special) emu::launch(match_kernel<G, kModeGeneric>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
         else if (sp.flags & FASTACE_IDX_MODULO) emu::launch(match_kernel<G, kModeCompact | kModeModulo>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
         else emu::launch(match_kernel<G, kModeCompact>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);

@@ -12,6 +12,7 @@ from fastace_b200 import _abi, scenario
 from tests import helpers as H
 
 EXACT_FLOAT = ("p_money", "f_money", "p_labor", "f_last_money")
+OPTIONAL_OUT = ("p_job_ok", "p_good_ok", "f_good_ok", "old_j_left", "old_j_taken", "old_m_left", "old_m_taken")
 
 
 @pytest.fixture(scope="module")
@@ -91,10 +92,10 @@ def test_specialised_compact_kernels(emu, oracle, modulo):
             for k in ("p_job_idx", "p_good_idx", "f_good_idx"):
                 act[k][...] = rng.integers(-1, 14, act[k].shape, dtype=np.int32)
     st = _episode(emu, oracle, (5, 100, 10, 2, 10), 24, 31, scenario.BENCH_PRESET, tweak=tweak,
-                  flags=_abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE, compact=True, drop_out=("p_job_ok", "p_good_ok"))
+                  flags=_abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE, compact=True, drop_out=OPTIONAL_OUT)
     assert st["sales_windows"] > 0 and st["rescans"] > 0
     _episode(emu, oracle, (3, 64, 40, 3, 16), 8, 9, dict(take_prob=0.7, prod_scale=0.8, wage_scale=3.0, price_scale=0.3, labor_mu=1.5),
-             flags=_abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE, compact=True, tweak=tweak, drop_out=("p_job_ok", "p_good_ok"))
+             flags=_abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE, compact=True, tweak=tweak, drop_out=OPTIONAL_OUT)
 
 
 def test_goods_rich_market_firms_buy(emu, oracle):
