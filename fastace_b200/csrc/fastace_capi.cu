@@ -278,11 +278,12 @@ typedef void (*match_fn)(const MatchParams);
 typedef void (*update_fn)(const UpdateParams);
 // match: the generic kernel; match_compact[modulo]: specialised for the compact encoding without per-person success flags
 // update_ces: both function families CES (the reference's default)
-struct KernelSet { serial_fn serial; match_fn match; update_fn update; match_fn match_compact[2]; update_fn update_ces; };
+struct KernelSet { serial_fn serial; match_fn match; update_fn update; match_fn match_compact[4]; update_fn update_ces; };
 template <int G>
 static KernelSet kernels_of() {
     return {step_kernel<G>, match_kernel<G, kModeGeneric>, update_kernel<G>,
-            {match_kernel<G, kModeCompact>, match_kernel<G, kModeCompact | kModeModulo>}, update_kernel<G, true>};
+            {match_kernel<G, kModeCompact>, match_kernel<G, kModeCompact | kModeModulo>,
+             match_kernel<G, kModeCompact | kModeSmall>, match_kernel<G, kModeCompact | kModeModulo | kModeSmall>}, update_kernel<G, true>};
 }
 static KernelSet kernels_for_goods(int G) {
     switch (G) {
@@ -294,7 +295,7 @@ static KernelSet kernels_for_goods(int G) {
         case 6: return kernels_of<6>();
         case 7: return kernels_of<7>();
         case 8: return kernels_of<8>();
-        default: return {nullptr, nullptr, nullptr, {nullptr, nullptr}, nullptr};
+        default: return {nullptr, nullptr, nullptr, {nullptr, nullptr, nullptr, nullptr}, nullptr};
     }
 }
 
@@ -348,7 +349,7 @@ int fastace_env_create(const fastace_dims_t* dims, int device, fastace_env_t** o
             FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.serial, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         if (ML.total > 48 * 1024) {
             FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
-            for (int m = 0; m < 2; m++)
+            for (int m = 0; m < 4; m++)
                 FASTACE_CUDA_CHECK(cudaFuncSetAttribute((const void*)ks.match_compact[m], cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total));
         }
     }
@@ -806,7 +807,8 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
             // the specialised kernel when the call is what it was compiled for (match_kernel.cuh: MODE)
             const bool special = dcz != nullptr && !only_p && !only_f && !dout->p_job_ok && !dout->p_good_ok && !dout->f_good_ok &&
                                  !dout->old_j_left && !dout->old_j_taken && !dout->old_m_left && !dout->old_m_taken;
-            const match_fn fn = special ? ks.match_compact[(flags & FASTACE_IDX_MODULO) ? 1 : 0] : ks.match;
+            const bool small = sp.F * (env->dims.num_goods + 1) + 2 <= 32;    // both books and the firms in one pass
+            const match_fn fn = special ? ks.match_compact[((flags & FASTACE_IDX_MODULO) ? 1 : 0) + (small ? 2 : 0)] : ks.match;
             FASTACE_CUDA_CHECK(launch_dependent((const void*)fn, dim3((unsigned)sp.E), dim3(32), env->match_smem_bytes, stream, &mp));
             FASTACE_CUDA_CHECK(cudaGetLastError());
             env->launches += 1;

@@ -195,8 +195,8 @@ static_assert(kMaxStack == 16, "request lists are staged as four words");
 // instruction fetch stall is the one issue stall that is not inherent to the algorithm):
 //   kModeGeneric  everything decided at run time (any encoding, any output set)
 //   kModeCompact  compact encoding (full steps only), none of the optional outputs requested; bit kModeModulo:
-//                 FASTACE_IDX_MODULO
-constexpr int kModeGeneric = 0, kModeCompact = 1, kModeModulo = 2;
+//                 FASTACE_IDX_MODULO; bit kModeSmall: all rows of both books and all firms fit one pass of the warp
+constexpr int kModeGeneric = 0, kModeCompact = 1, kModeModulo = 2, kModeSmall = 4;
 
 template <int G, int MODE = kModeGeneric>
 __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     const bool do_persons = (MODE & kModeCompact) ? true : !(p.flags & FASTACE_STEP_FIRMS);
     const bool do_firms = (MODE & kModeCompact) ? true : !(p.flags & (FASTACE_STEP_PERSONS | FASTACE_STEP_PERSONS_TRADE));
     const bool optional_out = !(MODE & kModeCompact);
+    // kModeSmall: every book and the firm list fit one pass of the warp (F * (G + 1) + 2 <= 32): the strided loops over
+    // rows / offers / firms run exactly once
+    constexpr int kMorePasses = (MODE & kModeSmall) ? 0 : 1;
     if (do_persons && compact) {
         // the economy's person-side inputs are five contiguous slabs: ask L2 for them now, use them window by window
         if (lane == 0) prefetch_slab_l2(p.cz.p_job_idx + (size_t)e * P * S, (size_t)P * S);
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
 
     // ------------------------------ stage: books and firms ---------------------------------
     const IndexMap mapJ(NJ, modulo), mapM(NM, modulo);
-    for (int R = lane; R < NT; R += 32) {
+    for (int R = lane, more = 1; R < NT && more; R += 32, more = kMorePasses) {
         const bool isJ = R <= NJ;
         const int n = isJ ? R : R - NJ - 1;
         const bool real = isJ ? n < NJ : n < NM;
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         sts_u32<kRecTaken>(rec, taken);
         sts_u32<kRecMeta>(rec, meta);
     }
-    for (int f = lane; f < F; f += 32) {
+    for (int f = lane, more = 1; f < F && more; f += 32, more = kMorePasses) {
         sts_f64(aFmoney + 8u * f, p.st.f_money[eF + f]);
         sts_u16(aPermf + 2u * f, do_firms ? (uint32_t)(compact ? (int)p.cz.perm_firm[eF + f] : p.ac.perm_firm[eF + f]) : (uint32_t)f);
         sts_u32(aFnh + 4u * f, 0u);
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     if (do_firms) {
         // the firms' own requests: byte i of firm f = goods offer number or kNone (empty book: no requests at all,
         // decisionNetHandler.cpp:398-403)
-        for (int f = lane; f < F; f += 32) {
+        for (int f = lane, more = 1; f < F && more; f += 32, more = kMorePasses) {
             const uint32_t none4 = (uint32_t)kNone * 0x01010101u;
             uint32_t w[kMaxStack / 4];
 #pragma unroll
@@ -322,8 +325,8 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         }
     }
     __syncwarp();
-    for (int n = lane; n < NJ; n += 32) sts_u8(aFjob + (lds_u32<kRecMeta>(aRec + (uint32_t)n * kRecBytes) & 0xFFu), (uint32_t)n);
-    for (int n = lane; n < NM; n += 32) {
+    for (int n = lane, more = 1; n < NJ && more; n += 32, more = kMorePasses) sts_u8(aFjob + (lds_u32<kRecMeta>(aRec + (uint32_t)n * kRecBytes) & 0xFFu), (uint32_t)n);
+    for (int n = lane, more = 1; n < NM && more; n += 32, more = kMorePasses) {
         // a firm's entries are contiguous in market order (it posts all its goods in one turn)
         const uint32_t rec = aRecM + (uint32_t)n * kRecBytes;
         const uint32_t owner = lds_u32<kRecMeta>(rec) & 0xFFu;
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         if (!(lds_f64<kRecValue>(rec) >= 0.0)) sts_u8(aFrisk + owner, 1u);   // a sale would not raise the seller's money
     }
     __syncwarp();
-    for (int n = lane; n < NM; n += 32) {
+    for (int n = lane, more = 1; n < NM && more; n += 32, more = kMorePasses) {
         const uint32_t rec = aRecM + (uint32_t)n * kRecBytes;
         const uint32_t owner = lds_u32<kRecMeta>(rec) & 0xFFu;
         const int next = (n + 1 < NM) ? (int)(lds_u32<kRecMeta + kRecBytes>(rec) & 0xFFu) : -1;
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     for (int base = 0; do_persons && base < P; base += 32) {
         // ---- (1) rows: death ordinals and initial rooms of the window
         bool lj = false, lm = false, rk = false;
-        for (int R = lane; R < NT; R += 32) {
+        for (int R = lane, more = 1; R < NT && more; R += 32, more = kMorePasses) {
             const uint32_t rec = aRec + (uint32_t)R * kRecBytes;
             const uint32_t left = lds_u32<kRecLeft>(rec);
             const uint32_t meta = lds_u32<kRecMeta>(rec);
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
             // while the applications to the row and everybody's purchases do)
             const bool goods_moved = risk_possible && __any_sync(0xffffffffu, (okm >> 16) != last_goods);
             last_goods = okm >> 16;
-            for (int cb = 0; cb < NT; cb += 32) {
+            for (int cb = 0, more = 1; cb < NT && more; cb += 32, more = kMorePasses) {
                 const int R = cb + lane;
                 bool needs = false;
                 if (R < NT) {
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                 if (lane == 0) mp.dev_err[kDevErrRounds] = 1u;
                 break;
             }
-            for (int R = lane; R < NT; R += 32) {
+            for (int R = lane, more = 1; R < NT && more; R += 32, more = kMorePasses) {
                 const uint32_t mat = aMat + (uint32_t)R * kMatBytes;
                 sts_v4<kMatCnt>(mat, make_uint4(0u, 0u, 0u, 0u));
                 sts_v4<kMatCnt + 16>(mat, make_uint4(0u, 0u, 0u, 0u));
@@ -758,7 +761,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         const unsigned buyers = __ballot_sync(0xffffffffu, (okm >> 16) != 0u);
         if (buyers != 0u) {
             // aFlive (free until the firm phase) collects, per firm, the lanes that bought from it in this window
-            for (int f = lane; f < F; f += 32) sts_u32(aFlive + 4u * f, 0u);
+            for (int f = lane, more = 1; f < F && more; f += 32, more = kMorePasses) sts_u32(aFlive + 4u * f, 0u);
             __syncwarp();
         }
         {
@@ -783,7 +786,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                 if (person_flags) write_person_ok(p, e, pid, okm);
             }
         }
-        for (int R = lane; R < NT; R += 32) {
+        for (int R = lane, more = 1; R < NT && more; R += 32, more = kMorePasses) {
             const uint32_t rec = aRec + (uint32_t)R * kRecBytes;
             const uint32_t tot = lds_u32<kRecTot>(rec);
             const uint32_t n = min(tot, lds_u32<kRecD>(rec));
@@ -812,7 +815,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         }
         __syncwarp();
         // ---- firm money of the window, event by event in the visiting order
-        for (int fb = 0; fb < F; fb += 32) {
+        for (int fb = 0, more = 1; fb < F && more; fb += 32, more = kMorePasses) {
             const int f = fb + lane;
             const uint32_t j = f < F ? lds_u8(aFjob + f) : (uint32_t)kNone;
             const bool has = j != (uint32_t)kNone;
@@ -861,16 +864,16 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
 
     // ---- person phase: counters to HBM
     // job counters are final after the person phase
-    if (do_persons && optional_out && p.out.old_j_left) for (int n = lane; n < NJ; n += 32) p.out.old_j_left[eF + n] = lds_u32<kRecLeft>(aRec + (uint32_t)n * kRecBytes);
-    if (do_persons && optional_out && p.out.old_j_taken) for (int n = lane; n < NJ; n += 32) p.out.old_j_taken[eF + n] = lds_u32<kRecTaken>(aRec + (uint32_t)n * kRecBytes);
+    if (do_persons && optional_out && p.out.old_j_left) for (int n = lane, more = 1; n < NJ && more; n += 32, more = kMorePasses) p.out.old_j_left[eF + n] = lds_u32<kRecLeft>(aRec + (uint32_t)n * kRecBytes);
+    if (do_persons && optional_out && p.out.old_j_taken) for (int n = lane, more = 1; n < NJ && more; n += 32, more = kMorePasses) p.out.old_j_taken[eF + n] = lds_u32<kRecTaken>(aRec + (uint32_t)n * kRecBytes);
     if (!do_firms) {
         // persons-only call: the books' counters go back to HBM for the firms call (a full step never needs them
         // there: update_kernel replaces the books)
-        for (int n = lane; n < NM; n += 32) {
+        for (int n = lane, more = 1; n < NM && more; n += 32, more = kMorePasses) {
             p.st.m_left[eCap + n] = lds_u32<kRecLeft>(aRecM + (uint32_t)n * kRecBytes);
             p.st.m_taken[eCap + n] = lds_u32<kRecTaken>(aRecM + (uint32_t)n * kRecBytes);
         }
-        for (int n = lane; n < NJ; n += 32) {
+        for (int n = lane, more = 1; n < NJ && more; n += 32, more = kMorePasses) {
             p.st.j_left[eF + n] = lds_u32<kRecLeft>(aRec + (uint32_t)n * kRecBytes);
             p.st.j_taken[eF + n] = lds_u32<kRecTaken>(aRec + (uint32_t)n * kRecBytes);
         }
@@ -880,7 +883,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     if (do_firms) {
         // requests on entries that are sold out can only fail (amountLeft never grows within a step)
         bool lv = false;
-        for (int f = lane; f < F; f += 32) {
+        for (int f = lane, more = 1; f < F && more; f += 32, more = kMorePasses) {
             const uint4 slots = lds_v4(aFatt + 16u * f);
             const uint32_t w[4] = {slots.x, slots.y, slots.z, slots.w};
             uint32_t live = 0;
@@ -976,7 +979,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         };
         if (!anylive) {
             // no purchase can happen: the firms' turns do not interact
-            for (int f = lane; f < F; f += 32) firm_turn(f, false);
+            for (int f = lane, more = 1; f < F && more; f += 32, more = kMorePasses) firm_turn(f, false);
         } else if (lane == 0) {
             FASTACE_STAT(kStatFirmSerial, 1);
             for (int r = 0; r < F; r++) firm_turn((int)lds_u16(aPermf + 2u * r), true);   // visiting order (economy.cpp:121-123)
@@ -987,9 +990,9 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     // the queue ticket is taken now: its round trip overlaps the write-back (only the flag store must follow the fence)
     uint32_t ticket = 0;
     if (mp.done_list && lane == 0) ticket = ticket_add(mp.done_count);
-    if (do_firms && optional_out && p.out.old_m_left) for (int n = lane; n < NM; n += 32) p.out.old_m_left[eCap + n] = lds_u32<kRecD>(aRecM + (uint32_t)n * kRecBytes);
-    if (do_firms && optional_out && p.out.old_m_taken) for (int n = lane; n < NM; n += 32) p.out.old_m_taken[eCap + n] = lds_u32<kRecTaken>(aRecM + (uint32_t)n * kRecBytes);
-    for (int f = lane; f < F; f += 32) {
+    if (do_firms && optional_out && p.out.old_m_left) for (int n = lane, more = 1; n < NM && more; n += 32, more = kMorePasses) p.out.old_m_left[eCap + n] = lds_u32<kRecD>(aRecM + (uint32_t)n * kRecBytes);
+    if (do_firms && optional_out && p.out.old_m_taken) for (int n = lane, more = 1; n < NM && more; n += 32, more = kMorePasses) p.out.old_m_taken[eCap + n] = lds_u32<kRecTaken>(aRecM + (uint32_t)n * kRecBytes);
+    for (int f = lane, more = 1; f < F && more; f += 32, more = kMorePasses) {
         p.st.f_money[eF + f] = lds_f64(aFmoney + 8u * f);
         if (do_firms) p.out.f_profit[eF + f] = lds_f64(aFlast + 8u * f);
 #pragma unroll

@@ -35,8 +35,13 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
         const bool special = sp.compact && !only_p && !only_f && !sp.out.p_job_ok && !sp.out.p_good_ok && !sp.out.f_good_ok &&
                              !sp.out.old_j_left && !sp.out.old_j_taken && !sp.out.old_m_left && !sp.out.old_m_taken;
         if (!special) emu::launch(match_kernel<G, kModeGeneric>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
-        else if (sp.flags & FASTACE_IDX_MODULO) emu::launch(match_kernel<G, kModeCompact | kModeModulo>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
-        else emu::launch(match_kernel<G, kModeCompact>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+        else {
+            const bool small = sp.F * (G + 1) + 2 <= 32, mod = (sp.flags & FASTACE_IDX_MODULO) != 0;
+            if (small && mod) emu::launch(match_kernel<G, kModeCompact | kModeModulo | kModeSmall>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+            else if (small) emu::launch(match_kernel<G, kModeCompact | kModeSmall>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+            else if (mod) emu::launch(match_kernel<G, kModeCompact | kModeModulo>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+            else emu::launch(match_kernel<G, kModeCompact>, (unsigned)sp.E, 32u, (size_t)mp.lay.total, mp);
+        }
     }
     const bool ces = sp.util_kind == FASTACE_FN_CES && sp.prod_kind == FASTACE_FN_CES;   // as launch_step does
     UpdateParams up;
