@@ -156,8 +156,6 @@ def test_firm_money_near_tie(emu, oracle):
     for t, act in enumerate(acts):
         before = H.copy_state(ost)
         oout, eout = _abi.alloc_host("out", dims), _abi.alloc_host("out", dims)
-        for k in drop_out:
-            del eout[k]
         oracle.step(dims, ost, act, oout, flags=_abi.IDX_ABSOLUTE, time_before=t)
         emu.step(dims, est, act, eout, flags=_abi.IDX_ABSOLUTE, time_before=t)
         H.compare_outputs(eout, oout, dims, before)
@@ -167,6 +165,22 @@ def test_firm_money_near_tie(emu, oracle):
     hired = np.array([h for (_, _, _, h) in ties])
     assert np.array_equal(oout["p_job_ok"][:, 0, 2].astype(bool), hired)     # the reference decides as constructed ...
     assert hired.any() and (~hired).any()                                   # ... both ways
+
+
+def test_firm_money_near_tie_specialised_kernel(emu, oracle):
+    """the same last-bit ties through the compact encoding without optional outputs (specialised match_kernel)"""
+    from tests import near_tie
+    dims, state, acts, ties = near_tie.build(24, seed=3)
+    ost, est = H.copy_state(state), H.copy_state(state)
+    for t, act in enumerate(acts):
+        oout = _abi.alloc_host("out", dims)
+        eout = {k: v for k, v in _abi.alloc_host("out", dims).items() if k not in OPTIONAL_OUT}
+        cz = _abi.compact_actions_for_counts(act, ost["j_count"], ost["m_count"], False)
+        oracle.step(dims, ost, act, oout, flags=_abi.IDX_ABSOLUTE, time_before=t)
+        emu.step(dims, est, None, eout, flags=_abi.IDX_ABSOLUTE, time_before=t, compact=cz)
+        H.compare_states(est, ost, dims)
+        for k in EXACT_FLOAT:
+            assert np.array_equal(est[k], ost[k], equal_nan=True), (k, t)
 
 
 def test_device_shuffle_equals_libstdcxx(emu):
