@@ -92,6 +92,7 @@ struct MatchLayout {
     int off_permf;                                        // u16
     int off_fatt;                                         // u8 [F][16]
     int off_fjob, off_ffirst, off_fcnt, off_frisk;        // u8 [F]
+    int off_flabor;                                       // f64 [F] laborHired at the start of the step
     int off_evlist;                                       // u8 [32][kEvPerLane]
     int off_req;                                          // u8 [32][kReqStride]
     int total;
@@ -117,6 +118,7 @@ __host__ __device__ inline MatchLayout make_match_layout(int P, int F, int G, in
     L.off_ffirst = take(F);
     L.off_fcnt = take(F);
     L.off_frisk = take(F);
+    L.off_flabor = take(8 * F);
     L.off_evlist = take(32 * kEvPerLane);
     L.off_req = take(32 * kReqStride);
     L.total = o;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
     const uint32_t aFmoney = sb + L.off_fmoney, aFinv = sb + L.off_finv, aFlast = sb + L.off_flast;
     const uint32_t aFnh = sb + L.off_fnh, aFok = sb + L.off_fok, aFlive = sb + L.off_flive, aPermf = sb + L.off_permf;
     const uint32_t aFatt = sb + L.off_fatt, aFjob = sb + L.off_fjob, aFfirst = sb + L.off_ffirst, aFcnt = sb + L.off_fcnt;
-    const uint32_t aFrisk = sb + L.off_frisk, aEv = sb + L.off_evlist;
+    const uint32_t aFrisk = sb + L.off_frisk, aEv = sb + L.off_evlist, aFlabor = sb + L.off_flabor;
     const uint32_t aReqL = keep_u32(sb + L.off_req + (uint32_t)lane * kReqStride);   // this lane's request lists
 
     const size_t eP = (size_t)e * P, eF = (size_t)e * F, eCap = (size_t)e * cap;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
 #pragma unroll
         for (int g = 0; g < G; g++) sts_f64(aFinv + 8u * (g * F + f), p.st.f_inv[((size_t)e * G + g) * F + f]);
         if (do_firms) sts_f64(aFlast + 8u * f, p.st.f_last_money[eF + f]);
-        prefetch_l1(p.st.f_labor + eF + f);          // read at the very end (laborHired += 0.5 per hire)
+        sts_f64(aFlabor + 8u * f, p.st.f_labor[eF + f]);   // used at the very end (laborHired += 0.5 per hire)
     }
     if (do_firms) {
         // the firms' own requests: byte i of firm f = goods offer number or kNone (empty book: no requests at all,
@@ -997,7 +999,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
         if (do_firms) p.out.f_profit[eF + f] = lds_f64(aFlast + 8u * f);
 #pragma unroll
         for (int g = 0; g < G; g++) p.st.f_inv[((size_t)e * G + g) * F + f] = lds_f64(aFinv + 8u * (g * F + f));
-        double labor = p.st.f_labor[eF + f];
+        double labor = lds_f64(aFlabor + 8u * f);
         const uint32_t nhf = lds_u32(aFnh + 4u * f);
         for (uint32_t k = 0; k < nhf; k++) labor += kLaborPerOffer;  // firm.cpp:109, one add per hire
         p.st.f_labor[eF + f] = labor;
