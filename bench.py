@@ -603,7 +603,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "peak_source": peak_src,
-                         "kernel": "fastace::match_kernel<2> (dominant: %.0f%% of the step's device time)" % (100 * match_s / max(match_s + update_s, 1e-12)),
+                         "kernel": "fastace::match_kernel<2, kModeCompact | kModeSmall> (dominant: %.0f%% of the step's device time)" % (100 * match_s / max(match_s + update_s, 1e-12)),
                          "algorithmic_bytes_per_launch": BYTES_MATCH_PER_ECON_STEP * E,
                          "launch_ms": match_s * 1e3,
                          "step": {"kernels": {"match_kernel_ms": match_s * 1e3, "update_kernel_ms": update_s * 1e3},
