@@ -50,6 +50,7 @@ struct Block {
 
 inline Block* g_block = nullptr;            // the emulator is single-threaded
 inline unsigned char* g_smem = nullptr;
+inline size_t g_smem_size = 0;
 inline Block*& cur_block() { return g_block; }
 
 inline uint3 tid() { Block* b = cur_block(); return b->threads[b->cur].tid; }
@@ -104,6 +105,7 @@ inline void trampoline() {
 inline void run_block(Block& b) {
     cur_block() = &b;
     g_smem = b.smem.data();
+    g_smem_size = b.smem.size();
     const int n = (int)b.threads.size();
     for (int t = 0; t < n; t++) {
         Thread& T = b.threads[t];
@@ -198,8 +200,15 @@ template <typename T> inline T from_bits(uint64_t u) { T v; std::memcpy(&v, &u, 
 namespace fastace {
 inline uint32_t smem_addr(const void* p) { return (uint32_t)(static_cast<const unsigned char*>(p) - emu::dyn_smem()); }
 inline uint32_t keep_u32(uint32_t x) { return x; }
-template <typename T> inline T emu_ld(uint32_t a) { T v; std::memcpy(&v, emu::dyn_smem() + a, sizeof(T)); return v; }
-template <typename T> inline void emu_st(uint32_t a, T v) { std::memcpy(emu::dyn_smem() + a, &v, sizeof(T)); }
+// every explicit shared-memory access is bounds- and alignment-checked against the block's dynamic allocation
+inline void emu_check(uint32_t a, size_t n) {
+    if ((size_t)a + n > emu::g_smem_size || (a % n) != 0) {
+        std::fprintf(stderr, "emulator: shared-memory access of %zu bytes at offset %u outside the %zu-byte allocation (or misaligned)\n", n, a, emu::g_smem_size);
+        std::abort();
+    }
+}
+template <typename T> inline T emu_ld(uint32_t a) { emu_check(a, sizeof(T)); T v; std::memcpy(&v, emu::dyn_smem() + a, sizeof(T)); return v; }
+template <typename T> inline void emu_st(uint32_t a, T v) { emu_check(a, sizeof(T)); std::memcpy(emu::dyn_smem() + a, &v, sizeof(T)); }
 template <int OFF = 0> inline uint32_t lds_u8(uint32_t a) { return emu_ld<uint8_t>(a + OFF); }
 template <int OFF = 0> inline uint32_t lds_u16(uint32_t a) { return emu_ld<uint16_t>(a + OFF); }
 template <int OFF = 0> inline uint32_t lds_u32(uint32_t a) { return emu_ld<uint32_t>(a + OFF); }
