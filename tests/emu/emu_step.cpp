@@ -153,6 +153,9 @@ void fastace_emu_expand_packed(int agents, int S, int bits, int bytes, const uin
 // pow_reward of common.cuh (the reward path's short-polynomial pow), for the accuracy test
 double fastace_emu_pow_reward(double x, double y) { return pow_reward(x, y); }
 
+// 0 ascending, 1 descending, 2 scrambled: the order in which the emulated blocks of every launch run
+void fastace_emu_block_order(int order) { emu::block_order() = order; }
+
 // event counters of the kernels since the last call (common.cuh: kStat*); resets them
 void fastace_emu_stats(unsigned long long* out) {
     for (int i = 0; i < kStatCount; i++) { out[i] = emu::stats()[i]; emu::stats()[i] = 0; }

@@ -50,6 +50,10 @@ class EmuKernels:
         self.lib.fastace_emu_stats(buf)
         return dict(zip(self.STAT_NAMES, list(buf)))
 
+    def block_order(self, order):
+        """0 ascending (default), 1 descending, 2 scrambled: the order in which the blocks of every launch run"""
+        self.lib.fastace_emu_block_order(int(order))
+
     def close(self):
         for h in self.handles.values():
             self.lib.fastace_emu_destroy(h)

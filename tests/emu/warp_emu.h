@@ -158,10 +158,21 @@ inline void run_block(Block& b) {
     cur_block() = nullptr;
 }
 
+// order in which the blocks of a launch run: 0 ascending, 1 descending, 2 a fixed scramble (tests of code whose result
+// must not depend on which block finishes first, e.g. the completion queue between match_kernel and update_kernel)
+inline int& block_order() { static int o = 0; return o; }
+
 // kernel<<<grid, block, smem>>>(params): blocks run one after the other
 template <typename Kernel, typename Params>
 void launch(Kernel kernel, unsigned grid, unsigned block, size_t smem_bytes, const Params& params) {
-    for (unsigned bx = 0; bx < grid; bx++) {
+    for (unsigned k = 0; k < grid; k++) {
+        unsigned bx = k;
+        if (block_order() == 1) bx = grid - 1 - k;
+        else if (block_order() == 2) {          // k -> k * odd + offset (mod the next power of two), skipping values >= grid
+            unsigned n = 1; while (n < grid) n <<= 1;
+            static thread_local unsigned cursor; if (k == 0) cursor = 0;
+            do { bx = (cursor * 0x9E3779B1u + 12345u) & (n - 1); cursor++; } while (bx >= grid);
+        }
         Block b;
         b.threads.resize(block);
         b.warps.resize((block + 31) / 32);

@@ -98,6 +98,19 @@ def test_specialised_compact_kernels(emu, oracle, modulo):
              flags=_abi.IDX_MODULO if modulo else _abi.IDX_ABSOLUTE, compact=True, tweak=tweak, drop_out=OPTIONAL_OUT)
 
 
+@pytest.mark.parametrize("order", [1, 2])
+def test_completion_queue_in_any_finishing_order(emu, oracle, order):
+    """match_kernel's warps hand their economies to update_kernel through the completion queue in the order they
+    finish: with the emulated blocks run in descending / scrambled order the queue is a permutation of the economies,
+    and the step must not notice (also with an economy count that is not a multiple of the queue's group size)"""
+    emu.block_order(order)
+    try:
+        _episode(emu, oracle, (37, 40, 6, 2, 10), 6, 21, scenario.BENCH_PRESET)
+        _episode(emu, oracle, (5, 100, 10, 2, 10), 4, 22, scenario.BENCH_PRESET, compact=True, drop_out=OPTIONAL_OUT)
+    finally:
+        emu.block_order(0)
+
+
 def test_goods_rich_market_firms_buy(emu, oracle):
     """plenty of goods and cheap prices: persons and FIRMS buy all episode long (serial firm walk, sale folds)"""
     st = _episode(emu, oracle, (3, 60, 8, 2, 10), 12, 31, dict(take_prob=0.6, prod_scale=0.2, wage_scale=0.3, price_scale=0.05, labor_mu=1.5))
