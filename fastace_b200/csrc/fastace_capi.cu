@@ -278,12 +278,14 @@ typedef void (*match_fn)(const MatchParams);
 typedef void (*update_fn)(const UpdateParams);
 // match: the generic kernel; match_compact[modulo]: specialised for the compact encoding without per-person success flags
 // update_ces: both function families CES (the reference's default)
-struct KernelSet { serial_fn serial; match_fn match; update_fn update; match_fn match_compact[4]; update_fn update_ces; };
+// update[ces][queue]: whole-grid / completion-queue assignment, generic / CES-only function families
+struct KernelSet { serial_fn serial; match_fn match; update_fn update[2][2]; match_fn match_compact[4]; };
 template <int G>
 static KernelSet kernels_of() {
-    return {step_kernel<G>, match_kernel<G, kModeGeneric>, update_kernel<G>,
+    return {step_kernel<G>, match_kernel<G, kModeGeneric>,
+            {{update_kernel<G, false, false>, update_kernel<G, false, true>}, {update_kernel<G, true, false>, update_kernel<G, true, true>}},
             {match_kernel<G, kModeCompact>, match_kernel<G, kModeCompact | kModeModulo>,
-             match_kernel<G, kModeCompact | kModeSmall>, match_kernel<G, kModeCompact | kModeModulo | kModeSmall>}, update_kernel<G, true>};
+             match_kernel<G, kModeCompact | kModeSmall>, match_kernel<G, kModeCompact | kModeModulo | kModeSmall>}};
 }
 static KernelSet kernels_for_goods(int G) {
     switch (G) {
@@ -295,7 +297,7 @@ static KernelSet kernels_for_goods(int G) {
         case 6: return kernels_of<6>();
         case 7: return kernels_of<7>();
         case 8: return kernels_of<8>();
-        default: return {nullptr, nullptr, nullptr, {nullptr, nullptr, nullptr, nullptr}, nullptr};
+        default: return {nullptr, nullptr, {{nullptr, nullptr}, {nullptr, nullptr}}, {nullptr, nullptr, nullptr, nullptr}};
     }
 }
 
@@ -814,7 +816,7 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
             env->launches += 1;
         }
         if (prof) FASTACE_CUDA_CHECK(cudaEventRecord(env->ev[1], stream));
-        const update_fn ufn = (sp.util_kind == FASTACE_FN_CES && sp.prod_kind == FASTACE_FN_CES) ? ks.update_ces : ks.update;
+        const int ces = (sp.util_kind == FASTACE_FN_CES && sp.prod_kind == FASTACE_FN_CES) ? 1 : 0;
         UpdateParams up;
         up.sp = sp; up.scr_pnh = env->scr_pnh; up.scr_pnb = env->scr_pnb;
         up.done_list = mp.done_list; up.done_tag = mp.done_tag; up.dev_err = env->err_dev;
@@ -826,11 +828,11 @@ static int launch_step(fastace_env_t* env, const fastace_actions_t* dact, const 
             const int qgroups = (sp.E + kQueueGroup - 1) / kQueueGroup;
             up.group_person_blocks = (kQueueGroup * sp.P + kUpdateThreads - 1) / kUpdateThreads;
             const int qblocks = qgroups * (kQueueGroup / (kUpdateThreads / 32) + up.group_person_blocks);
-            FASTACE_CUDA_CHECK(launch_dependent((const void*)ufn, dim3((unsigned)qblocks), dim3(kUpdateThreads), 0, stream, &up));
+            FASTACE_CUDA_CHECK(launch_dependent((const void*)ks.update[ces][1], dim3((unsigned)qblocks), dim3(kUpdateThreads), 0, stream, &up));
             env->launches += 1;
             env->queue_launches += 1;
         } else if (person_blocks + up.firm_blocks > 0) {
-            FASTACE_CUDA_CHECK(launch_dependent((const void*)ufn, dim3((unsigned)(person_blocks + up.firm_blocks)), dim3(kUpdateThreads), 0, stream, &up));
+            FASTACE_CUDA_CHECK(launch_dependent((const void*)ks.update[ces][0], dim3((unsigned)(person_blocks + up.firm_blocks)), dim3(kUpdateThreads), 0, stream, &up));
             env->launches += 1;
         }
         FASTACE_CUDA_CHECK(cudaGetLastError());

@@ -21,13 +21,14 @@ namespace fastace {
 //      (neuralPersonDecisionMaker.cpp:93-111) + UtilMaxer::u (utilMaxer.cpp:54-62)
 // CES: both function families are the reference's default CES — the other families' code (accurate pow chains of
 // Cobb-Douglas / Stone-Geary, theta loads) is compiled out of the specialised kernel
-template <int G, bool CES>
+// FULL: the call is a full step (no phase flag): the trade-only / consume-only variants are compiled out
+template <int G, bool CES, bool FULL>
 __device__ __forceinline__ void update_person(const StepParams& p, const uint8_t* scr_pnh, const uint8_t* scr_pnb, int e, int pid) {
     const int util_kind = CES ? (int)FASTACE_FN_CES : p.util_kind;
     const int P = p.P;
     const size_t t = (size_t)e * P + pid;
     const double labor = kLaborPerOffer * (double)scr_pnh[t];       // exact: 0, 0.5 or 1.0
-    if (p.flags & FASTACE_STEP_PERSONS_TRADE) {
+    if (!FULL && (p.flags & FASTACE_STEP_PERSONS_TRADE)) {
         // trade-only call: purchases and labour go into the state, consumption follows in its own call
         // (it touches nobody but the person, so deferring it changes nothing: utilMaxer.cpp:88-92)
 #pragma unroll
@@ -41,7 +42,7 @@ __device__ __forceinline__ void update_person(const StepParams& p, const uint8_t
         p.st.p_labor[t] = labor;
         return;
     }
-    const bool applied = (p.flags & FASTACE_STEP_PERSONS_CONSUME) != 0;   // purchases are already in p_inv
+    const bool applied = !FULL && (p.flags & FASTACE_STEP_PERSONS_CONSUME) != 0;   // purchases are already in p_inv
     double x[G + 1], inv[G];
     x[0] = 1 - labor;
 #pragma unroll
@@ -175,14 +176,15 @@ constexpr int kUpdateThreads = 128;
 constexpr unsigned kQueuePollNs = 128;
 constexpr uint32_t kQueuePollCap = 1u << 23;     // x 128 ns: about a second, then kDevErrQueue
 
-template <int G, bool CES = false>
+// QUEUE: the instance of the full step (completion queue, no phase flags); otherwise the whole-grid assignment
+template <int G, bool CES = false, bool QUEUE = false>
 __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateParams up) {
     const StepParams& p = up.sp;
     const int P = p.P, F = p.F;
     const int lane = threadIdx.x & 31;
     int e = 0, pid = 0, pid_end = 0, pid_step = 1;
     bool firms_here = false;
-    if (up.done_list) {
+    if (QUEUE) {
         grid_launch_dependents();
         // blocks come in groups that consume kQueueGroup consecutive queue slots: first the firm blocks (a warp per
         // slot), then the person blocks (a thread per person of those slots), so that blocks are dispatched in the
@@ -229,10 +231,10 @@ __global__ void __launch_bounds__(kUpdateThreads, 8) update_kernel(const UpdateP
         }
     }
     if (firms_here) update_firms<G, CES>(p, e, lane);
-    for (; pid < pid_end; pid += pid_step) update_person<G, CES>(p, up.scr_pnh, up.scr_pnb, e, pid);
+    for (; pid < pid_end; pid += pid_step) update_person<G, CES, QUEUE>(p, up.scr_pnh, up.scr_pnb, e, pid);
     // queue mode: the block of the last economy to finish keeps this grid open until match_kernel has completed as a
     // grid, so that whatever follows in the stream is ordered after both kernels
-    if (up.done_list && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) grid_dependency_wait();
+    if (QUEUE && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) grid_dependency_wait();
 }
 
 }  // namespace fastace

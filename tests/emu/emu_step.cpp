@@ -51,8 +51,8 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
         const int qgroups = (sp.E + kQueueGroup - 1) / kQueueGroup;
         up.group_person_blocks = (kQueueGroup * sp.P + kUpdateThreads - 1) / kUpdateThreads;
         const int qblocks = qgroups * (kQueueGroup / (kUpdateThreads / 32) + up.group_person_blocks);
-        if (ces) emu::launch(update_kernel<G, true>, (unsigned)qblocks, (unsigned)kUpdateThreads, 0, up);
-        else emu::launch(update_kernel<G, false>, (unsigned)qblocks, (unsigned)kUpdateThreads, 0, up);
+        if (ces) emu::launch(update_kernel<G, true, true>, (unsigned)qblocks, (unsigned)kUpdateThreads, 0, up);
+        else emu::launch(update_kernel<G, false, true>, (unsigned)qblocks, (unsigned)kUpdateThreads, 0, up);
         queue_launches += 1;
         return;
     }
@@ -60,8 +60,8 @@ static void run_step(const StepParams& sp, std::vector<uint8_t>& pnh, std::vecto
     const int person_blocks = only_f ? 0 : (int)((persons + kUpdateThreads - 1) / kUpdateThreads);
     up.firm_blocks = only_p ? 0 : (sp.E + kUpdateThreads / 32 - 1) / (kUpdateThreads / 32);
     if (person_blocks + up.firm_blocks > 0)
-        if (ces) emu::launch(update_kernel<G, true>, (unsigned)(person_blocks + up.firm_blocks), (unsigned)kUpdateThreads, 0, up);
-        else emu::launch(update_kernel<G, false>, (unsigned)(person_blocks + up.firm_blocks), (unsigned)kUpdateThreads, 0, up);
+        if (ces) emu::launch(update_kernel<G, true, false>, (unsigned)(person_blocks + up.firm_blocks), (unsigned)kUpdateThreads, 0, up);
+        else emu::launch(update_kernel<G, false, false>, (unsigned)(person_blocks + up.firm_blocks), (unsigned)kUpdateThreads, 0, up);
 }
 
 struct EmuEnv {
