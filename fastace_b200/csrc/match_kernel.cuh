@@ -488,13 +488,14 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                     const bool go = rem != 0u && nh < 2;
                     if (!__any_sync(0xffffffffu, go)) break;
                     if (go) {
-                        const int i = __ffs((int)rem) - 1;
-                        rem &= rem - 1;
+                        const uint32_t low = rem & (0u - rem);               // the lane's next kept slot, as a mask
+                        rem ^= low;
+                        const int i = 31 - __clz((int)low);
                         const uint32_t cell = aCellJ + lds_u8(aReqL + (uint32_t)i) * kMatBytes;
                         const uint32_t c = lds_u8<kMatCnt>(cell);
                         const uint32_t rm = lds_u8<kMatRoom>(cell);
                         sts_u8<kMatCnt>(cell, c + 1u);
-                        if (c < rm) { nh++; okm |= 1u << i; }
+                        if (c < rm) { nh++; okm |= low; }
                     }
                 }
                 // the wages of the (at most two) jobs, in request order (person.cpp:49)
@@ -509,8 +510,9 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                     const bool go = rem != 0u;
                     if (!__any_sync(0xffffffffu, go)) break;
                     if (go) {
-                        const int i = __ffs((int)rem) - 1;
-                        rem &= rem - 1;
+                        const uint32_t low = rem & (0u - rem);
+                        rem ^= low;
+                        const int i = 31 - __clz((int)low);
                         const uint32_t n = lds_u8<kReqGoods>(aReqL + (uint32_t)i);
                         const double price = lds_f64<kRecValue>(aRecM + n * kRecBytes);
                         if (money >= price) {
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(32, 28) match_kernel(const MatchParams mp) {
                             const uint32_t c = lds_u8<kMatCnt>(cell);
                             const uint32_t rm = lds_u8<kMatRoom>(cell);
                             sts_u8<kMatCnt>(cell, c + 1u);
-                            if (c < rm) { money -= price; okm |= 1u << (16 + i); }   // agent.cpp:108
+                            if (c < rm) { money -= price; okm |= low << 16; }   // agent.cpp:108
                         }
                     }
                 }
