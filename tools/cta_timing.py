@@ -11,6 +11,7 @@ from fastace_b200.env import BatchedEconomy
 
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+COMPACT = len(sys.argv) > 3 and sys.argv[3] == "compact"
 DIMS = (E, 100, 10, 2, 10)
 import os
 lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(lib.__file__)), "libfastace_b200_timing.so")
@@ -21,7 +22,12 @@ orders = scenario.OrderStream(DIMS, 7)
 import torch
 for t in range(STEPS):
     act = scenario.synthetic_actions(DIMS, seed=99, step=t, perms=orders.next(), **scenario.BENCH_PRESET)
-    dact = env.alloc_actions(act)
+    if COMPACT:      # the call the specialised match_kernel<G, kModeCompact ...> is compiled for
+        st = env.get_state()
+        cz = _abi.compact_actions_for_counts(act, st["j_count"], st["m_count"], True)
+        dact = env.pack_device("compact", env.alloc_compact_actions(cz))
+    else:
+        dact = env.alloc_actions(act)
     dout = env.alloc_outputs()
     torch.cuda.synchronize()
     env.time_step(dact, dout, flags=_abi.IDX_MODULO)
